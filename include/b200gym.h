@@ -1,0 +1,278 @@
+/* libb200gym.so -- C ABI of the B200-native legged_gym_custom hot path.
+ *
+ * The reference (JustinMLu/legged_gym_custom) has no FFI layer: its boundary is Python
+ * duck-typing between OnPolicyRunner, the env object and the PPO object.
+ * This header is the boundary a maintainer binds UNDER those Python classes (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless it says "host";
+ *  - the caller (PyTorch on the Python side) owns all memory; the library allocates nothing
+ *    but small per-handle scratch, and never frees caller memory;
+ *  - every call is asynchronous on the passed cudaStream_t (as void*), never synchronises,
+ *    never reads back to the host;
+ *  - return 0 = OK, <0 = argument error, >0 = cudaError_t; text via b200_last_error();
+ *  - one host thread per process/GPU; not re-entrant per handle.
+ */
+#ifndef B200GYM_H_
+#define B200GYM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#define B200_NUM_DOF 12          /* go2 family: {FL,FR,RL,RR}_{hip,thigh,calf}_joint */
+#define B200_NUM_BODIES 19       /* base, Head_upper, Head_lower, 4 x {hip,thigh,calf,foot} */
+#define B200_NUM_FEET 4          /* FL, FR, RL, RR (reference order, go2.py:295-298) */
+#define B200_MAX_SCAN_AXIS 24
+#define B200_MAX_PROPRIO 64
+
+/* Reward terms: every `_reward_*` of legged_robot.py:1036-1148 and go2.py:578-831, in the
+ * ALPHABETICAL order in which the reference sums them (class_to_dict iterates dir(),
+ * helpers.py:45; legged_robot.py:735-750).  A zero scale disables a term, exactly like
+ * _prepare_reward_function pops it.  `termination` is applied after the positive clip
+ * (legged_robot.py:234-237) and is kept last. */
+enum B200RewardTerm {
+  B200_REW_action_rate = 0,
+  B200_REW_ang_vel_xy,
+  B200_REW_base_height,
+  B200_REW_calf_collision,
+  B200_REW_calf_pos,
+  B200_REW_calf_symmetry,
+  B200_REW_collision,
+  B200_REW_delta_torques,
+  B200_REW_dof_acc,
+  B200_REW_dof_error,
+  B200_REW_dof_pos_limits,
+  B200_REW_dof_vel,
+  B200_REW_dof_vel_limits,
+  B200_REW_feet_air_time,
+  B200_REW_feet_contact_forces,
+  B200_REW_heading_alignment,
+  B200_REW_hip_pos,
+  B200_REW_jump_zone_forward_vel,
+  B200_REW_jump_zone_upward_vel,
+  B200_REW_lin_vel_z,
+  B200_REW_min_height,
+  B200_REW_orientation,
+  B200_REW_phase_contact_match,
+  B200_REW_phase_foot_lifting,
+  B200_REW_reverse_penalty,
+  B200_REW_stand_still,
+  B200_REW_stumble_calves,
+  B200_REW_stumble_feet,
+  B200_REW_thigh_pos,
+  B200_REW_thigh_symmetry,
+  B200_REW_torque_limits,
+  B200_REW_torques,
+  B200_REW_tracking_ang_vel,
+  B200_REW_tracking_lin_vel,
+  B200_REW_tracking_pitch,
+  B200_REW_tracking_roll,
+  B200_REW_zero_cmd_dof_error,
+  B200_REW_termination,
+  B200_NUM_REWARD_TERMS
+};
+
+/* Constants the reference bakes at init from its cfg classes (legged_robot.py:933-955 _parse_cfg,
+ * :625-727 _init_buffers, :730-754 _prepare_reward_function; go2.py:110-129).  All "python
+ * scalars" are stored as the fp32 value torch would broadcast them to. */
+typedef struct B200EnvParams {
+  int32_t abi_version;
+  int32_t num_envs;
+  int32_t num_proprio;        /* 52 */
+  int32_t history_len;        /* 10 */
+  int32_t num_priv;           /* 29 = mass/com 4 + friction 1 + kp 12 + kd 12 */
+  int32_t num_est;            /* 3 */
+  int32_t num_scan;           /* scan_nx * scan_ny = 132 */
+  int32_t control_type;       /* 0 'P', 1 'V', 2 'T' (legged_robot.py:456-471) */
+  int32_t randomize_kp_kd;
+  int32_t decimation;
+  float sim_dt;
+  float dt;                   /* decimation * sim_dt */
+  float action_scale;
+  float clip_actions;
+  float clip_obs;
+  float p_gains[B200_NUM_DOF];
+  float d_gains[B200_NUM_DOF];
+  float default_dof_pos[B200_NUM_DOF];
+  float torque_limits[B200_NUM_DOF];
+  float dof_pos_lo[B200_NUM_DOF];      /* soft limits (legged_robot.py:354-357) */
+  float dof_pos_hi[B200_NUM_DOF];
+  float dof_vel_limits[B200_NUM_DOF];
+  /* episode / domain randomisation */
+  int32_t max_episode_length;          /* ceil(episode_length_s / dt); time-out is ep_len > this */
+  float max_episode_length_s;
+  int32_t resample_interval;           /* int(resampling_time / dt) */
+  int32_t push_robots;
+  int32_t push_interval;
+  float max_push_vel;
+  /* gait phase (go2.py:279-283) */
+  float period, fr_offset, bl_offset, fl_offset, br_offset;
+  /* commands: index 0 vx, 1 vy, 2 yaw rate, 3 heading; value = span * u + lo */
+  float cmd_lo[4];
+  float cmd_span[4];
+  int32_t heading_command;
+  float heading_error_gain;
+  int32_t zero_command;
+  float zero_command_prob;
+  /* terrain / height scan (legged_robot.py:997-1032) */
+  int32_t has_height_samples;          /* 0 for mesh_type 'plane' -> heights == 0 */
+  int32_t hs_rows, hs_cols;
+  float border_size, horizontal_scale, vertical_scale;
+  int32_t index_div_mode;              /* 0: x / h_scale (torch CPU); 1: x * fp32(1/h_scale) (torch CUDA) */
+  int32_t parkour;                     /* hole termination + jump flags (go2.py:202-204, :487-494) */
+  int32_t curriculum;
+  int32_t custom_origins;              /* heightfield/trimesh -> xy randomised on reset */
+  float promote_dist;                  /* env_length * promote_threshold */
+  float demote_threshold;
+  int32_t max_terrain_level;           /* = terrain.num_rows */
+  int32_t terrain_cols;
+  int32_t scan_nx, scan_ny;
+  float scan_x[B200_MAX_SCAN_AXIS];
+  float scan_y[B200_MAX_SCAN_AXIS];
+  /* reset */
+  float base_init_state[13];
+  float dof_reset_lo, dof_reset_span;  /* default + U(0, 0.9) (legged_robot.py:491) */
+  /* observations (go2.py:467-574) */
+  float obs_lin_vel, obs_ang_vel, obs_dof_pos, obs_dof_vel;
+  int32_t add_noise;
+  float noise_vec[B200_MAX_PROPRIO];
+  /* rewards */
+  float reward_scales[B200_NUM_REWARD_TERMS];   /* already multiplied by dt */
+  int32_t only_positive_rewards;
+  float tracking_sigma, base_height_target, max_contact_force, max_foot_height;
+  float stance_threshold;              /* 2 * percent_time_on_ground - 1 */
+  float soft_dof_vel_limit, soft_torque_limit, pitch_deg_target, roll_deg_target;
+  /* rigid-body / joint index tables */
+  int32_t feet[B200_NUM_FEET];
+  int32_t calves[B200_NUM_FEET];
+  int32_t n_penalised;
+  int32_t penalised[B200_NUM_BODIES];
+  int32_t n_termination;
+  int32_t termination[B200_NUM_BODIES];
+  int32_t hip_joints[4], thigh_joints[4], calf_joints[4];
+  int32_t _pad0;
+  uint64_t seed;                       /* Philox key (oracle/philox.py, csrc/philox.cuh) */
+} B200EnvParams;
+
+/* Device buffers of one env shard.  "PhysX" = written by the simulator each step and only
+ * READ here except for reset/push writes (exactly the in-place writes the reference pushes
+ * back with set_*_tensor_indexed).  "own" = persistent state of this library's env.
+ * Shapes use N = num_envs; all float = fp32; rows are contiguous. */
+typedef struct B200EnvBuffers {
+  /* PhysX (legged_robot.py:632-646, go2.py:136-138) */
+  float* root_states;            /* [N,13] in/out */
+  float* dof_state;              /* [N*12,2] in/out */
+  const float* contact_forces;   /* [N*19,3] */
+  const float* rigid_body_states;/* [N*19,13] */
+  /* static per-env randomisation (legged_robot.py:687-701) */
+  const float* kp_kd_multipliers;    /* [2,N,12] */
+  const float* priv_mass_params;     /* [N,4] */
+  const float* priv_friction;        /* [N,1] */
+  /* terrain */
+  const int16_t* height_samples;     /* [hs_rows,hs_cols] or NULL */
+  const float* terrain_origins;      /* [max_terrain_level,terrain_cols,3] or NULL */
+  /* own persistent state */
+  float* actions;                /* [N,12] clipped actions of this step (written by b200_pd_torques) */
+  float* torques;                /* [N,12] */
+  float* commands;               /* [N,4] */
+  int64_t* episode_length_buf;   /* [N] */
+  float* last_actions;           /* [N,12] */
+  float* last_dof_vel;           /* [N,12] */
+  float* last_root_vel;          /* [N,6] */
+  float* last_base_lin_vel;      /* [N,3] */
+  float* last_torques;           /* [N,12] */
+  float* obs_history_buf;        /* [N,history_len,num_proprio] */
+  uint8_t* last_contacts;        /* [N,4] bool */
+  float* last_contact_heights;   /* [N,4] */
+  float* feet_air_time;          /* [N,4] */
+  float* jump_flags;             /* [N,1] */
+  float* episode_sums;           /* [B200_NUM_REWARD_TERMS,N]; rows of disabled terms stay 0 */
+  int64_t* terrain_levels;       /* [N] */
+  const int64_t* terrain_types;  /* [N] */
+  float* env_origins;            /* [N,3] */
+  /* derived quantities kept for the Python attribute surface (play.py:81-92) */
+  float* base_lin_vel;           /* [N,3] */
+  float* base_ang_vel;           /* [N,3] */
+  float* projected_gravity;      /* [N,3] */
+  float* rpy;                    /* [N,3] roll, pitch, yaw */
+  float* measured_heights;       /* [N,num_scan] */
+  int64_t* height_index;         /* [N,num_scan,2] clipped (px,py); NULL = do not record (parity tests only) */
+  float* phases;                 /* [N,5] phase, fr, fl, bl, br */
+  uint8_t* foot_contacts;        /* [N,4] bool fl, fr, bl, br (filtered) */
+  /* step outputs (legged_robot.py:100) */
+  float* obs_buf;                /* [N,(history_len+1)*num_proprio] clipped */
+  float* privileged_obs_buf;     /* [N,num_priv] clipped */
+  float* critic_obs_buf;         /* [N,obs+priv+est+scan] clipped */
+  float* estimated_obs_buf;      /* [N,num_est] clipped */
+  float* scan_obs_buf;           /* [N,num_scan] (NOT clipped to clip_obs, legged_robot.py:97) */
+  float* rew_buf;                /* [N] */
+  uint8_t* reset_buf;            /* [N] bool */
+  uint8_t* time_out_buf;         /* [N] bool */
+  /* extras (go2.py:246-263): refreshed only on steps where >=1 env reset */
+  uint8_t* extras_time_outs;     /* [N] bool */
+  float* extras_episode;         /* [B200_NUM_REWARD_TERMS + 1]: rew_<term> means, then terrain_level */
+  int32_t* reset_count;          /* [1] number of envs reset this step */
+} B200EnvBuffers;
+
+typedef struct B200Env B200Env;  /* opaque handle: params in device constant storage + scratch */
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+int b200_env_params_size(void);      /* sizeof(B200EnvParams), for the binding's self-check */
+int b200_env_buffers_size(void);
+
+/* Handle lifetime. Copies `params`; `device` is the CUDA ordinal. */
+int b200_env_create(const B200EnvParams* params, int device, B200Env** out);
+int b200_env_destroy(B200Env* env);
+
+/* Replaces LeggedRobot.step's action clip (legged_robot.py:74-75) + _compute_torques
+ * (legged_robot.py:440-478).  `actions_in` [N,12] raw policy actions; when `clip_and_store`
+ * != 0 they are clipped to +-clip_actions and stored into bufs->actions (first substep of an
+ * env step), otherwise bufs->actions is used.  Writes bufs->torques. */
+int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actions_in,
+                    int clip_and_store, void* stream);
+
+/* Replaces Go2Robot.post_physics_step (go2.py:345-387) and everything it calls:
+ * update_feet_states, quaternion_to_euler, _post_physics_step_callback (command resample,
+ * heading controller, _get_heights, _push_robots), check_termination, compute_reward (all
+ * _reward_* terms), reset_idx (terrain curriculum, _reset_dofs, _reset_root_states,
+ * _resample_commands, buffer zeroing, episode extras), compute_observations, the last_*
+ * updates, and the observation clip of LeggedRobot.step (legged_robot.py:91-95).
+ * `common_step_counter` is the value AFTER this step's increment (go2.py:355). */
+int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter,
+                           void* stream);
+
+/* Replaces BaseTask.reset's reset_idx(arange(N)) (base_task.py:131-135): resets every env
+ * with the curriculum update skipped when `init_done` == 0 (legged_robot.py:551-552). */
+int b200_reset_all(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter,
+                   int init_done, void* stream);
+
+/* Standalone height scan = LeggedRobot._get_heights (legged_robot.py:997-1032) for all envs;
+ * writes bufs->measured_heights and, if non-NULL, bufs->height_index. */
+int b200_get_heights(B200Env* env, const B200EnvBuffers* bufs, void* stream);
+
+/* Replaces RolloutStorage.compute_returns (rollout_storage.py:110-124): GAE reverse scan,
+ * then advantages = (A - mean(A)) / (std_unbiased(A) + 1e-8) over all T*N.
+ * rewards/values/returns/advantages [T,N] fp32, dones [T,N] uint8, last_values [N].
+ * `scratch` >= b200_gae_scratch_bytes(T, N) bytes of device memory. */
+int64_t b200_gae_scratch_bytes(int T, int N);
+int b200_compute_returns(const float* rewards, const uint8_t* dones, const float* values,
+                         const float* last_values, float* returns, float* advantages,
+                         int T, int N, float gamma, float lam, void* scratch, void* stream);
+
+/* PPO.process_env_step's time-out bootstrap + RolloutStorage.add_transitions scalars
+ * (ppo.py:156-171, rollout_storage.py:87-105): rewards_t = rew + gamma * value * time_out;
+ * dones_t = reset.  `time_outs` may be NULL ('time_outs' not in infos). */
+int b200_store_step_scalars(const float* rew, const uint8_t* reset, const uint8_t* time_outs,
+                            const float* values, float gamma, float* rewards_t, uint8_t* dones_t,
+                            int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GYM_H_ */

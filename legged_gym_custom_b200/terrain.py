@@ -1,0 +1,72 @@
+"""Parkour height-field generation (init-time, host numpy).
+
+The height-scan kernel's input format is the reference's `height_samples`: int16
+[tot_rows, tot_cols] in units of vertical_scale, rows = world x / horizontal_scale,
+with a border of border_size metres (legged_robot.py:788-802, terrain.py:9-57).  This
+module produces that array and `terrain_origins` [num_rows, num_cols, 3] for the two
+parkour layouts the go2 tasks use -- `parkour_curriculum` (terrain.py:103-115,
+:195-246) and `parkour_selected_terrain` (terrain.py:118-131) built on `parkour_terrain`
+(terrain_utils.py:318-399) -- so tests and benchmarks on the GPU box need neither the
+reference nor a 19 MB fixture.  tests/test_terrain.py pins it against the reference's
+own `Terrain` output (sha256 in tests/golden/terrain_sha.json).
+
+The trimesh conversion for PhysX (terrain_utils.convert_heightfield_to_trimesh) is the
+simulator's input, not the hot path's, and is out of scope.
+"""
+import numpy as np
+
+
+def _course(length_px, width_px, h_scale, v_scale, start_platform_length, start_platform_height, x_positions,
+            y_positions, obstacle_lengths, obstacle_heights, half_valid_width, border_width, border_height):
+    """One obstacle course tile: rows = along-track (x), cols = across (y)."""
+    hf = np.zeros((length_px, width_px), dtype=np.int16)
+    hf[:round(start_platform_length / h_scale), :] = round(start_platform_height / v_scale)
+    mid = width_px // 2
+    half_gap = round(half_valid_width / h_scale)
+    for x, y, length, height in zip(x_positions, y_positions, obstacle_lengths, obstacle_heights):
+        cx, cy = round(x / h_scale), mid + round(y / h_scale)
+        half = round(length / h_scale) // 2
+        rows = slice(cx - half, cx + half)
+        hf[rows, :] = round(height / v_scale)
+        hf[rows, :cy - half_gap] = 0          # outside the valid corridor the obstacle is removed
+        hf[rows, cy + half_gap:] = 0
+    pad = int(border_width / h_scale)
+    hf[:, :pad] = int(border_height / v_scale)
+    hf[:, -pad:] = int(border_height / v_scale)
+    return hf
+
+
+def _curriculum_tile_kwargs(choice, difficulty, proportion0):
+    """terrain.py:195-246 make_parkour_terrain: gaps widen / hurdles rise with difficulty."""
+    if choice < proportion0:
+        n, x0, dx = 7, 5.0, 3.5
+        lengths, heights = [difficulty] * n, [-2.0] * n
+    else:
+        n, x0, dx = 14, 4.0, 1.99
+        lengths, heights = [0.35] * n, [0.05 + 0.44 * difficulty] * n
+    return dict(start_platform_length=3., start_platform_height=0., x_positions=list(np.arange(x0, x0 + n * dx, dx)),
+                y_positions=[0.0] * n, obstacle_lengths=lengths, obstacle_heights=heights, half_valid_width=5.0,
+                border_width=0.50, border_height=-2.0)
+
+
+def make_parkour_terrain(tcfg):
+    """-> (height_samples int16 [rows, cols], terrain_origins float32 [num_rows, num_cols, 3])."""
+    hs, vs = tcfg.horizontal_scale, tcfg.vertical_scale
+    width_px, length_px = int(tcfg.terrain_width / hs), int(tcfg.terrain_length / hs)
+    border = int(tcfg.border_size / hs)
+    rows = int(tcfg.num_rows * length_px) + 2 * border
+    cols = int(tcfg.num_cols * width_px) + 2 * border
+    field = np.zeros((rows, cols), dtype=np.int16)
+    origins = np.zeros((tcfg.num_rows, tcfg.num_cols, 3))
+    proportion0 = float(np.sum(tcfg.terrain_proportions[:1]))
+    for j in range(tcfg.num_cols):
+        for i in range(tcfg.num_rows):
+            if tcfg.curriculum:
+                kw = _curriculum_tile_kwargs(j / tcfg.num_cols + 0.001, (i + 1) / 10, proportion0)
+            else:
+                kw = tcfg.parkour_kwargs
+            tile = _course(length_px, width_px, hs, vs, **kw)
+            r0, c0 = border + i * length_px, border + j * width_px
+            field[r0:r0 + length_px, c0:c0 + width_px] = tile
+            origins[i, j] = [i * tcfg.terrain_length, (j + 0.5) * tcfg.terrain_width, 0.0]   # start line, centred in y
+    return field, origins.astype(np.float32)

@@ -1,0 +1,103 @@
+"""Shared replay helpers for the golden fixtures in tests/golden (made by oracle/make_golden.py)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from legged_gym_custom_b200 import configs, terrain
+from legged_gym_custom_b200.params import env_params_from_cfg, REWARD_TERMS, REWARD_INDEX, NUM_DOF, NUM_BODIES
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TASKS = ("go2_parkour", "go2_parkour_finetune", "go2")
+_terrain_cache = {}
+
+
+def load(task):
+    return np.load(os.path.join(GOLDEN_DIR, f"env_{task}.npz"), allow_pickle=False)
+
+
+def terrain_for(task):
+    """(height_samples int16 | None, terrain_origins | None), regenerated and sha-pinned."""
+    cfg = configs.TASKS[task][0]
+    if cfg.terrain.mesh_type == "plane":
+        return None, None
+    if task not in _terrain_cache:
+        hs, origins = terrain.make_parkour_terrain(cfg.terrain)
+        with open(os.path.join(GOLDEN_DIR, "terrain_sha.json")) as f:
+            sha = json.load(f)[task]
+        assert hashlib.sha256(hs.tobytes()).hexdigest() == sha["sha256"]
+        assert hashlib.sha256(origins.tobytes()).hexdigest() == sha["origins_sha256"]
+        _terrain_cache[task] = (hs, origins)
+    return _terrain_cache[task]
+
+
+def params_for(task, g, index_div_mode=0):
+    cfg = configs.TASKS[task][0]
+    hs, _ = terrain_for(task)
+    return env_params_from_cfg(cfg, num_envs=int(g["num_envs"]), seed=int(g["seed"]), index_div_mode=index_div_mode,
+                               hs_shape=None if hs is None else hs.shape)
+
+
+def statics_for(task, g):
+    hs, origins = terrain_for(task)
+    return dict(kp_kd_multipliers=g["static/kp_kd_multipliers"], privileged_mass_params=g["static/privileged_mass_params"],
+                privileged_friction_coeffs=g["static/privileged_friction_coeffs"], height_samples=hs, terrain_origins=origins)
+
+
+def init_state(g, p):
+    """golden 'init/*' -> persistent-state dict with the oracle / B200EnvBuffers names."""
+    N = p.num_envs
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(g["init/" + k]))
+    sums = torch.zeros(len(REWARD_TERMS), N)
+    ep = torch.zeros(len(REWARD_TERMS) + 1)
+    for i, name in enumerate(REWARD_TERMS):
+        if "init/episode_sums/" + name in g.files:
+            sums[i] = t("episode_sums/" + name)
+        if "init/extras/episode/rew_" + name in g.files:
+            ep[i] = float(g["init/extras/episode/rew_" + name])
+    if "init/extras/episode/terrain_level" in g.files:
+        ep[len(REWARD_TERMS)] = float(g["init/extras/episode/terrain_level"])
+    st = dict(
+        root_states=t("root_states"), dof_state=t("dof_state"), contact_forces=torch.zeros(N * NUM_BODIES, 3),
+        rigid_body_states=torch.zeros(N * NUM_BODIES, 13), actions=t("actions"), torques=t("torques"),
+        commands=t("commands"), episode_length_buf=t("episode_length_buf"), last_actions=t("last_actions"),
+        last_dof_vel=t("last_dof_vel"), last_root_vel=t("last_root_vel"), last_base_lin_vel=t("last_base_lin_vel"),
+        last_torques=t("last_torques"), obs_history_buf=t("obs_history_buf"), last_contacts=t("last_contacts").bool(),
+        last_contact_heights=t("last_contact_heights"), feet_air_time=t("feet_air_time"), jump_flags=t("jump_flags"),
+        episode_sums=sums, terrain_levels=t("terrain_levels") if "init/terrain_levels" in g.files else torch.zeros(N, dtype=torch.int64),
+        terrain_types=t("terrain_types") if "init/terrain_types" in g.files else torch.zeros(N, dtype=torch.int64),
+        env_origins=t("env_origins"), reset_buf=t("reset_buf").bool(), time_out_buf=t("time_out_buf").bool(),
+        extras_time_outs=t("extras/time_outs").bool() if "init/extras/time_outs" in g.files else torch.zeros(N, dtype=torch.bool),
+        extras_episode=ep, common_step_counter=torch.tensor(int(g["init/common_step_counter"]), dtype=torch.int64),
+    )
+    return st
+
+
+def frames_of(g, t):
+    return {k: g[f"step{t}/in/{k}"] for k in ("dof", "root", "contact", "rigid")}
+
+
+def expected(g, t):
+    """dict name -> numpy of the reference's tensors after step t, mapped to our names."""
+    pre = f"step{t}/out/"
+    e = {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+    N = int(g["num_envs"])
+    sums = np.zeros((len(REWARD_TERMS), N), dtype=np.float32)
+    ep = {}
+    for k, v in list(e.items()):
+        if k.startswith("episode_sums/"):
+            sums[REWARD_INDEX[k.split("/", 1)[1]]] = v
+        if k.startswith("extras/episode/rew_"):
+            ep[REWARD_INDEX[k[len("extras/episode/rew_"):]]] = float(v)
+        if k == "extras/episode/terrain_level":
+            ep[len(REWARD_TERMS)] = float(v)
+    e["episode_sums"] = sums
+    e["extras_episode"] = ep
+    return e
+
+
+def critic_sha(obs, priv, est, scan):
+    c = np.concatenate([obs, priv, est, scan], axis=-1).astype(np.float32)
+    return hashlib.sha256(np.ascontiguousarray(c).tobytes()).hexdigest()
