@@ -29,6 +29,9 @@ extern "C" {
 #define B200_NUM_FEET 4          /* FL, FR, RL, RR (reference order, go2.py:295-298) */
 #define B200_MAX_SCAN_AXIS 24
 #define B200_MAX_PROPRIO 64
+#define B200_MAX_SCAN 192         /* scan_nx * scan_ny upper bound (base LeggedRobot uses 17 x 11 = 187) */
+#define B200_MAX_HIST 640          /* history_len * num_proprio upper bound */
+#define B200_PROPRIO 52          /* go2 cur-obs layout (go2.py:506-515); other widths are rejected */
 
 /* Reward terms: every `_reward_*` of legged_robot.py:1036-1148 and go2.py:578-831, in the
  * ALPHABETICAL order in which the reference sums them (class_to_dict iterates dir(),
@@ -191,7 +194,7 @@ typedef struct B200EnvBuffers {
   float* last_contact_heights;   /* [N,4] */
   float* feet_air_time;          /* [N,4] */
   float* jump_flags;             /* [N,1] */
-  float* episode_sums;           /* [B200_NUM_REWARD_TERMS,N]; rows of disabled terms stay 0 */
+  float* episode_sums;           /* [N,B200_NUM_REWARD_TERMS] env-major; columns of disabled terms stay 0 */
   int64_t* terrain_levels;       /* [N] */
   const int64_t* terrain_types;  /* [N] */
   float* env_origins;            /* [N,3] */
@@ -217,6 +220,7 @@ typedef struct B200EnvBuffers {
   uint8_t* extras_time_outs;     /* [N] bool */
   float* extras_episode;         /* [B200_NUM_REWARD_TERMS + 1]: rew_<term> means, then terrain_level */
   int32_t* reset_count;          /* [1] number of envs reset this step */
+  float* reset_episode_sums;     /* [N,B200_NUM_REWARD_TERMS] scratch: pre-zeroing sums of envs reset this step */
 } B200EnvBuffers;
 
 typedef struct B200Env B200Env;  /* opaque handle: params in device constant storage + scratch */

@@ -1,0 +1,89 @@
+"""Allocation of the B200EnvBuffers block (include/b200gym.h) as torch tensors.
+
+All memory is owned by PyTorch on the Python side and outlives every library call
+(SURVEY.md §8(b) ownership rule); the struct handed to the C ABI only carries data_ptr()s.
+`device` is a CUDA device for the product path; tests/host_emul passes 'cpu' to run the
+kernel source under the host emulator.
+"""
+import ctypes as C
+
+import torch
+
+from .params import BUFFER_FIELDS, EnvBuffers, NUM_BODIES, NUM_DOF, NUM_REWARD_TERMS
+
+
+def buffer_specs(p):
+    """name -> (shape, dtype) for every pointer of B200EnvBuffers."""
+    N, NP, H, NS = p.num_envs, p.num_proprio, p.history_len, p.num_scan
+    obs = NP * (H + 1)
+    crit = obs + p.num_priv + p.num_est + NS
+    f, i64, b = torch.float32, torch.int64, torch.bool
+    return {
+        "root_states": ((N, 13), f), "dof_state": ((N * NUM_DOF, 2), f), "contact_forces": ((N * NUM_BODIES, 3), f),
+        "rigid_body_states": ((N * NUM_BODIES, 13), f), "kp_kd_multipliers": ((2, N, NUM_DOF), f),
+        "priv_mass_params": ((N, 4), f), "priv_friction": ((N, 1), f),
+        "height_samples": ((p.hs_rows, p.hs_cols), torch.int16) if p.has_height_samples else None,
+        "terrain_origins": ((p.max_terrain_level, p.terrain_cols, 3), f) if p.has_height_samples else None,
+        "actions": ((N, NUM_DOF), f), "torques": ((N, NUM_DOF), f), "commands": ((N, 4), f),
+        "episode_length_buf": ((N,), i64), "last_actions": ((N, NUM_DOF), f), "last_dof_vel": ((N, NUM_DOF), f),
+        "last_root_vel": ((N, 6), f), "last_base_lin_vel": ((N, 3), f), "last_torques": ((N, NUM_DOF), f),
+        "obs_history_buf": ((N, H, NP), f), "last_contacts": ((N, 4), b), "last_contact_heights": ((N, 4), f),
+        "feet_air_time": ((N, 4), f), "jump_flags": ((N, 1), f), "episode_sums": ((N, NUM_REWARD_TERMS), f),
+        "terrain_levels": ((N,), i64), "terrain_types": ((N,), i64), "env_origins": ((N, 3), f),
+        "base_lin_vel": ((N, 3), f), "base_ang_vel": ((N, 3), f), "projected_gravity": ((N, 3), f), "rpy": ((N, 3), f),
+        "measured_heights": ((N, NS), f), "height_index": None, "phases": ((N, 5), f), "foot_contacts": ((N, 4), b),
+        "obs_buf": ((N, obs), f), "privileged_obs_buf": ((N, p.num_priv), f), "critic_obs_buf": ((N, crit), f),
+        "estimated_obs_buf": ((N, p.num_est), f), "scan_obs_buf": ((N, NS), f), "rew_buf": ((N,), f),
+        "reset_buf": ((N,), b), "time_out_buf": ((N,), b), "extras_time_outs": ((N,), b),
+        "extras_episode": ((NUM_REWARD_TERMS + 1,), f), "reset_count": ((1,), torch.int32),
+        "reset_episode_sums": ((N, NUM_REWARD_TERMS), f),
+    }
+
+
+class BufferSet:
+    """Named torch tensors + the ctypes struct that points at them."""
+
+    def __init__(self, p, device, record_height_index=False):
+        self.p, self.device = p, torch.device(device)
+        self.t = {}
+        for name, spec in buffer_specs(p).items():
+            if name == "height_index" and record_height_index:
+                spec = ((p.num_envs, p.num_scan, 2), torch.int64)
+            self.t[name] = None if spec is None else torch.zeros(spec[0], dtype=spec[1], device=self.device)
+        self.t["root_states"][:, 6] = 1.0
+        self.t["reset_buf"].fill_(True)                      # base_task.py:83
+        self.struct = EnvBuffers()
+        self.refresh_pointers()
+
+    def refresh_pointers(self):
+        for name in BUFFER_FIELDS:
+            t = self.t[name]
+            if t is not None:
+                assert t.is_contiguous(), name
+            setattr(self.struct, name, None if t is None else C.c_void_p(t.data_ptr()))
+
+    def rebind(self, name, tensor):
+        """Point a PhysX-owned slot at another tensor (zero-copy replay of pre-generated frames)."""
+        old = self.t[name]
+        assert tensor.shape == old.shape and tensor.dtype == old.dtype and tensor.device == old.device and tensor.is_contiguous()
+        self.t[name] = tensor
+        setattr(self.struct, name, C.c_void_p(tensor.data_ptr()))
+
+    def __getitem__(self, name):
+        return self.t[name]
+
+    def load_state(self, st):
+        """Copy a persistent-state dict (oracle / golden naming) into the buffers."""
+        for k, v in st.items():
+            if k == "episode_sums":
+                self.t[k].copy_(torch.as_tensor(v).t())
+            elif k in self.t and self.t[k] is not None:
+                self.t[k].copy_(torch.as_tensor(v).reshape(self.t[k].shape).to(self.t[k].dtype))
+
+    def load_statics(self, statics):
+        self.t["kp_kd_multipliers"].copy_(torch.as_tensor(statics["kp_kd_multipliers"]))
+        self.t["priv_mass_params"].copy_(torch.as_tensor(statics["privileged_mass_params"]))
+        self.t["priv_friction"].copy_(torch.as_tensor(statics["privileged_friction_coeffs"]).reshape(-1, 1))
+        if self.t["height_samples"] is not None:
+            self.t["height_samples"].copy_(torch.as_tensor(statics["height_samples"]))
+            self.t["terrain_origins"].copy_(torch.as_tensor(statics["terrain_origins"]))

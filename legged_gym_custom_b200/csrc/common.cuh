@@ -1,0 +1,30 @@
+// Shared host-side helpers of libb200gym.so (error text, launch checks).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/b200gym.h"
+
+void b200_set_error(const char* fmt, ...);
+
+#define B200_CHECK_ARG(cond, ...)   \
+  do {                              \
+    if (!(cond)) {                  \
+      b200_set_error(__VA_ARGS__);  \
+      return -1;                    \
+    }                               \
+  } while (0)
+
+#define B200_CHECK_LAUNCH(name)                                             \
+  do {                                                                      \
+    cudaError_t err_ = cudaGetLastError();                                  \
+    if (err_ != cudaSuccess) {                                              \
+      b200_set_error("%s: %s", name, cudaGetErrorString(err_));             \
+      return (int)err_;                                                     \
+    }                                                                       \
+  } while (0)
+
+struct B200Env {
+  B200EnvParams p;
+  int device;
+};

@@ -1,0 +1,217 @@
+// Env-side kernels of libb200gym.so (compiled with -fmad=false, see env_core.cuh).
+//
+//   K1 pd_torques_kernel        one thread per (env, dof)            legged_robot.py:74-75, :440-478
+//   K2 post_physics_kernel      one warp per env, 4 warps per CTA    go2.py:345-387 and callees
+//   K3 extras_kernel            one CTA per reward term (+1)         go2.py:246-263 (episode means, time_outs)
+//      reset_all_kernel         one thread per env                   base_task.py:131-133
+//      heights_kernel           one thread per scan point            legged_robot.py:997-1032
+//
+// All are HBM-bound streaming kernels: rows are read/written with consecutive lanes on
+// consecutive addresses (16-byte vectors for the bulk rows), the per-env working set lives in
+// shared memory, and the params/pointer structs travel as __grid_constant__ kernel arguments
+// (constant bank, no extra copy per launch).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "env_core.cuh"
+
+static thread_local char g_err[512] = "";
+void b200_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int kWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step) {
+  __shared__ EnvScratch scratch[kWarpsPerCta];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kWarpsPerCta + warp;
+  if (e >= P.num_envs) return;
+  env_warp_step(P, B, scratch[warp], e, step, lane, lane + 1);
+}
+
+__global__ void __launch_bounds__(256)
+pd_torques_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B,
+                  const float* __restrict__ actions_in, int clip_and_store) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)P.num_envs * B200_NUM_DOF) return;
+  pd_torque_element(P, B, actions_in, clip_and_store, idx);
+}
+
+__global__ void __launch_bounds__(128)
+reset_all_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step, int init_done) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.num_envs) return;
+  env_reset_only(P, B, e, step, init_done);
+}
+
+__global__ void __launch_bounds__(256)
+heights_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)P.num_envs * P.num_scan) return;
+  const int e = (int)(idx / P.num_scan), j = (int)(idx % P.num_scan);
+  float h = 0.0f;
+  int px = 0, py = 0;
+  if (P.has_height_samples) {
+    float root[7];
+    for (int i = 0; i < 7; ++i) root[i] = B.root_states[(int64_t)e * 13 + i];
+    height_cell(P, yaw_quat(root + 3), root, j, &px, &py);
+    h = height_at(P, B.height_samples, px, py);
+  }
+  B.measured_heights[idx] = h;
+  if (B.height_index) {
+    B.height_index[idx * 2] = px;
+    B.height_index[idx * 2 + 1] = py;
+  }
+}
+
+// Deterministic CTA-wide sums (fixed tree), used for the episode means.
+template <typename T>
+__device__ T cta_sum_256(T v, T* smem) {
+  const int t = threadIdx.x;
+  smem[t] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) smem[t] += smem[t + s];
+    __syncthreads();
+  }
+  const T r = smem[0];
+  __syncthreads();
+  return r;
+}
+
+// extras["episode"]["rew_<term>"] = mean(episode_sums[term][reset ids]) / max_episode_length_s,
+// extras["episode"]["terrain_level"] = mean(terrain_levels), extras["time_outs"] = time_out_buf --
+// all only when at least one env reset this step (go2.py:214-215, :246-263).
+__global__ void __launch_bounds__(256)
+extras_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B) {
+  __shared__ float fsm[256];
+  __shared__ int ism[256];
+  const int k = blockIdx.x, T = B200_NUM_REWARD_TERMS, N = P.num_envs;
+  int cnt = 0;
+  float acc = 0.0f;
+  for (int e = threadIdx.x; e < N; e += 256) {
+    const int r = B.reset_buf[e] != 0;
+    cnt += r;
+    if (k < T) {
+      if (r) acc += B.reset_episode_sums[(int64_t)e * T + k];
+    } else {
+      acc += (float)B.terrain_levels[e];
+    }
+  }
+  const int count = cta_sum_256<int>(cnt, ism);
+  const float sum = cta_sum_256<float>(acc, fsm);
+  if (count == 0) {
+    if (k == 0 && threadIdx.x == 0) B.reset_count[0] = 0;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    if (k < T) {
+      if (P.reward_scales[k] != 0.0f) B.extras_episode[k] = (sum / (float)count) / P.max_episode_length_s;
+    } else if (P.curriculum) {
+      B.extras_episode[T] = sum / (float)N;
+    }
+    if (k == 0) B.reset_count[0] = count;
+  }
+  const int per = (N + gridDim.x - 1) / gridDim.x;
+  const int lo = k * per, hi = min(N, lo + per);
+  for (int e = lo + threadIdx.x; e < hi; e += 256) B.extras_time_outs[e] = B.time_out_buf[e];
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200_last_error(void) { return g_err; }
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+int b200_env_params_size(void) { return (int)sizeof(B200EnvParams); }
+int b200_env_buffers_size(void) { return (int)sizeof(B200EnvBuffers); }
+
+int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
+  B200_CHECK_ARG(p && out, "b200_env_create: null argument");
+  B200_CHECK_ARG(p->abi_version == B200_ABI_VERSION, "b200_env_create: abi_version %d != %d", p->abi_version, B200_ABI_VERSION);
+  B200_CHECK_ARG(p->num_envs > 0, "b200_env_create: num_envs must be > 0");
+  B200_CHECK_ARG(p->num_proprio == B200_PROPRIO, "b200_env_create: num_proprio %d unsupported (go2 layout is %d)", p->num_proprio, B200_PROPRIO);
+  B200_CHECK_ARG(p->history_len > 0 && p->history_len * p->num_proprio <= B200_MAX_HIST, "b200_env_create: history too long");
+  B200_CHECK_ARG(p->num_scan == p->scan_nx * p->scan_ny && p->num_scan <= B200_MAX_SCAN, "b200_env_create: bad scan grid");
+  B200_CHECK_ARG(p->num_priv == 29 && p->num_est == 3, "b200_env_create: privileged/estimated layout must be 29/3");
+  B200_CHECK_ARG(p->n_penalised <= B200_NUM_BODIES && p->n_termination <= B200_NUM_BODIES, "b200_env_create: body tables");
+  B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2), "b200_env_create: height_samples shape");
+  B200_CHECK_ARG(p->resample_interval > 0 && p->push_interval > 0, "b200_env_create: intervals must be > 0");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess) {
+    b200_set_error("b200_env_create: %s", cudaGetErrorString(err));
+    return (int)err;
+  }
+  B200_CHECK_ARG(device >= 0 && device < ndev, "b200_env_create: device %d of %d", device, ndev);
+  B200Env* env = new B200Env;
+  env->p = *p;
+  env->device = device;
+  *out = env;
+  return 0;
+}
+
+int b200_env_destroy(B200Env* env) {
+  delete env;
+  return 0;
+}
+
+static int check_bufs(const B200Env* env, const B200EnvBuffers* b, const char* who) {
+  B200_CHECK_ARG(env && b, "%s: null argument", who);
+  const void* const* ptrs = reinterpret_cast<const void* const*>(b);
+  const int n = (int)(sizeof(B200EnvBuffers) / sizeof(void*));
+  const int idx_height_samples = (int)(offsetof(B200EnvBuffers, height_samples) / sizeof(void*));
+  const int idx_origins = (int)(offsetof(B200EnvBuffers, terrain_origins) / sizeof(void*));
+  const int idx_hidx = (int)(offsetof(B200EnvBuffers, height_index) / sizeof(void*));
+  for (int i = 0; i < n; ++i) {
+    if (ptrs[i]) continue;
+    if (i == idx_hidx) continue;
+    if (i == idx_height_samples && !env->p.has_height_samples) continue;
+    if (i == idx_origins && !env->p.curriculum) continue;
+    b200_set_error("%s: buffer #%d of B200EnvBuffers is NULL", who, i);
+    return -1;
+  }
+  return 0;
+}
+
+int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actions_in, int clip_and_store, void* stream) {
+  if (int rc = check_bufs(env, bufs, "b200_pd_torques")) return rc;
+  B200_CHECK_ARG(!clip_and_store || actions_in, "b200_pd_torques: actions_in is NULL");
+  const int64_t n = (int64_t)env->p.num_envs * B200_NUM_DOF;
+  pd_torques_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->p, *bufs, actions_in, clip_and_store);
+  B200_CHECK_LAUNCH("pd_torques_kernel");
+  return 0;
+}
+
+int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, void* stream) {
+  if (int rc = check_bufs(env, bufs, "b200_post_physics_step")) return rc;
+  const int ctas = (env->p.num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
+  post_physics_kernel<<<ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter);
+  B200_CHECK_LAUNCH("post_physics_kernel");
+  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+  B200_CHECK_LAUNCH("extras_kernel");
+  return 0;
+}
+
+int b200_reset_all(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, int init_done, void* stream) {
+  if (int rc = check_bufs(env, bufs, "b200_reset_all")) return rc;
+  reset_all_kernel<<<(env->p.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter, init_done);
+  B200_CHECK_LAUNCH("reset_all_kernel");
+  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+  B200_CHECK_LAUNCH("extras_kernel");
+  return 0;
+}
+
+int b200_get_heights(B200Env* env, const B200EnvBuffers* bufs, void* stream) {
+  if (int rc = check_bufs(env, bufs, "b200_get_heights")) return rc;
+  const int64_t n = (int64_t)env->p.num_envs * env->p.num_scan;
+  heights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+  B200_CHECK_LAUNCH("heights_kernel");
+  return 0;
+}
+
+}  // extern "C"

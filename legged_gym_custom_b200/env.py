@@ -1,0 +1,301 @@
+"""`Go2Env`: the drop-in for the reference's `Go2Robot` / `LeggedRobot` env object, with the
+torch op-by-op path replaced by the sm_100a kernels of libb200gym.so.
+
+Mirrors the Python surface OnPolicyRunner / play.py use: constructor
+`(cfg, sim_params, physics_engine, sim_device, headless)`, `step(actions)` returning the
+reference's 8-tuple (legged_robot.py:100), `reset()`, `reset_idx()`, `get_*observations()`
+(base_task.py:112-135) and the buffer attributes, all backed by device tensors that the kernels
+update in place.  PhysX is out of scope (BASELINE.json north_star): it is an opaque producer of
+the four state tensors, represented here by a small provider object (`SyntheticPhysX` replays
+pre-generated frames; an Isaac Gym adapter would wrap gym.simulate / refresh_*).
+
+There is no CPU path: constructing a Go2Env without CUDA or without the built library raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, synth, terrain as terrain_mod
+from .buffers import BufferSet
+from .params import NUM_BODIES, NUM_DOF, REWARD_INDEX, REWARD_TERMS, env_params_from_cfg
+
+
+class SyntheticPhysX:
+    """Replays a ring of pre-generated PhysX frame sets (synth.make_frames) with zero copies: the
+    env's PhysX-owned buffer slots are re-pointed at the next frame, as if the simulator had just
+    written them."""
+
+    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, **frame_kw):
+        rng = np.random.default_rng(seed)
+        origins = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
+        self.frames = []
+        for _ in range(ring):
+            f = synth.make_frames(num_envs, origins, rng, decimation=decimation, **frame_kw)
+            self.frames.append({k: torch.from_numpy(v).to(device).contiguous() for k, v in f.items()})
+        self.cursor = -1
+
+    def begin_step(self, env):
+        self.cursor = (self.cursor + 1) % len(self.frames)
+
+    def simulate(self, env, substep):
+        """gym.set_dof_actuation_force_tensor + gym.simulate + refresh_dof_state_tensor (legged_robot.py:81-85)."""
+        env.bufs.rebind("dof_state", self.frames[self.cursor]["dof"][substep])
+
+    def refresh(self, env):
+        """refresh_actor_root_state / net_contact_force / rigid_body_state tensors (go2.py:352-353, :272)."""
+        f = self.frames[self.cursor]
+        env.bufs.rebind("root_states", f["root"])
+        env.bufs.rebind("contact_forces", f["contact"])
+        env.bufs.rebind("rigid_body_states", f["rigid"])
+
+    def push_state(self, env):
+        """set_dof_state_tensor_indexed / set_actor_root_state_tensor_indexed: nothing to do for a replay."""
+
+
+class ExternalPhysX:
+    """The caller writes the PhysX tensors itself (tests replaying recorded frames)."""
+
+    def begin_step(self, env):
+        pass
+
+    def simulate(self, env, substep):
+        if self.on_simulate is not None:
+            self.on_simulate(env, substep)
+
+    def refresh(self, env):
+        if self.on_refresh is not None:
+            self.on_refresh(env)
+
+    def push_state(self, env):
+        pass
+
+    def __init__(self, on_simulate=None, on_refresh=None):
+        self.on_simulate, self.on_refresh = on_simulate, on_refresh
+
+
+def _buffer_property(name):
+    def get(self):
+        return self.bufs[name]
+
+    def set_(self, value):                 # the runner ASSIGNS episode_length_buf (on_policy_runner.py:122)
+        self.bufs[name].copy_(torch.as_tensor(value, device=self.device))
+
+    return property(get, set_)
+
+
+class Go2Env:
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, physx=None,
+                 seed=None, index_div_mode=0, height_samples=None, terrain_origins=None, record_height_index=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("Go2Env needs a CUDA device: the hot path has no CPU fallback")
+        self.lib = _lib.lib()
+        self.cfg = cfg
+        self.sim_params = sim_params
+        self.device = torch.device(sim_device)
+        self.headless = headless
+        seed = int(seed if seed is not None else getattr(cfg, "seed", 1))
+        N = int(cfg.env.num_envs)
+
+        hs = origins = None
+        if cfg.terrain.mesh_type in ("heightfield", "trimesh"):
+            if height_samples is None:
+                if not getattr(cfg.terrain, "parkour", False):
+                    raise ValueError("non-parkour terrains: pass height_samples / terrain_origins (terrain generation "
+                                     "beyond the parkour layouts is out of scope, SURVEY.md §8(f1))")
+                height_samples, terrain_origins = terrain_mod.make_parkour_terrain(cfg.terrain)
+            hs, origins = np.asarray(height_samples, dtype=np.int16), np.asarray(terrain_origins, dtype=np.float32)
+        self.params = p = env_params_from_cfg(cfg, num_envs=N, seed=seed, index_div_mode=index_div_mode,
+                                              hs_shape=None if hs is None else hs.shape)
+        self.bufs = BufferSet(p, self.device, record_height_index=record_height_index)
+        self._handle = C.c_void_p()
+        _lib.check(self.lib.b200_env_create(C.byref(p), self.device.index or 0, C.byref(self._handle)))
+
+        # sizes (base_task.py:57-66)
+        self.num_envs, self.num_actions = N, NUM_DOF
+        self.num_proprio, self.history_buffer_length = p.num_proprio, p.history_len
+        self.num_obs = p.num_proprio * (p.history_len + 1)
+        self.num_privileged_obs, self.num_estimated_obs, self.num_scan_obs = p.num_priv, p.num_est, p.num_scan
+        self.num_critic_obs = self.num_obs + p.num_priv + p.num_est + p.num_scan
+        self.dt = cfg.control.decimation * float(cfg.sim.dt)
+        self.max_episode_length_s = cfg.env.episode_length_s
+        self.max_episode_length = float(np.ceil(self.max_episode_length_s / self.dt))
+        self.common_step_counter = 0
+        self.init_done = False
+        self.reward_names = p.reward_names()
+        self.feet_indices = torch.tensor(list(p.feet), device=self.device)
+        self.penalised_contact_indices = torch.tensor(list(p.penalised)[:p.n_penalised], device=self.device)
+        self.termination_contact_indices = torch.tensor(list(p.termination)[:p.n_termination], device=self.device)
+        self.default_dof_pos = torch.tensor(list(p.default_dof_pos), device=self.device).unsqueeze(0)
+        self._extras = {}
+
+        self._init_domain_randomisation(cfg, hs, origins, seed)
+        self.physx = physx if physx is not None else SyntheticPhysX(N, self.bufs["env_origins"], self.device, seed=seed,
+                                                                    decimation=p.decimation)
+        self.init_done = True
+
+    # ---- env-creation-time randomisation (legged_robot.py:306-380, :687-701, :897-930); host torch, runs once
+    def _init_domain_randomisation(self, cfg, hs, origins, seed):
+        p, b, N = self.params, self.bufs, self.num_envs
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        dr = cfg.domain_rand
+        if getattr(dr, "randomize_friction", False):
+            lo, hi = dr.friction_range
+            buckets = (hi - lo) * torch.rand(64, 1, generator=g) + lo
+            b["priv_friction"].copy_(buckets[torch.randint(0, 64, (N,), generator=g)])
+        else:
+            b["priv_friction"].fill_(cfg.terrain.dynamic_friction)
+        mass = torch.zeros(N, 4)
+        if getattr(dr, "randomize_base_mass", False):
+            lo, hi = dr.added_mass_range
+            mass[:, 0] = (hi - lo) * torch.rand(N, generator=g) + lo
+        if getattr(dr, "randomize_center_of_mass", False):
+            lo, hi = dr.added_com_range
+            mass[:, 1:] = (hi - lo) * torch.rand(N, 3, generator=g) + lo
+        b["priv_mass_params"].copy_(mass)
+        lo, hi = getattr(dr, "kp_kd_range", (1.0, 1.0))
+        b["kp_kd_multipliers"].copy_((hi - lo) * torch.rand(2, N, NUM_DOF, generator=g) + lo)
+        if hs is not None:
+            b["height_samples"].copy_(torch.from_numpy(hs))
+            b["terrain_origins"].copy_(torch.from_numpy(origins))
+            ter = cfg.terrain
+            max_init = ter.max_init_terrain_level if ter.curriculum else ter.num_rows - 1
+            levels = torch.randint(0, max_init + 1, (N,), generator=g)
+            types = torch.div(torch.arange(N), (N / ter.num_cols), rounding_mode="floor").to(torch.long)
+            b["terrain_levels"].copy_(levels)
+            b["terrain_types"].copy_(types)
+            b["env_origins"].copy_(torch.from_numpy(origins)[levels, types])
+        else:
+            cols = np.floor(np.sqrt(N))
+            rows = np.ceil(N / cols)
+            xx, yy = torch.meshgrid(torch.arange(rows), torch.arange(cols), indexing="ij")
+            o = torch.zeros(N, 3)
+            o[:, 0] = cfg.env.env_spacing * xx.flatten()[:N]
+            o[:, 1] = cfg.env.env_spacing * yy.flatten()[:N]
+            b["env_origins"].copy_(o)
+
+    def __del__(self):
+        try:
+            if self._handle:
+                self.lib.b200_env_destroy(self._handle)
+        except Exception:
+            pass
+
+    # ---- the VecEnv contract -----------------------------------------------------------------------
+    def step(self, actions):
+        """legged_robot.py:67-100. -> (obs, privileged_obs, critic_obs, estimated_obs, scan_obs, rew, reset, extras)"""
+        actions = actions.to(self.device, torch.float32).contiguous()
+        st = _lib.stream_ptr()
+        b = self.bufs
+        self.physx.begin_step(self)
+        for k in range(self.params.decimation):
+            _lib.check(self.lib.b200_pd_torques(self._handle, C.byref(b.struct), C.c_void_p(actions.data_ptr()), int(k == 0), st))
+            self.physx.simulate(self, k)
+        self.physx.refresh(self)
+        self.common_step_counter += 1
+        _lib.check(self.lib.b200_post_physics_step(self._handle, C.byref(b.struct), self.common_step_counter, st))
+        self.physx.push_state(self)
+        return (b["obs_buf"], b["privileged_obs_buf"], b["critic_obs_buf"], b["estimated_obs_buf"], b["scan_obs_buf"],
+                b["rew_buf"], b["reset_buf"], self.extras)
+
+    def step5(self, actions):
+        """upstream rsl_rl VecEnv 5-tuple (rsl_rl/env/vec_env.py:28): obs, privileged_obs, rew, done, info."""
+        obs, priv, _, _, _, rew, done, info = self.step(actions)
+        return obs, priv, rew, done, info
+
+    def reset_idx(self, env_ids=None):
+        """go2.py:207-263 outside a step.  Only the all-envs form is used by the reference (BaseTask.reset)."""
+        if env_ids is not None and len(env_ids) != self.num_envs:
+            raise NotImplementedError("partial reset_idx outside step() is not on the hot path; step() resets flagged envs itself")
+        _lib.check(self.lib.b200_reset_all(self._handle, C.byref(self.bufs.struct), self.common_step_counter,
+                                           int(self.init_done), _lib.stream_ptr()))
+        self.physx.push_state(self)
+
+    def reset(self):
+        """base_task.py:131-135."""
+        self.reset_idx()
+        out = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        return out[:5]
+
+    def get_observations(self):
+        return self.bufs["obs_buf"]
+
+    def get_privileged_observations(self):
+        return self.bufs["privileged_obs_buf"]
+
+    def get_critic_observations(self):
+        return self.bufs["critic_obs_buf"]
+
+    def get_estimated_observations(self):
+        return self.bufs["estimated_obs_buf"]
+
+    def get_scan_observations(self):
+        return self.bufs["scan_obs_buf"]
+
+    def get_heights(self):
+        """LeggedRobot._get_heights as a standalone launch (legged_robot.py:997-1032)."""
+        _lib.check(self.lib.b200_get_heights(self._handle, C.byref(self.bufs.struct), _lib.stream_ptr()))
+        return self.bufs["measured_heights"]
+
+    # ---- extras: device-resident, refreshed by the kernels only on steps with >= 1 reset (go2.py:246-263)
+    @property
+    def extras(self):
+        if not self._extras:
+            ep = self.bufs["extras_episode"]
+            episode = {"rew_" + n: ep[REWARD_INDEX[n]] for n in REWARD_TERMS if self.params.reward_scales[REWARD_INDEX[n]] != 0.0}
+            if self.params.curriculum:
+                episode["terrain_level"] = ep[len(REWARD_TERMS)]
+            self._extras = {"episode": episode}
+            if getattr(self.cfg.env, "send_timeouts", True):
+                self._extras["time_outs"] = self.bufs["extras_time_outs"]
+        return self._extras
+
+    @property
+    def episode_sums(self):
+        s = self.bufs["episode_sums"]
+        return {n: s[:, REWARD_INDEX[n]] for n in REWARD_TERMS if self.params.reward_scales[REWARD_INDEX[n]] != 0.0}
+
+    @property
+    def dof_pos(self):
+        return self.bufs["dof_state"].view(self.num_envs, NUM_DOF, 2)[..., 0]
+
+    @property
+    def dof_vel(self):
+        return self.bufs["dof_state"].view(self.num_envs, NUM_DOF, 2)[..., 1]
+
+    @property
+    def contact_forces(self):
+        return self.bufs["contact_forces"].view(self.num_envs, NUM_BODIES, 3)
+
+    @property
+    def base_quat(self):
+        return self.bufs["root_states"][:, 3:7]
+
+    @property
+    def roll(self):
+        return self.bufs["rpy"][:, 0]
+
+    @property
+    def pitch(self):
+        return self.bufs["rpy"][:, 1]
+
+    @property
+    def yaw(self):
+        return self.bufs["rpy"][:, 2]
+
+    @property
+    def privileged_mass_params(self):
+        return self.bufs["priv_mass_params"]
+
+    @property
+    def privileged_friction_coeffs(self):
+        return self.bufs["priv_friction"]
+
+
+for _name in ("obs_buf", "privileged_obs_buf", "critic_obs_buf", "estimated_obs_buf", "scan_obs_buf", "rew_buf", "reset_buf",
+              "time_out_buf", "obs_history_buf", "commands", "torques", "actions", "base_lin_vel", "base_ang_vel",
+              "projected_gravity", "root_states", "dof_state", "rigid_body_states", "episode_length_buf", "last_actions",
+              "last_dof_vel", "last_root_vel", "last_base_lin_vel", "last_torques", "last_contacts", "last_contact_heights",
+              "feet_air_time", "jump_flags", "terrain_levels", "terrain_types", "env_origins", "measured_heights",
+              "kp_kd_multipliers", "height_samples", "terrain_origins"):
+    setattr(Go2Env, _name, _buffer_property(_name))

@@ -87,7 +87,7 @@ BUFFER_FIELDS = [
     "terrain_types", "env_origins", "base_lin_vel", "base_ang_vel", "projected_gravity", "rpy", "measured_heights",
     "height_index", "phases", "foot_contacts", "obs_buf", "privileged_obs_buf", "critic_obs_buf",
     "estimated_obs_buf", "scan_obs_buf", "rew_buf", "reset_buf", "time_out_buf", "extras_time_outs",
-    "extras_episode", "reset_count",
+    "extras_episode", "reset_count", "reset_episode_sums",
 ]
 
 

@@ -101,3 +101,99 @@ def expected(g, t):
 def critic_sha(obs, priv, est, scan):
     c = np.concatenate([obs, priv, est, scan], axis=-1).astype(np.float32)
     return hashlib.sha256(np.ascontiguousarray(c).tobytes()).hexdigest()
+
+
+# ---- comparison of a BufferSet (host emulator or CUDA) with the reference's tensors ---------
+RTOL = 1e-5          # BASELINE.json north_star: "within 1e-5 relative in fp32"
+EXACT = ("episode_length_buf", "last_contacts", "terrain_levels", "reset_buf", "time_out_buf", "height_index",
+         "foot_contacts", "jump_flags")
+# golden name -> (buffer name, transform)
+FLOAT_MAP = {
+    "base_lin_vel": "base_lin_vel", "base_ang_vel": "base_ang_vel", "projected_gravity": "projected_gravity",
+    "measured_heights": "measured_heights", "rew_buf": "rew_buf", "obs_buf": "obs_buf",
+    "privileged_obs_buf": "privileged_obs_buf", "estimated_obs_buf": "estimated_obs_buf", "scan_obs_buf": "scan_obs_buf",
+    "actions": "actions", "torques": "torques", "commands": "commands", "last_actions": "last_actions",
+    "last_dof_vel": "last_dof_vel", "last_root_vel": "last_root_vel", "last_base_lin_vel": "last_base_lin_vel",
+    "last_torques": "last_torques", "last_contact_heights": "last_contact_heights", "env_origins": "env_origins",
+    "feet_air_time": "feet_air_time", "root_states": "root_states", "dof_state": "dof_state",
+}
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, s): relative to the element, floored at the tensor's own scale s (rms, >= 1e-6)
+    so that exact zeros / cancellations do not make the ratio meaningless."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    s = max(float(np.sqrt(np.mean(b * b))), 1e-6)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), s)))
+
+
+def check_step(bufs, exp, t, rtol=RTOL, report=None):
+    """bufs: BufferSet after step t; exp: expected(g, t). Raises AssertionError on mismatch."""
+    get = lambda name: bufs[name].detach().cpu().numpy()
+    worst = {}
+    for gname, bname in FLOAT_MAP.items():
+        if gname not in exp:
+            continue
+        a, b = get(bname), exp[gname]
+        assert a.shape == b.shape, (gname, a.shape, b.shape)
+        assert np.isfinite(a).all(), f"{gname} step {t}: non-finite values"
+        worst[gname] = rel_err(a, b)
+    rpy = get("rpy")
+    for i, k in enumerate(("roll", "pitch", "yaw")):
+        worst[k] = rel_err(rpy[:, i], exp[k])
+    ph = get("phases")
+    for i, k in enumerate(("phase", "phase_fr", "phase_fl", "phase_bl", "phase_br")):
+        worst[k] = rel_err(ph[:, i], exp[k])
+    worst["episode_sums"] = rel_err(get("episode_sums").T, exp["episode_sums"])
+    crit = get("critic_obs_buf")
+    worst["critic_obs_buf"] = rel_err(crit, np.concatenate([exp["obs_buf"], exp["privileged_obs_buf"], exp["estimated_obs_buf"],
+                                                            exp["scan_obs_buf"]], axis=-1))
+    ep = get("extras_episode")
+    for i, v in exp["extras_episode"].items():
+        worst[f"extras_episode[{i}]"] = rel_err(ep[i:i + 1], np.array([v]))
+    if report is not None:
+        for k, v in worst.items():
+            report[k] = max(report.get(k, 0.0), v)
+    bad = {k: v for k, v in worst.items() if not v <= rtol}
+    assert not bad, f"step {t}: relative error above {rtol}: {bad}"
+    # bit-exact: indices, masks, levels
+    fc = get("foot_contacts")
+    for i, k in enumerate(("fl_contact", "fr_contact", "bl_contact", "br_contact")):
+        assert (fc[:, i].astype(bool) == exp[k].astype(bool)).all(), (k, t)
+    for k in ("episode_length_buf", "terrain_levels"):
+        if k in exp:
+            assert (get(k) == exp[k]).all(), (k, t)
+    for k in ("reset_buf", "time_out_buf", "last_contacts"):
+        assert (get(k).astype(bool) == exp[k].astype(bool)).all(), (k, t)
+    assert (get("jump_flags") == exp["jump_flags"]).all(), ("jump_flags", t)
+    if bufs["height_index"] is not None:
+        assert (get("height_index") == exp["height_index"]).all(), ("height_index", t)
+    if "extras/time_outs" in exp:
+        assert (get("extras_time_outs").astype(bool) == exp["extras/time_outs"].astype(bool)).all(), ("extras_time_outs", t)
+    assert int(get("reset_count")[0]) == int(exp["n_reset"]), ("reset_count", t)
+
+
+def oracle_expected(orc, out):
+    """oracle tensors -> the dict shape golden_util.check_step expects."""
+    st = orc.st
+    e = {k: out[k].numpy() for k in ("base_lin_vel", "base_ang_vel", "projected_gravity", "roll", "pitch", "yaw",
+                                     "measured_heights", "phase", "phase_fr", "phase_fl", "phase_bl", "phase_br",
+                                     "fl_contact", "fr_contact", "bl_contact", "br_contact", "rew_buf", "obs_buf",
+                                     "privileged_obs_buf", "estimated_obs_buf", "scan_obs_buf", "height_index")}
+    for k in ("actions", "torques", "commands", "episode_length_buf", "last_actions", "last_dof_vel", "last_root_vel",
+              "last_base_lin_vel", "last_torques", "last_contacts", "last_contact_heights", "jump_flags", "terrain_levels",
+              "env_origins", "reset_buf", "time_out_buf", "feet_air_time", "root_states", "dof_state"):
+        e[k] = st[k].numpy()
+    e["episode_sums"] = st["episode_sums"].numpy()
+    e["extras_episode"] = {i: float(v) for i, v in enumerate(st["extras_episode"].numpy())
+                           if i == len(st["extras_episode"]) - 1 or orc.p.reward_scales[i] != 0.0}
+    if not orc.p.curriculum:
+        e["extras_episode"].pop(len(st["extras_episode"]) - 1, None)
+    e["extras/time_outs"] = st["extras_time_outs"].numpy()
+    e["n_reset"] = out["reset_count"]
+    return e
+
+

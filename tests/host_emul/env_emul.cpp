@@ -1,0 +1,59 @@
+// Host emulation of the env kernels: compiles legged_gym_custom_b200/csrc/env_core.cuh -- the
+// SAME source the CUDA kernels execute -- with g++ (-ffp-contract=off mirrors -fmad=false) and
+// runs each warp's lanes sequentially stage by stage.  TEST INFRASTRUCTURE: lets the CPU test
+// suite check the kernel source against the golden vectors without a GPU.  Not a product path
+// (the product library has no host fallback).
+#include <string.h>
+
+#include "../../legged_gym_custom_b200/csrc/env_core.cuh"
+
+extern "C" {
+
+int emul_params_size(void) { return (int)sizeof(B200EnvParams); }
+int emul_buffers_size(void) { return (int)sizeof(B200EnvBuffers); }
+int emul_scratch_size(void) { return (int)sizeof(EnvScratch); }
+
+int emul_pd_torques(const B200EnvParams* p, const B200EnvBuffers* b, const float* actions_in, int clip_and_store) {
+  const int64_t n = (int64_t)p->num_envs * B200_NUM_DOF;
+  for (int64_t i = 0; i < n; ++i) pd_torque_element(*p, *b, actions_in, clip_and_store, i);
+  return 0;
+}
+
+static void extras(const B200EnvParams& P, const B200EnvBuffers& B) {
+  const int T = B200_NUM_REWARD_TERMS, N = P.num_envs;
+  int count = 0;
+  for (int e = 0; e < N; ++e) count += B.reset_buf[e] != 0;
+  B.reset_count[0] = count;
+  if (count == 0) return;
+  for (int k = 0; k < T; ++k) {
+    if (P.reward_scales[k] == 0.0f) continue;
+    float s = 0.0f;
+    for (int e = 0; e < N; ++e)
+      if (B.reset_buf[e]) s += B.reset_episode_sums[(int64_t)e * T + k];
+    B.extras_episode[k] = (s / (float)count) / P.max_episode_length_s;
+  }
+  if (P.curriculum) {
+    float s = 0.0f;
+    for (int e = 0; e < N; ++e) s += (float)B.terrain_levels[e];
+    B.extras_episode[T] = s / (float)N;
+  }
+  for (int e = 0; e < N; ++e) B.extras_time_outs[e] = B.time_out_buf[e];
+}
+
+int emul_post_physics_step(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step) {
+  static EnvScratch S;
+  for (int e = 0; e < p->num_envs; ++e) {
+    memset(&S, 0xCD, sizeof(S));   // poison: a stage that reads what no stage wrote shows up as garbage
+    env_warp_step(*p, *b, S, e, step, 0, 32);
+  }
+  extras(*p, *b);
+  return 0;
+}
+
+int emul_reset_all(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step, int init_done) {
+  for (int e = 0; e < p->num_envs; ++e) env_reset_only(*p, *b, e, step, init_done);
+  extras(*p, *b);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""Parity of the CUDA env kernels, called through the C ABI (libb200gym.so), with the reference
+(golden fixtures) and with the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): bit-exact for height-sample indices, termination / reset /
+time-out masks, contact flags, jump flags, episode lengths and curriculum levels; <= 1e-5 relative
+(golden_util.rel_err) for every fp32 tensor."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import state_util as su
+from legged_gym_custom_b200 import _lib, configs, synth
+from legged_gym_custom_b200.buffers import BufferSet
+from legged_gym_custom_b200.params import NUM_DOF, env_params_from_cfg
+from oracle.go2_oracle import Go2Oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class CudaEnv:
+    """thin driver of the C ABI over a BufferSet (what Go2Env does, minus the PhysX provider)."""
+
+    def __init__(self, p, record_height_index=True):
+        self.lib, self.p = _lib.lib(), p
+        self.bufs = BufferSet(p, DEV, record_height_index=record_height_index)
+        self.h = C.c_void_p()
+        _lib.check(self.lib.b200_env_create(C.byref(p), 0, C.byref(self.h)))
+
+    def step(self, actions, frames, step):
+        b, st = self.bufs, _lib.stream_ptr()
+        a = torch.as_tensor(actions).to(DEV).contiguous()
+        for k in range(self.p.decimation):
+            _lib.check(self.lib.b200_pd_torques(self.h, C.byref(b.struct), C.c_void_p(a.data_ptr()), int(k == 0), st))
+            b["dof_state"].copy_(torch.as_tensor(frames["dof"][k]))
+        for name, key in (("root_states", "root"), ("contact_forces", "contact"), ("rigid_body_states", "rigid")):
+            b[name].copy_(torch.as_tensor(frames[key]))
+        _lib.check(self.lib.b200_post_physics_step(self.h, C.byref(b.struct), step, st))
+        torch.cuda.synchronize()
+
+    def close(self):
+        self.lib.b200_env_destroy(self.h)
+
+
+@pytest.mark.parametrize("task", gu.TASKS)
+def test_cuda_env_matches_reference_golden(task):
+    g = gu.load(task)
+    p = gu.params_for(task, g)
+    env = CudaEnv(p)
+    env.bufs.load_statics(gu.statics_for(task, g))
+    st = gu.init_state(g, p)
+    step = int(st.pop("common_step_counter"))
+    env.bufs.load_state(st)
+    report = {}
+    for t in range(int(g["steps"])):
+        step += 1
+        env.step(g[f"step{t}/in/actions"], gu.frames_of(g, t), step)
+        gu.check_step(env.bufs, gu.expected(g, t), t, report=report)
+    assert gu.rel_err(env.bufs["obs_history_buf"].cpu().numpy(), g["final/obs_history_buf"]) <= gu.RTOL
+    print(task, {k: f"{v:.1e}" for k, v in sorted(report.items(), key=lambda kv: -kv[1])[:5]})
+    env.close()
+
+
+@pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 4096, 3), ("go2_parkour_finetune", 1000, 2), ("go2", 777, 2)])
+def test_cuda_env_matches_oracle_at_scale(task, num_envs, steps):
+    """BASELINE config sizes (4096 envs), ragged sizes (not a multiple of the CTA's 4 envs), all three tasks."""
+    cfg = configs.TASKS[task][0]
+    hs, origins = gu.terrain_for(task)
+    p = env_params_from_cfg(cfg, num_envs=num_envs, seed=99, hs_shape=None if hs is None else hs.shape)
+    rng = np.random.default_rng(7)
+    statics = su.random_statics(p, rng, hs, origins)
+    st = su.random_state(p, rng, origins)
+    orc = Go2Oracle(p, statics, st)
+    env = CudaEnv(p)
+    env.bufs.load_statics(statics)
+    st2 = dict(st)
+    step = int(st2.pop("common_step_counter"))
+    env.bufs.load_state(st2)
+    origins0 = st["env_origins"].numpy()
+    total_resets = 0
+    for t in range(steps):
+        frames = synth.make_frames(num_envs, origins0, rng, hole_prob=0.01, flip_prob=0.01)
+        actions = rng.normal(0, 1.5, (num_envs, NUM_DOF)).astype(np.float32)
+        out = orc.step(torch.from_numpy(actions), frames)
+        step += 1
+        env.step(actions, frames, step)
+        gu.check_step(env.bufs, gu.oracle_expected(orc, out), t)
+        total_resets += out["reset_count"]
+    assert total_resets > 0
+    env.close()
+
+
+def test_height_index_torch_cuda_division_mode():
+    """index_div_mode=1 reproduces torch-CUDA's `points / horizontal_scale` (= points * fp32(1/scale)):
+    compared bit-for-bit with the same torch ops executed on this GPU (SURVEY.md §7 hard part 1)."""
+    task = "go2_parkour"
+    cfg = configs.TASKS[task][0]
+    hs, origins = gu.terrain_for(task)
+    N = 4096
+    p = env_params_from_cfg(cfg, num_envs=N, seed=5, hs_shape=hs.shape, index_div_mode=1)
+    rng = np.random.default_rng(3)
+    env = CudaEnv(p)
+    env.bufs.load_statics(su.random_statics(p, rng, hs, origins))
+    st = su.random_state(p, rng, origins)
+    frames = synth.make_frames(N, st["env_origins"].numpy(), rng)
+    env.bufs["root_states"].copy_(torch.from_numpy(frames["root"]))
+    _lib.check(env.lib.b200_get_heights(env.h, C.byref(env.bufs.struct), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    # the reference's ops (legged_robot.py:1018-1032, math.py:38-42) on the GPU
+    root = env.bufs["root_states"]
+    xs = torch.tensor(list(p.scan_x)[:p.scan_nx], device=DEV)
+    ys = torch.tensor(list(p.scan_y)[:p.scan_ny], device=DEV)
+    gx, gy = torch.meshgrid(xs, ys, indexing="ij")
+    pts = torch.zeros(N, p.num_scan, 3, device=DEV)
+    pts[:, :, 0], pts[:, :, 1] = gx.flatten(), gy.flatten()
+    q = root[:, 3:7].repeat(1, p.num_scan).view(-1, 4).clone()
+    q[:, :2] = 0.
+    q = q / q.norm(p=2, dim=-1).clamp(min=1e-9).unsqueeze(-1)
+    v = pts.view(-1, 3)
+    xyz = q[:, :3]
+    tt = xyz.cross(v, dim=-1) * 2
+    rot = (v + q[:, 3:] * tt + xyz.cross(tt, dim=-1)).view(N, p.num_scan, 3) + root[:, :3].unsqueeze(1)
+    rot += cfg.terrain.border_size
+    idx = (rot / cfg.terrain.horizontal_scale).long()
+    px = torch.clip(idx[:, :, 0], 0, hs.shape[0] - 2)
+    py = torch.clip(idx[:, :, 1], 0, hs.shape[1] - 2)
+    mine = env.bufs["height_index"]
+    mism = int(((mine[..., 0] != px) | (mine[..., 1] != py)).sum())
+    hsd = env.bufs["height_samples"]
+    h = torch.min(torch.min(hsd[px, py], hsd[px + 1, py]), hsd[px, py + 1]).float() * cfg.terrain.vertical_scale
+    print("torch-CUDA division-mode mismatches:", mism, "of", px.numel())
+    assert mism == 0
+    assert torch.equal(h, env.bufs["measured_heights"])
+    env.close()
+
+
+def test_go2env_api_smoke():
+    """the drop-in surface: 8-tuple step, reset(), assignable episode_length_buf, extras on device."""
+    from legged_gym_custom_b200.env import Go2Env
+
+    class Cfg(configs.Go2ParkourCfg):
+        class env(configs.Go2ParkourCfg.env):
+            num_envs = 256
+    env = Go2Env(Cfg, sim_device=DEV)
+    obs, priv, crit, est, scan = env.reset()
+    assert obs.shape == (256, 572) and priv.shape == (256, 29) and crit.shape == (256, 736) and est.shape == (256, 3) and scan.shape == (256, 132)
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
+    for _ in range(5):
+        out = env.step(torch.randn(256, 12, device=DEV))
+    assert len(out) == 8 and out[5].shape == (256,) and out[6].dtype == torch.bool
+    assert "time_outs" in out[7] and "rew_tracking_lin_vel" in out[7]["episode"] and "terrain_level" in out[7]["episode"]
+    assert torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+    assert torch.equal(out[2][:, :572], out[0])
+    assert len(env.step5(torch.zeros(256, 12, device=DEV))) == 5

@@ -1,0 +1,82 @@
+"""The CUDA kernel SOURCE (csrc/env_core.cuh), compiled for the host and run lane by lane, against
+the reference's golden tensors: bit-exact indices / masks / levels, <= 1e-5 relative floats.
+The same checks run against the real kernels on the GPU in test_env_gpu.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from host_emul import emul
+from legged_gym_custom_b200.buffers import BufferSet
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emul.load()
+
+
+@pytest.mark.parametrize("task", gu.TASKS)
+def test_kernel_source_matches_reference(lib, task):
+    g = gu.load(task)
+    p = gu.params_for(task, g)
+    bufs = BufferSet(p, "cpu", record_height_index=True)
+    bufs.load_statics(gu.statics_for(task, g))
+    st = gu.init_state(g, p)
+    step = int(st.pop("common_step_counter"))
+    bufs.load_state(st)
+    report = {}
+    for t in range(int(g["steps"])):
+        fr = gu.frames_of(g, t)
+        actions = torch.from_numpy(g[f"step{t}/in/actions"]).contiguous()
+        for k in range(p.decimation):
+            lib.emul_pd_torques(C.byref(p), C.byref(bufs.struct), C.c_void_p(actions.data_ptr()), int(k == 0))
+            bufs["dof_state"].copy_(torch.from_numpy(fr["dof"][k]))
+        bufs["root_states"].copy_(torch.from_numpy(fr["root"]))
+        bufs["contact_forces"].copy_(torch.from_numpy(fr["contact"]))
+        bufs["rigid_body_states"].copy_(torch.from_numpy(fr["rigid"]))
+        step += 1
+        lib.emul_post_physics_step(C.byref(p), C.byref(bufs.struct), step)
+        gu.check_step(bufs, gu.expected(g, t), t, report=report)
+    hist = bufs["obs_history_buf"].numpy()
+    assert gu.rel_err(hist, g["final/obs_history_buf"]) <= gu.RTOL
+    print(task, "worst relative errors:", {k: f"{v:.1e}" for k, v in sorted(report.items(), key=lambda kv: -kv[1])[:6]})
+
+
+@pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 1500, 3), ("go2", 333, 2)])
+def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
+    """same harness as tests/test_env_gpu.py::test_cuda_env_matches_oracle_at_scale, on the host emulator."""
+    import state_util as su
+    from legged_gym_custom_b200 import configs, synth
+    from legged_gym_custom_b200.params import NUM_DOF, env_params_from_cfg
+    from oracle.go2_oracle import Go2Oracle
+    cfg = configs.TASKS[task][0]
+    hs, origins = gu.terrain_for(task)
+    p = env_params_from_cfg(cfg, num_envs=num_envs, seed=99, hs_shape=None if hs is None else hs.shape)
+    rng = np.random.default_rng(7)
+    statics = su.random_statics(p, rng, hs, origins)
+    st = su.random_state(p, rng, origins)
+    orc = Go2Oracle(p, statics, st)
+    bufs = BufferSet(p, "cpu", record_height_index=True)
+    bufs.load_statics(statics)
+    st2 = dict(st)
+    step = int(st2.pop("common_step_counter"))
+    bufs.load_state(st2)
+    origins0 = st["env_origins"].numpy()
+    total = 0
+    for t in range(steps):
+        frames = synth.make_frames(num_envs, origins0, rng, hole_prob=0.01, flip_prob=0.01)
+        actions = torch.from_numpy(rng.normal(0, 1.5, (num_envs, NUM_DOF)).astype(np.float32))
+        out = orc.step(actions, frames)
+        for k in range(p.decimation):
+            lib.emul_pd_torques(C.byref(p), C.byref(bufs.struct), C.c_void_p(actions.data_ptr()), int(k == 0))
+            bufs["dof_state"].copy_(torch.from_numpy(frames["dof"][k]))
+        bufs["root_states"].copy_(torch.from_numpy(frames["root"]))
+        bufs["contact_forces"].copy_(torch.from_numpy(frames["contact"]))
+        bufs["rigid_body_states"].copy_(torch.from_numpy(frames["rigid"]))
+        step += 1
+        lib.emul_post_physics_step(C.byref(p), C.byref(bufs.struct), step)
+        gu.check_step(bufs, gu.oracle_expected(orc, out), t)
+        total += out["reset_count"]
+    assert total > 0
