@@ -446,11 +446,14 @@ class Go2Oracle:
 
         # compute_reward (legged_robot.py:216-237)
         rew = torch.zeros(N)
+        mag = torch.zeros(N)          # sum of |terms|: the scale rounding errors of the (cancelling) sum live on
         for name in self.active:
             i = REWARD_INDEX[name]
             r = self._reward(name) * p.reward_scales[i]
             rew += r
+            mag += r.abs()
             st["episode_sums"][i] += r
+        o["rew_terms_abs"] = mag
         if p.only_positive_rewards:
             rew = torch.clip(rew, min=0.)
         ti = REWARD_INDEX["termination"]

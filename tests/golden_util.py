@@ -119,14 +119,16 @@ FLOAT_MAP = {
 }
 
 
-def rel_err(a, b):
-    """max |a-b| / max(|b|, s): relative to the element, floored at the tensor's own scale s (rms, >= 1e-6)
-    so that exact zeros / cancellations do not make the ratio meaningless."""
+def rel_err(a, b, scale=None):
+    """max |a-b| / max(|b|, s): relative to the element, floored at a scale s so that exact zeros and
+    cancellations do not make the ratio meaningless.  s = the tensor's own rms (>= 1e-6) by default;
+    for a sum of signed terms (rew_buf) pass `scale` = sum of |terms| per element, the magnitude its
+    rounding errors are proportional to."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     if a.size == 0:
         return 0.0
-    s = max(float(np.sqrt(np.mean(b * b))), 1e-6)
+    s = max(float(np.sqrt(np.mean(b * b))), 1e-6) if scale is None else np.maximum(np.asarray(scale, dtype=np.float64), 1e-6)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), s)))
 
 
@@ -140,7 +142,7 @@ def check_step(bufs, exp, t, rtol=RTOL, report=None):
         a, b = get(bname), exp[gname]
         assert a.shape == b.shape, (gname, a.shape, b.shape)
         assert np.isfinite(a).all(), f"{gname} step {t}: non-finite values"
-        worst[gname] = rel_err(a, b)
+        worst[gname] = rel_err(a, b, scale=exp.get("rew_terms_abs") if gname == "rew_buf" else None)
     rpy = get("rpy")
     for i, k in enumerate(("roll", "pitch", "yaw")):
         worst[k] = rel_err(rpy[:, i], exp[k])
@@ -194,6 +196,7 @@ def oracle_expected(orc, out):
         e["extras_episode"].pop(len(st["extras_episode"]) - 1, None)
     e["extras/time_outs"] = st["extras_time_outs"].numpy()
     e["n_reset"] = out["reset_count"]
+    e["rew_terms_abs"] = out["rew_terms_abs"].numpy()
     return e
 
 
