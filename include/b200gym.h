@@ -276,6 +276,72 @@ int b200_store_step_scalars(const float* rew, const uint8_t* reset, const uint8_
                             const float* values, float gamma, float* rewards_t, uint8_t* dones_t,
                             int N, void* stream);
 
+/* ---- learner: fused Linear layers on tensor cores (csrc/linear_kernels.cu) ----------------------
+ * Replace the nn.Linear (+ nn.ELU) stacks of ActorCritic / MlpEstimator / ScanEncoder /
+ * PrivilegedEncoder / AdaptationEncoder (actor_critic.py:84-108, support_networks.py:9-175) and
+ * their autograd backward.  Row-major fp32; every leading dimension a multiple of 4 floats and
+ * X / W / dY pointers 16-byte aligned.  act: 0 none, 1 ELU.  precise: 0 = TF32 (the reference's
+ * matmul precision on GPU, train.py:39), 1 = 3xTF32 (fp32-accurate, used for parity). */
+int b200_linear_forward(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                        int M, int N, int K, int act, int precise, void* stream);
+/* dX[M,K] (+)= (dY[M,N] . W[N,K]) * elu'(Yprev[M,K])   (Yprev may be NULL) */
+int b200_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX,
+                      int lddx, int M, int N, int K, int accumulate, int precise, void* stream);
+/* dW[N,K] += dY[M,N]^T . X[M,K] ;  db[N] += column sums of dY   (db may be NULL) */
+int b200_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int ldw, float* db, int M, int N,
+                      int K, int precise, void* stream);
+
+/* ---- learner: storage traffic, heads, optimiser (csrc/learner_kernels.cu) ---------------------- */
+typedef struct B200CopySeg {
+  const float* src;
+  float* dst;
+  int32_t width, src_ld, dst_ld, _pad;
+} B200CopySeg;
+/* RolloutStorage.add_transitions' copies (rollout_storage.py:87-105): up to 8 strided 2-D copies, one launch. */
+int b200_copy_segments(const B200CopySeg* segs /* host */, int nseg, int rows, void* stream);
+/* mini_batch_generator's gathers (rollout_storage.py:134-181): dst[i,:] = src[idx[i],:] */
+int b200_gather_rows(const float* src, int src_ld, const int64_t* idx, float* dst, int dst_ld, int width, int64_t rows, void* stream);
+int b200_gather_bytes(const uint8_t* src, const int64_t* idx, uint8_t* dst, int64_t rows, void* stream);
+/* ActorCritic.act + get_actions_log_prob (actor_critic.py:190-226): a = mu + std*z, z keyed by (seed, step, env, action). */
+int b200_sample_actions(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t step, float* actions, float* logp,
+                        float* mu_out, float* sigma_out, int N, int A, void* stream);
+
+/* PPO.update's loss head, forward + backward (ppo.py:199-270). `sums` receives SUMS over the minibatch of
+ * surrogate, value, regularisation and entropy terms (divide by M for the reference's means). */
+typedef struct B200PpoLossArgs {
+  const float* mu;        int32_t ldmu;
+  const float* std;
+  const float* actions;
+  const float* old_logp;
+  const float* adv;
+  const float* returns;
+  const float* target_values;
+  const float* value;     int32_t ldv;
+  const float* latent_p;  int32_t ldlp;
+  const float* latent_a;  int32_t ldla;
+  float* dmu;             int32_t lddmu;
+  float* dvalue;          int32_t lddv;
+  float* dlatent_p;       int32_t lddlp;
+  float* dstd;
+  float* sums;
+  int32_t M, A, L;
+  float clip, value_coef, entropy_coef, reg_coef;
+  int32_t use_clipped_value_loss;
+  const float* reg_coef_dev;   /* if non-NULL, the ROA coefficient is read from device memory (graph replay) */
+} B200PpoLossArgs;
+int b200_ppo_loss(const B200PpoLossArgs* args /* host */, void* stream);
+/* estimator loss mean ||pred - target||_2^2 (ppo.py:224-226) and DAgger loss mean ||target - pred||_2 (ppo.py:330-333) */
+int b200_mse_rows_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* sum, int M, int D, void* stream);
+int b200_l2_rows_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* sum, int M, int D, void* stream);
+int b200_elu_backward(float* dY, int lddy, const float* Y, int ldy, int M, int N, void* stream);
+/* clip_grad_norm_ + Adam.step on flat buffers (ppo.py:228-231, :273-276, :336-339); zeroes `grads`.
+ * grad_scale = 1/world_size after the NCCL sum all-reduce of `grads`.
+ * `state` = 8 doubles on the device: [0] scratch, [1] step, [2] beta1^step, [3] beta2^step, [4] lr -- advanced
+ * by the call itself so a captured CUDA graph replays correctly (initialise to {0, 0, 1, 1, lr}). */
+int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
+                   float grad_scale, float max_norm, float beta1, float beta2, float eps, void* stream);
+int b200_fill(float* p, float value, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,37 @@ SYMBOLS = {
     "b200_gae_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "b200_compute_returns": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "b200_store_step_scalars": (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_linear_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 5 + [C.c_void_p]),
+    "b200_linear_dgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 5 + [C.c_void_p]),
+    "b200_linear_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "b200_copy_segments": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    "b200_gather_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200_sample_actions": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p]),
+    "b200_ppo_loss": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_mse_rows_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200_l2_rows_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200_elu_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b200_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p]),
+    "b200_fill": (C.c_int, [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]),
 }
+
+
+class CopySeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("src_ld", C.c_int32), ("dst_ld", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class PpoLossArgs(C.Structure):
+    _fields_ = [("mu", C.c_void_p), ("ldmu", C.c_int32), ("std", C.c_void_p), ("actions", C.c_void_p), ("old_logp", C.c_void_p),
+                ("adv", C.c_void_p), ("returns", C.c_void_p), ("target_values", C.c_void_p), ("value", C.c_void_p), ("ldv", C.c_int32),
+                ("latent_p", C.c_void_p), ("ldlp", C.c_int32), ("latent_a", C.c_void_p), ("ldla", C.c_int32),
+                ("dmu", C.c_void_p), ("lddmu", C.c_int32), ("dvalue", C.c_void_p), ("lddv", C.c_int32),
+                ("dlatent_p", C.c_void_p), ("lddlp", C.c_int32), ("dstd", C.c_void_p), ("sums", C.c_void_p),
+                ("M", C.c_int32), ("A", C.c_int32), ("L", C.c_int32), ("clip", C.c_float), ("value_coef", C.c_float),
+                ("entropy_coef", C.c_float), ("reg_coef", C.c_float), ("use_clipped_value_loss", C.c_int32),
+                ("reg_coef_dev", C.c_void_p)]
 
 _lib = None
 

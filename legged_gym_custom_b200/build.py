@@ -21,6 +21,7 @@ UNITS = [
     ("env_kernels.cu", ["-fmad=false"]),
     ("gae_kernels.cu", ["-fmad=false"]),
     ("learner_kernels.cu", []),
+    ("linear_kernels.cu", []),
     ("mlp_tcgen05.cu", []),
 ]
 

@@ -1,0 +1,384 @@
+// Learner-side non-GEMM kernels (SURVEY.md §2.1 K7 / K8 and the storage traffic of a14 / a18).
+//
+//   copy_segments_kernel   strided 2-D copies, several (src,dst) pairs per launch   rollout_storage.py:87-105
+//   gather_rows_kernel     dst[i,:] = src[idx[i],:]  (the ONE permutation of an iteration, a18)
+//   sample_actions_kernel  a = mu + std * z (keyed Philox + Box-Muller), log-prob    actor_critic.py:190-226
+//   ppo_loss_kernel        surrogate / clipped value / entropy / ROA regulariser, fwd + bwd   ppo.py:199-270
+//   mse_rows_loss_kernel   estimator loss  mean ||pred - target||_2^2, fwd + bwd               ppo.py:224-226
+//   l2_rows_loss_kernel    DAgger loss     mean ||target - pred||_2,   fwd + bwd               ppo.py:330-333
+//   sumsq / clip_adam      global grad-norm clip fused with the Adam step on flat buffers      ppo.py:228-231, :273-276
+//
+// All are streaming, HBM/latency-bound kernels; reductions use warp shuffles + one atomic per CTA.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// CTA-wide sum of up to 4 values; result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void cta_sum(float (&v)[NV], float* smem /* [NV][32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = warp_sum_f(v[i]);
+    if (lane == 0) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float t = lane < nw ? smem[i * 32 + lane] : 0.0f;
+      v[i] = warp_sum_f(t);
+    }
+  }
+}
+
+}  // namespace
+
+struct CopyArgs {
+  B200CopySeg seg[8];
+  int nseg, rows;
+};
+
+__global__ void __launch_bounds__(256) copy_segments_kernel(const __grid_constant__ CopyArgs a) {
+  const B200CopySeg s = a.seg[blockIdx.y];
+  const bool v4 = (s.width % 4 == 0) && (s.src_ld % 4 == 0) && (s.dst_ld % 4 == 0) && (((uintptr_t)s.src | (uintptr_t)s.dst) % 16 == 0);
+  if (v4) {
+    const int w4 = s.width / 4;
+    const int64_t total = (int64_t)a.rows * w4;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+      const int64_t r = i / w4;
+      const int c = (int)(i % w4);
+      reinterpret_cast<float4*>(s.dst + r * s.dst_ld)[c] = reinterpret_cast<const float4*>(s.src + r * s.src_ld)[c];
+    }
+  } else {
+    const int64_t total = (int64_t)a.rows * s.width;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+      const int64_t r = i / s.width;
+      const int c = (int)(i % s.width);
+      s.dst[r * s.dst_ld + c] = s.src[r * s.src_ld + c];
+    }
+  }
+}
+
+// one warp per destination row
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, int src_ld, const int64_t* __restrict__ idx, float* __restrict__ dst, int dst_ld,
+                   int width, int64_t rows) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = src + idx[row] * src_ld;
+  float* d = dst + row * dst_ld;
+  if ((width % 4 == 0) && (src_ld % 4 == 0) && (dst_ld % 4 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0)) {
+    for (int c = lane; c < width / 4; c += 32) reinterpret_cast<float4*>(d)[c] = __ldg(reinterpret_cast<const float4*>(s) + c);
+  } else {
+    for (int c = lane; c < width; c += 32) d[c] = s[c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_bytes_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ idx, uint8_t* __restrict__ dst, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < rows) dst[i] = src[idx[i]];
+}
+
+// actions ~ Normal(mu, std): z from two keyed uniforms (Box-Muller); log_prob summed over actions.
+__global__ void __launch_bounds__(256)
+sample_actions_kernel(const float* __restrict__ mu, int ldmu, const float* __restrict__ std, uint64_t seed, uint32_t step,
+                      float* __restrict__ actions, float* __restrict__ logp, float* __restrict__ mu_out, float* __restrict__ sigma_out,
+                      int N, int A) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= N) return;
+  float lp = 0.0f;
+  for (int a = 0; a < A; ++a) {
+    const float u1 = ((float)(keyed_u32(seed, SITE_ACTION_NOISE, step, e, 2 * a) >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float u2 = u32_to_uniform(keyed_u32(seed, SITE_ACTION_NOISE, step, e, 2 * a + 1));
+    const float z = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+    const float m = mu[(int64_t)e * ldmu + a], s = std[a];
+    const float act = m + s * z;
+    actions[(int64_t)e * A + a] = act;
+    if (mu_out) mu_out[(int64_t)e * A + a] = m;
+    if (sigma_out) sigma_out[(int64_t)e * A + a] = s;
+    const float d = act - m;
+    lp += -(d * d) / (2.0f * s * s) - logf(s) - 0.9189385332046727f;
+  }
+  logp[e] = lp;
+}
+
+typedef B200PpoLossArgs PpoLossArgs;
+
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const __grid_constant__ PpoLossArgs p) {
+  __shared__ float red[4 * 32];
+  __shared__ float dstd_s[16];
+  if (threadIdx.x < 16) dstd_s[threadIdx.x] = 0.0f;
+  __syncthreads();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float invM = 1.0f / (float)p.M;
+  float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (i < p.M) {
+    // log-prob and entropy of Normal(mu, std) (torch.distributions.Normal)
+    float lp = 0.0f, ent = 0.0f;
+    for (int a = 0; a < p.A; ++a) {
+      const float s = p.std[a], d = p.actions[(int64_t)i * p.A + a] - p.mu[(int64_t)i * p.ldmu + a];
+      lp += -(d * d) / (2.0f * s * s) - logf(s) - 0.9189385332046727f;
+      ent += 1.4189385332046727f + logf(s);
+    }
+    const float adv = p.adv[i];
+    const float ratio = expf(lp - p.old_logp[i]);
+    const float s1 = -adv * ratio;
+    const float rc = fminf(fmaxf(ratio, 1.0f - p.clip), 1.0f + p.clip);
+    const float s2 = -adv * rc;
+    part[0] = fmaxf(s1, s2);
+    const bool inside = (ratio >= 1.0f - p.clip) && (ratio <= 1.0f + p.clip);
+    // d max(s1,s2)/d logp: both branches carry -adv*ratio inside the clip range; outside only s1 does
+    const float dlp = (inside || s1 > s2) ? (-adv * ratio) * invM : 0.0f;
+    float dsig_entropy = -p.entropy_coef * invM;
+    for (int a = 0; a < p.A; ++a) {
+      const float s = p.std[a], d = p.actions[(int64_t)i * p.A + a] - p.mu[(int64_t)i * p.ldmu + a];
+      p.dmu[(int64_t)i * p.lddmu + a] = dlp * d / (s * s);
+      const float dsig = dlp * (d * d - s * s) / (s * s * s) + dsig_entropy / s;
+      atomicAdd(&dstd_s[a], dsig);
+    }
+    // value loss (ppo.py:256-264)
+    const float v = p.value[(int64_t)i * p.ldv], R = p.returns[i];
+    float dv;
+    if (p.use_clipped_value_loss) {
+      const float tv = p.target_values[i];
+      const float dvt = v - tv;
+      const float vc = tv + fminf(fmaxf(dvt, -p.clip), p.clip);
+      const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+      part[1] = fmaxf(l1, l2);
+      const bool in_v = (dvt >= -p.clip) && (dvt <= p.clip);
+      const float d1 = 2.0f * (v - R), d2 = in_v ? 2.0f * (vc - R) : 0.0f;
+      dv = l1 > l2 ? d1 : (l1 < l2 ? d2 : 0.5f * (d1 + d2));
+    } else {
+      part[1] = (R - v) * (R - v);
+      dv = 2.0f * (v - R);
+    }
+    p.dvalue[(int64_t)i * p.lddv] = p.value_coef * dv * invM;
+    // ROA regulariser: mean ||latent_p - latent_a||_2 (ppo.py:216)
+    float n2 = 0.0f;
+    for (int l = 0; l < p.L; ++l) {
+      const float d = p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l];
+      n2 += d * d;
+    }
+    const float nrm = sqrtf(n2);
+    part[2] = nrm;
+    const float reg_coef = p.reg_coef_dev ? p.reg_coef_dev[0] : p.reg_coef;
+    const float g = nrm > 0.0f ? reg_coef * invM / nrm : 0.0f;
+    for (int l = 0; l < p.L; ++l)
+      p.dlatent_p[(int64_t)i * p.lddlp + l] = g * (p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l]);
+    part[3] = ent;
+  }
+  cta_sum<4>(part, red);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 4; ++k) atomicAdd(p.sums + k, part[k]);
+  if (threadIdx.x < p.A) atomicAdd(p.dstd + threadIdx.x, dstd_s[threadIdx.x]);
+}
+
+// loss = mean_i ||pred_i - target_i||_2^2 ; dpred = 2 (pred - target) / M      (estimator, ppo.py:224-226)
+__global__ void __launch_bounds__(256)
+mse_rows_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ target, int ldt, float* __restrict__ dpred,
+                     int lddp, float* __restrict__ sum, int M, int D) {
+  __shared__ float red[32];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  float part[1] = {0.0f};
+  if (i < M) {
+    for (int d = 0; d < D; ++d) {
+      const float e = pred[(int64_t)i * ldp + d] - target[(int64_t)i * ldt + d];
+      part[0] += e * e;
+      dpred[(int64_t)i * lddp + d] = 2.0f * e / (float)M;
+    }
+  }
+  cta_sum<1>(part, red);
+  if (threadIdx.x == 0) atomicAdd(sum, part[0]);
+}
+
+// loss = mean_i ||target_i - pred_i||_2 ; dpred = -(target - pred) / (||.|| M)   (DAgger, ppo.py:330-333)
+__global__ void __launch_bounds__(256)
+l2_rows_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ target, int ldt, float* __restrict__ dpred,
+                    int lddp, float* __restrict__ sum, int M, int D) {
+  __shared__ float red[32];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  float part[1] = {0.0f};
+  if (i < M) {
+    float n2 = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float e = target[(int64_t)i * ldt + d] - pred[(int64_t)i * ldp + d];
+      n2 += e * e;
+    }
+    const float nrm = sqrtf(n2);
+    part[0] = nrm;
+    const float g = nrm > 0.0f ? 1.0f / (nrm * (float)M) : 0.0f;
+    for (int d = 0; d < D; ++d) dpred[(int64_t)i * lddp + d] = -g * (target[(int64_t)i * ldt + d] - pred[(int64_t)i * ldp + d]);
+  }
+  cta_sum<1>(part, red);
+  if (threadIdx.x == 0) atomicAdd(sum, part[0]);
+}
+
+// dY *= elu'(Y) in place, for heads whose last layer has an activation (AdaptationEncoder.fc_final)
+__global__ void __launch_bounds__(256)
+elu_backward_kernel(float* __restrict__ dY, int lddy, const float* __restrict__ Y, int ldy, int M, int N) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int64_t r = i / N;
+  const int c = (int)(i % N);
+  const float y = Y[r * ldy + c];
+  dY[r * lddy + c] *= (y > 0.0f ? 1.0f : y + 1.0f);
+}
+
+// Optimiser state block (device, doubles) so that a captured CUDA graph can be replayed step after step:
+//   [0] sum of squared gradients (scratch)  [1] step  [2] beta1^step  [3] beta2^step  [4] lr
+__global__ void adam_advance_kernel(double* __restrict__ state, double beta1, double beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    state[0] = 0.0;
+    state[1] += 1.0;
+    state[2] *= beta1;
+    state[3] *= beta2;
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ state) {
+  __shared__ float red[32];
+  float part[1] = {0.0f};
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) part[0] += g[i] * g[i];
+  cta_sum<1>(part, red);
+  if (threadIdx.x == 0) atomicAdd(state, (double)part[0]);
+}
+
+// torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (default, non-amsgrad, weight_decay 0) on flat buffers.
+// `grad_scale` pre-multiplies the gradient (1/world_size after an NCCL sum all-reduce); the gradient
+// buffer is zeroed for the next accumulation.
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                 const double* __restrict__ state, float grad_scale, float max_norm, float beta1, float beta2, float eps) {
+  const float total_norm = (float)sqrt(state[0]) * grad_scale;
+  float coef = max_norm / (total_norm + 1e-6f);
+  coef = (coef > 1.0f ? 1.0f : coef) * grad_scale;
+  const float bc1 = (float)(1.0 - state[2]), bc2_sqrt = (float)sqrt(1.0 - state[3]);
+  const float step_size = (float)state[4] / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    g[i] = 0.0f;
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float value, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = value;
+}
+
+extern "C" {
+
+int b200_copy_segments(const B200CopySeg* segs, int nseg, int rows, void* stream) {
+  B200_CHECK_ARG(segs && nseg > 0 && nseg <= 8 && rows > 0, "b200_copy_segments: need 1..8 segments and rows > 0");
+  CopyArgs a{};
+  a.nseg = nseg;
+  a.rows = rows;
+  int64_t maxw = 0;
+  for (int i = 0; i < nseg; ++i) {
+    B200_CHECK_ARG(segs[i].src && segs[i].dst && segs[i].width > 0 && segs[i].src_ld >= segs[i].width && segs[i].dst_ld >= segs[i].width,
+                   "b200_copy_segments: bad segment %d", i);
+    a.seg[i] = segs[i];
+    maxw = segs[i].width > maxw ? segs[i].width : maxw;
+  }
+  int64_t work = ((int64_t)rows * maxw / 4 + 255) / 256;
+  int bx = (int)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
+  copy_segments_kernel<<<dim3(bx, nseg), 256, 0, (cudaStream_t)stream>>>(a);
+  B200_CHECK_LAUNCH("copy_segments_kernel");
+  return 0;
+}
+
+int b200_gather_rows(const float* src, int src_ld, const int64_t* idx, float* dst, int dst_ld, int width, int64_t rows, void* stream) {
+  B200_CHECK_ARG(src && idx && dst && width > 0 && rows > 0 && src_ld >= width && dst_ld >= width, "b200_gather_rows: bad argument");
+  gather_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(src, src_ld, idx, dst, dst_ld, width, rows);
+  B200_CHECK_LAUNCH("gather_rows_kernel");
+  return 0;
+}
+
+int b200_gather_bytes(const uint8_t* src, const int64_t* idx, uint8_t* dst, int64_t rows, void* stream) {
+  B200_CHECK_ARG(src && idx && dst && rows > 0, "b200_gather_bytes: bad argument");
+  gather_bytes_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, rows);
+  B200_CHECK_LAUNCH("gather_bytes_kernel");
+  return 0;
+}
+
+int b200_sample_actions(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t step, float* actions, float* logp,
+                        float* mu_out, float* sigma_out, int N, int A, void* stream) {
+  B200_CHECK_ARG(mu && std && actions && logp && N > 0 && A > 0 && A <= 16 && ldmu >= A, "b200_sample_actions: bad argument");
+  sample_actions_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, seed, (uint32_t)step, actions, logp, mu_out,
+                                                                         sigma_out, N, A);
+  B200_CHECK_LAUNCH("sample_actions_kernel");
+  return 0;
+}
+
+int b200_ppo_loss(const PpoLossArgs* a, void* stream) {
+  B200_CHECK_ARG(a && a->M > 0 && a->A > 0 && a->A <= 16 && a->L > 0, "b200_ppo_loss: bad sizes");
+  B200_CHECK_ARG(a->mu && a->std && a->actions && a->old_logp && a->adv && a->returns && a->target_values && a->value && a->latent_p &&
+                     a->latent_a && a->dmu && a->dvalue && a->dlatent_p && a->dstd && a->sums,
+                 "b200_ppo_loss: null pointer");
+  ppo_loss_kernel<<<(a->M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+  B200_CHECK_LAUNCH("ppo_loss_kernel");
+  return 0;
+}
+
+int b200_mse_rows_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* sum, int M, int D,
+                       void* stream) {
+  B200_CHECK_ARG(pred && target && dpred && sum && M > 0 && D > 0, "b200_mse_rows_loss: bad argument");
+  mse_rows_loss_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pred, ldp, target, ldt, dpred, lddp, sum, M, D);
+  B200_CHECK_LAUNCH("mse_rows_loss_kernel");
+  return 0;
+}
+
+int b200_l2_rows_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* sum, int M, int D,
+                      void* stream) {
+  B200_CHECK_ARG(pred && target && dpred && sum && M > 0 && D > 0, "b200_l2_rows_loss: bad argument");
+  l2_rows_loss_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pred, ldp, target, ldt, dpred, lddp, sum, M, D);
+  B200_CHECK_LAUNCH("l2_rows_loss_kernel");
+  return 0;
+}
+
+int b200_elu_backward(float* dY, int lddy, const float* Y, int ldy, int M, int N, void* stream) {
+  B200_CHECK_ARG(dY && Y && M > 0 && N > 0, "b200_elu_backward: bad argument");
+  const int64_t n = (int64_t)M * N;
+  elu_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dY, lddy, Y, ldy, M, N);
+  B200_CHECK_LAUNCH("elu_backward_kernel");
+  return 0;
+}
+
+int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double* state, float grad_scale,
+                   float max_norm, float beta1, float beta2, float eps, void* stream) {
+  B200_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && n > 0, "b200_clip_adam: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_advance_kernel<<<1, 32, 0, st>>>(state, (double)beta1, (double)beta2);
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 4 ? 148 * 4 : blocks);
+  sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, state);
+  B200_CHECK_LAUNCH("sumsq_kernel");
+  clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, grad_scale, max_norm, beta1, beta2, eps);
+  B200_CHECK_LAUNCH("clip_adam_kernel");
+  return 0;
+}
+
+int b200_fill(float* p, float value, int64_t n, void* stream) {
+  B200_CHECK_ARG(p && n > 0, "b200_fill: bad argument");
+  int blocks = (int)((n + 255) / 256);
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, value, n);
+  B200_CHECK_LAUNCH("fill_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+"""`RolloutStorage` and `PPO`: drop-ins for rsl_rl/storage/rollout_storage.py and
+rsl_rl/algorithms/ppo.py with the tensor math done by libb200gym.so.
+
+Same constructor arguments, methods and public tensor attributes as the reference:
+`PPO.init_storage / act / process_env_step / compute_returns / update / update_dagger`,
+`RolloutStorage.add_transitions / clear / compute_returns / mini_batch_generator` and
+`.observations / .values / .returns / .advantages / ...`.
+
+What changes underneath:
+  * storage rows are written by one fused multi-segment copy per env step; 29- and 3-wide tensors
+    are kept 32- / 4-wide internally (16-byte rows) and exposed as sliced views;
+  * compute_returns is the GAE scan + normalisation kernels;
+  * the reference draws ONE permutation per update and reuses it for all epochs
+    (rollout_storage.py:142, :159-164), so the storage is gathered ONCE per update into permuted,
+    contiguous minibatch slabs -- every epoch then reads dense slices, and the actor-input slab
+    [T*N, 628] doubles as the concat buffer ([obs | latent | scan latent | estimated obs]);
+  * forward / backward of all networks, the loss head, clip + Adam are kernel launches with no host
+    synchronisation inside an update; the four logged means come back in one copy at the end.
+There is no CPU fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .networks import ActorCritic, MlpEstimator, Workspace, _p, ceil4, chain_backward
+
+
+class RolloutStorage:
+    class Transition:
+        def __init__(self):
+            self.clear()
+
+        def clear(self):
+            self.observations = self.privileged_observations = self.critic_observations = None
+            self.true_estimated_observations = self.scan_observations = None
+            self.actions = self.rewards = self.dones = self.values = None
+            self.actions_log_prob = self.action_mean = self.action_sigma = None
+
+    def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, critic_obs_shape,
+                 estimated_obs_shape, scan_obs_shape, actions_shape, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RolloutStorage lives on the GPU: the hot path has no CPU fallback")
+        self.lib = _lib.lib()
+        T, N = num_transitions_per_env, num_envs
+        self.num_transitions_per_env, self.num_envs = T, N
+        self.obs_shape, self.privileged_obs_shape, self.critic_obs_shape = obs_shape, privileged_obs_shape, critic_obs_shape
+        self.estimated_obs_shape, self.actions_shape = estimated_obs_shape, actions_shape
+        self.d_obs, self.d_priv, self.d_crit = obs_shape[0], privileged_obs_shape[0], critic_obs_shape[0]
+        self.d_est, self.d_scan, self.d_act = estimated_obs_shape[0], scan_obs_shape[0], actions_shape[0]
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=self.device)
+        self.observations = z(T, N, self.d_obs)
+        self._priv = z(T, N, ceil4(self.d_priv))
+        self.critic_observations = z(T, N, self.d_crit)
+        self._est = z(T, N, ceil4(self.d_est))
+        self.scan_observations = z(T, N, self.d_scan)
+        self.rewards, self.values, self.returns, self.advantages, self.actions_log_prob = (z(T, N, 1) for _ in range(5))
+        self.actions, self.mu, self.sigma = z(T, N, self.d_act), z(T, N, self.d_act), z(T, N, self.d_act)
+        self.dones = z(T, N, 1, dt=torch.uint8)
+        self.saved_hidden_states_a = self.saved_hidden_states_c = None
+        self.step = 0
+        self._gae_scratch = torch.zeros(max(16, int(self.lib.b200_gae_scratch_bytes(T, N))), dtype=torch.uint8, device=self.device)
+
+    @property
+    def privileged_observations(self):
+        return self._priv[:, :, :self.d_priv]
+
+    @property
+    def true_estimated_observations(self):
+        return self._est[:, :, :self.d_est]
+
+    def add_transitions(self, transition):
+        """rollout_storage.py:87-105 for callers that hold a Transition (PPO writes rows directly)."""
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        t = self.step
+        self.observations[t].copy_(transition.observations)
+        self._priv[t, :, :self.d_priv].copy_(transition.privileged_observations)
+        self.critic_observations[t].copy_(transition.critic_observations)
+        self._est[t, :, :self.d_est].copy_(transition.true_estimated_observations)
+        self.scan_observations[t].copy_(transition.scan_observations)
+        self.actions[t].copy_(transition.actions)
+        self.rewards[t].copy_(transition.rewards.view(-1, 1))
+        self.dones[t].copy_(transition.dones.view(-1, 1))
+        self.values[t].copy_(transition.values)
+        self.actions_log_prob[t].copy_(transition.actions_log_prob.view(-1, 1))
+        self.mu[t].copy_(transition.action_mean)
+        self.sigma[t].copy_(transition.action_sigma)
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam):
+        """rollout_storage.py:110-124 (GAE reverse scan + advantage normalisation)."""
+        lv = last_values.contiguous()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(self.lib.b200_compute_returns(p(self.rewards), p(self.dones), p(self.values), p(lv), p(self.returns), p(self.advantages),
+                                                 self.num_transitions_per_env, self.num_envs, gamma, lam, p(self._gae_scratch),
+                                                 _lib.stream_ptr()))
+
+    def get_statistics(self):
+        done = self.dones.clone()
+        done[-1] = 1
+        flat = done.permute(1, 0, 2).reshape(-1, 1)
+        idx = torch.cat((flat.new_tensor([-1], dtype=torch.int64), flat.nonzero(as_tuple=False)[:, 0]))
+        return (idx[1:] - idx[:-1]).float().mean(), self.rewards.mean()
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices=None):
+        """rollout_storage.py:134-181 (same tuple).  PPO.update does not go through this generator: it uses the
+        permuted slabs; this is kept for API compatibility and for the tests."""
+        batch = self.num_envs * self.num_transitions_per_env
+        mb = batch // num_mini_batches
+        if indices is None:
+            indices = torch.randperm(num_mini_batches * mb, device=self.device)
+        f = lambda t: t.flatten(0, 1)
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                idx = indices[i * mb:(i + 1) * mb]
+                yield (f(self.observations)[idx], f(self.privileged_observations)[idx], f(self.critic_observations)[idx],
+                       f(self.true_estimated_observations)[idx], f(self.scan_observations)[idx], f(self.actions)[idx],
+                       f(self.values)[idx], f(self.advantages)[idx], f(self.returns)[idx], f(self.actions_log_prob)[idx],
+                       f(self.mu)[idx], f(self.sigma)[idx], (None, None), None)
+
+
+class _AdamFacade:
+    """Minimal torch.optim-like surface (`state_dict`, `load_state_dict`, `param_groups`) over a FlatGroup."""
+
+    def __init__(self, group, lr):
+        self.group = group
+        self.param_groups = [{"lr": lr}]
+
+    def state_dict(self):
+        g = self.group
+        return {"flat_exp_avg": g.exp_avg.clone(), "flat_exp_avg_sq": g.exp_avg_sq.clone(), "adam_state": g.state.clone(),
+                "param_groups": self.param_groups}
+
+    def load_state_dict(self, sd):
+        g = self.group
+        if "flat_exp_avg" not in sd:
+            raise ValueError("optimizer state of a reference checkpoint is per-tensor; load the model weights and restart the "
+                             "optimiser (the reference itself drops the estimator / adaptation optimisers on resume)")
+        g.exp_avg.copy_(sd["flat_exp_avg"])
+        g.exp_avg_sq.copy_(sd["flat_exp_avg_sq"])
+        g.state.copy_(sd["adam_state"])
+
+
+class PPO:
+    def __init__(self, actor_critic, estimator, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998,
+                 lam=0.95, value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, estimator_learning_rate=1e-3,
+                 max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, resume=False,
+                 device="cuda:0", seed=0, process_group=None):
+        if schedule != "fixed":
+            raise NotImplementedError("schedule='adaptive' needs a host decision per minibatch; every go2 config uses 'fixed'")
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        self.desired_kl, self.schedule = desired_kl, schedule
+        self.learning_rate, self.estimator_learning_rate = learning_rate, estimator_learning_rate
+        # ROA schedule (ppo.py:40-43)
+        self.start_val, self.end_val, self.start_step, self.duration = 0.0, 0.05, 5000, 10000
+        if resume:
+            self.start_val, self.end_val, self.start_step, self.duration = 0.0, 0.1, 0, 1
+        self.actor_critic, self.estimator = actor_critic, estimator
+        self.storage = None
+        ac = actor_critic
+        ac.main.set_lr(learning_rate)
+        ac.adapt.set_lr(learning_rate)
+        estimator.group.set_lr(estimator_learning_rate)
+        self.optimizer = _AdamFacade(ac.main, learning_rate)
+        self.adaptation_optimizer = _AdamFacade(ac.adapt, learning_rate)
+        self.estimator_optimizer = _AdamFacade(estimator.group, estimator_learning_rate)
+        self.transition = RolloutStorage.Transition()
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef, self.gamma, self.lam = value_loss_coef, entropy_coef, gamma, lam
+        self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
+        self.total_updates = 0.0
+        self.seed = seed
+        self.act_counter = 0
+        self.process_group = process_group            # torch.distributed group for the gradient all-reduce, or None
+        self.world_size = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self._perm_gen = torch.Generator(device=self.device).manual_seed(seed + 12345)
+        self.launches = 0
+
+    # ---- storage ------------------------------------------------------------------------------------
+    def init_storage(self, num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
+                     estimated_obs_shape, scan_obs_shape, action_shape):
+        self.storage = s = RolloutStorage(num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
+                                          estimated_obs_shape, scan_obs_shape, action_shape, self.device)
+        ac = self.actor_critic
+        T, N = num_transitions_per_env, num_envs
+        self.batch = T * N
+        self.mb = self.batch // self.num_mini_batches
+        z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.device)
+        # permuted slabs (one gather per update); +64 floats of slack after the actor-input slab for the conv windows
+        self.p_actor_in = z(self.batch + 1, ac.ld_actor_in)
+        self.p_priv, self.p_crit, self.p_scan = z(self.batch, ceil4(s.d_priv)), z(self.batch, s.d_crit), z(self.batch, s.d_scan)
+        self.p_est, self.p_act = z(self.batch, ceil4(s.d_est)), z(self.batch, s.d_act)
+        self.p_val, self.p_ret, self.p_logp, self.p_adv = z(self.batch), z(self.batch), z(self.batch), z(self.batch)
+        self.roll_ws = Workspace(self.device)          # rollout-time activations (M = N)
+        self.upd_ws = Workspace(self.device)           # update-time activations  (M = minibatch)
+        self.loss_sums = z(8)
+        self.reg_coef_dev = z(1)
+        self.last_values = z(N, 1)
+
+    def test_mode(self):
+        self.actor_critic.test()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    # ---- rollout --------------------------------------------------------------------------------------
+    def _copy_segments(self, segs, rows):
+        arr = (_lib.CopySeg * len(segs))()
+        for i, (src, sld, dst, dld, w) in enumerate(segs):
+            arr[i].src, arr[i].dst, arr[i].width, arr[i].src_ld, arr[i].dst_ld = src, dst, w, sld, dld
+        _lib.check(self.lib.b200_copy_segments(arr, len(segs), rows, _lib.stream_ptr()))
+
+    def act(self, obs, privileged_obs, critic_obs, true_estimated_obs, scan_obs, adaptation_mode=False):
+        """ppo.py:129-153 fused with RolloutStorage.add_transitions' observation copies."""
+        s, ac, est = self.storage, self.actor_critic, self.estimator
+        if s.step >= s.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        t, N, ws = s.step, s.num_envs, self.roll_ws
+        ld = ac.ld_actor_in
+        x = ws.get("actor_in", N, ld)
+        obs, privileged_obs, critic_obs = obs.contiguous(), privileged_obs.contiguous(), critic_obs.contiguous()
+        true_estimated_obs, scan_obs = true_estimated_obs.contiguous(), scan_obs.contiguous()
+        self._copy_segments([
+            (_p(obs), s.d_obs, _p(s.observations[t]), s.d_obs, s.d_obs),
+            (_p(obs), s.d_obs, _p(x), ld, s.d_obs),
+            (_p(privileged_obs), s.d_priv, _p(s._priv[t]), s._priv.shape[2], s.d_priv),
+            (_p(critic_obs), s.d_crit, _p(s.critic_observations[t]), s.d_crit, s.d_crit),
+            (_p(true_estimated_obs), s.d_est, _p(s._est[t]), s._est.shape[2], s.d_est),
+            (_p(scan_obs), s.d_scan, _p(s.scan_observations[t]), s.d_scan, s.d_scan),
+        ], N)
+        # estimated obs -> actor input (the rollout acts on the ESTIMATE, ppo.py:134-137)
+        est.fwd(ws, _p(x), ld, _p(x, ac.col_est), ld, N)
+        if adaptation_mode:
+            ac.fwd_adapt(ws, _p(x), ld, _p(x, ac.col_latent), ld, N)
+        else:
+            ac.fwd_priv(ws, _p(s._priv[t]), s._priv.shape[2], _p(x, ac.col_latent), ld, N)
+        ac.fwd_scan(ws, _p(scan_obs), s.d_scan, _p(x, ac.col_scan), ld, N)
+        mu = ws.get("mu", N, s.d_act)
+        ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
+        ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
+        _lib.check(self.lib.b200_sample_actions(_p(mu), s.d_act, ac.main.ptr("std"), self.seed, self.act_counter, _p(s.actions[t]),
+                                                _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act, _lib.stream_ptr()))
+        self.act_counter += 1
+        self.transition.actions, self.transition.values = s.actions[t], s.values[t]
+        return s.actions[t]
+
+    def process_env_step(self, rewards, dones, infos):
+        """ppo.py:156-171: time-out bootstrap + scalar part of add_transitions."""
+        s = self.storage
+        t = s.step
+        tmo = infos["time_outs"] if "time_outs" in infos else None
+        p = lambda x: C.c_void_p(x.data_ptr())
+        _lib.check(self.lib.b200_store_step_scalars(p(rewards), p(dones), p(tmo) if tmo is not None else None, p(s.values[t]), self.gamma,
+                                                    p(s.rewards[t]), p(s.dones[t]), s.num_envs, _lib.stream_ptr()))
+        s.step += 1
+        self.transition.clear()
+
+    def compute_returns(self, last_critic_obs):
+        """ppo.py:174-179."""
+        s, ac = self.storage, self.actor_critic
+        x = last_critic_obs.contiguous()
+        ac.fwd_critic(self.roll_ws, _p(x), s.d_crit, _p(self.last_values), 1, s.num_envs)
+        s.compute_returns(self.last_values, self.gamma, self.lam)
+
+    # ---- update ---------------------------------------------------------------------------------------
+    def _gather_storage(self, indices):
+        """the one permutation of this update (rollout_storage.py:142) applied to every storage tensor."""
+        s, ac, B = self.storage, self.actor_critic, self.batch
+        st = _lib.stream_ptr
+        g = lambda src, sld, dst, dld, w: _lib.check(self.lib.b200_gather_rows(src, sld, _p_i64(indices), dst, dld, w, B, st()))
+        g(_p(s.observations), s.d_obs, _p(self.p_actor_in), ac.ld_actor_in, s.d_obs)
+        g(_p(s._est), s._est.shape[2], _p(self.p_actor_in, ac.col_est), ac.ld_actor_in, s._est.shape[2])   # actor sees the TRUE value (ppo.py:199)
+        g(_p(s._est), s._est.shape[2], _p(self.p_est), self.p_est.shape[1], s._est.shape[2])
+        g(_p(s._priv), s._priv.shape[2], _p(self.p_priv), self.p_priv.shape[1], s._priv.shape[2])
+        g(_p(s.critic_observations), s.d_crit, _p(self.p_crit), s.d_crit, s.d_crit)
+        g(_p(s.scan_observations), s.d_scan, _p(self.p_scan), s.d_scan, s.d_scan)
+        g(_p(s.actions), s.d_act, _p(self.p_act), s.d_act, s.d_act)
+        for src, dst in ((s.values, self.p_val), (s.returns, self.p_ret), (s.actions_log_prob, self.p_logp), (s.advantages, self.p_adv)):
+            g(_p(src), 1, _p(dst), 1, 1)
+
+    def _reg_coef(self):
+        stage = min(max((self.total_updates - self.start_step) / self.duration, 0.0), 1.0)     # ppo.py:219-220
+        return self.start_val + stage * (self.end_val - self.start_val)
+
+    def _allreduce(self, group):
+        if self.process_group is not None:
+            torch.distributed.all_reduce(group.grads, group=self.process_group)
+
+    def _adam(self, group):
+        self._allreduce(group)
+        _lib.check(self.lib.b200_clip_adam(_p(group.params), _p(group.grads), _p(group.exp_avg), _p(group.exp_avg_sq), group.n,
+                                           C.c_void_p(group.state.data_ptr()), 1.0 / self.world_size, self.max_grad_norm, 0.9, 0.999, 1e-8,
+                                           _lib.stream_ptr()))
+
+    def _minibatch(self, r0, M):
+        """one PPO minibatch on rows [r0, r0+M) of the permuted slabs (ppo.py:194-276)."""
+        ac, est, ws, k, s = self.actor_critic, self.estimator, self.upd_ws, self.actor_critic.k, self.storage
+        ld = ac.ld_actor_in
+        X = _p(self.p_actor_in) + 4 * r0 * ld
+        priv, ldp = _p(self.p_priv) + 4 * r0 * self.p_priv.shape[1], self.p_priv.shape[1]
+        crit, scan = _p(self.p_crit) + 4 * r0 * s.d_crit, _p(self.p_scan) + 4 * r0 * s.d_scan
+        tgt_est, ldte = _p(self.p_est) + 4 * r0 * self.p_est.shape[1], self.p_est.shape[1]
+        L, A = ac.latent_dim, s.d_act
+        # forward
+        ac.fwd_priv(ws, priv, ldp, X + 4 * ac.col_latent, ld, M)
+        ac.fwd_scan(ws, scan, s.d_scan, X + 4 * ac.col_scan, ld, M)
+        mu, val = ws.get("mu", M, A), ws.get("val", M, 4)
+        ac.fwd_actor(ws, X, ld, _p(mu), A, M)
+        ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
+        lat_a = ws.get("lat_a", M, L)
+        ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M)                     # torch.inference_mode() in the reference (ppo.py:213-214)
+        pred = ws.get("pred", M, 4)
+        est.fwd(ws, X, ld, _p(pred), 4, M)
+        # estimator: loss, backward, own optimiser (ppo.py:224-231)
+        dpred = ws.get("dpred", M, 4)
+        _lib.check(self.lib.b200_mse_rows_loss(_p(pred), 4, tgt_est, ldte, _p(dpred), 4, _p(self.loss_sums, 4), M, est.output_dim,
+                                               _lib.stream_ptr()))
+        chain_backward(est.k, est.layers, ws, "e", X + 4 * est.in_col, ld, _p(dpred), 4, M)
+        self._adam(est.group)
+        # PPO loss head (ppo.py:249-270)
+        dmu, dval, dlat, dscan = ws.get("dmu", M, A), ws.get("dval", M, 4), ws.get("dlat", M, L), ws.get("dscan", M, ac.scan_latent_dim)
+        a = _lib.PpoLossArgs()
+        a.mu, a.ldmu, a.std, a.actions = _p(mu), A, ac.main.ptr("std"), _p(self.p_act) + 4 * r0 * A
+        a.old_logp, a.adv = _p(self.p_logp) + 4 * r0, _p(self.p_adv) + 4 * r0
+        a.returns, a.target_values = _p(self.p_ret) + 4 * r0, _p(self.p_val) + 4 * r0
+        a.value, a.ldv = _p(val), 4
+        a.latent_p, a.ldlp, a.latent_a, a.ldla = X + 4 * ac.col_latent, ld, _p(lat_a), L
+        a.dmu, a.lddmu, a.dvalue, a.lddv, a.dlatent_p, a.lddlp = _p(dmu), A, _p(dval), 4, _p(dlat), L
+        a.dstd, a.sums = ac.main.ptr("std", "grads"), _p(self.loss_sums)
+        a.M, a.A, a.L = M, A, L
+        a.clip, a.value_coef, a.entropy_coef, a.reg_coef = self.clip_param, self.value_loss_coef, self.entropy_coef, 0.0
+        a.use_clipped_value_loss, a.reg_coef_dev = int(self.use_clipped_value_loss), _p(self.reg_coef_dev)
+        _lib.check(self.lib.b200_ppo_loss(C.byref(a), _lib.stream_ptr()))
+        # backward: actor (input gradient only for the latent / scan-latent columns), critic, encoders
+        chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M)
+        da0, lda0 = ws.ptr("da0", M, ceil4(ac.actor[0].N)), ceil4(ac.actor[0].N)
+        k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dlat), L, M, accumulate=1, wcol=ac.col_latent, K=L)
+        k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dscan), ac.scan_latent_dim, M, accumulate=0, wcol=ac.col_scan, K=ac.scan_latent_dim)
+        chain_backward(k, ac.critic, ws, "c", crit, s.d_crit, _p(dval), 4, M)
+        chain_backward(k, ac.priv, ws, "p", priv, ldp, _p(dlat), L, M)
+        chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dscan), ac.scan_latent_dim, M)
+        self._adam(ac.main)
+
+    def update(self):
+        """ppo.py:182-293 -> (value_loss, surrogate_loss, reg_loss, reg_coef, estimator_loss)."""
+        indices = torch.randperm(self.num_mini_batches * self.mb, device=self.device, generator=self._perm_gen)
+        return self.update_with_indices(indices)
+
+    def update_with_indices(self, indices):
+        self._gather_storage(indices)
+        reg_coef = self._reg_coef()
+        self.reg_coef_dev.fill_(reg_coef)
+        self.loss_sums.zero_()
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                self._minibatch(i * self.mb, self.mb)
+        n = self.num_learning_epochs * self.num_mini_batches
+        sums = (self.loss_sums / (n * self.mb)).tolist()              # the only host read-back of the update
+        self.storage.clear()
+        self.total_updates += 1
+        self.enforce_max_std(1.0)
+        # sums: [surrogate, value, reg, entropy, estimator]
+        return sums[1], sums[0], sums[2], reg_coef, sums[4]
+
+    def enforce_max_std(self, max_action_std=1.0):
+        self.actor_critic.std.clamp_(max=max_action_std)             # ppo.py:301-307
+
+    def increase_update_count(self):
+        self.total_updates += 1
+
+    def _dagger_minibatch(self, r0, M):
+        """ppo.py:318-339: regress the adaptation encoder onto the (detached) privileged latent."""
+        ac, ws, s = self.actor_critic, self.upd_ws, self.storage
+        ld, L = ac.ld_actor_in, ac.latent_dim
+        X = _p(self.p_actor_in) + 4 * r0 * ld
+        priv, ldp = _p(self.p_priv) + 4 * r0 * self.p_priv.shape[1], self.p_priv.shape[1]
+        lat_p, lat_a, dlat_a = ws.get("lat_p", M, L), ws.get("lat_a", M, L), ws.get("dlat_a", M, L)
+        ac.fwd_priv(ws, priv, ldp, _p(lat_p), L, M)
+        ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M)
+        _lib.check(self.lib.b200_l2_rows_loss(_p(lat_a), L, _p(lat_p), L, _p(dlat_a), L, _p(self.loss_sums, 5), M, L, _lib.stream_ptr()))
+        ac.bwd_adapt(ws, X, ld, _p(dlat_a), L, _p(lat_a), L, M)
+        self._adam(ac.adapt)
+
+    def update_dagger(self):
+        indices = torch.randperm(self.num_mini_batches * self.mb, device=self.device, generator=self._perm_gen)
+        return self.update_dagger_with_indices(indices)
+
+    def update_dagger_with_indices(self, indices):
+        self._gather_storage(indices)
+        self.loss_sums.zero_()
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                self._dagger_minibatch(i * self.mb, self.mb)
+        n = self.num_learning_epochs * self.num_mini_batches
+        loss = float(self.loss_sums[5].item()) / (n * self.mb)
+        self.storage.clear()
+        self.total_updates += 1
+        return loss
+
+
+def _p_i64(t):
+    return C.c_void_p(t.data_ptr())

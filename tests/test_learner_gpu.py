@@ -1,0 +1,229 @@
+"""Learner kernels + host classes (through the C ABI) vs the CPU oracle / the reference golden.
+
+Tolerances, stated per check:
+  * GEMMs in 3xTF32 ('precise') mode are fp32-accurate: <= 2e-5 relative to the output scale vs torch fp32;
+    in TF32 mode (the reference's own GPU matmul precision, train.py:39) <= 3e-3;
+  * network outputs / losses in precise mode: <= 1e-4 relative;
+  * gradients: <= 1e-3 relative to each tensor's rms (fp32 atomics in split-K reorder the sums);
+  * post-Adam parameters: within 2% of the largest possible movement (lr * steps) -- Adam's g/sqrt(v)
+    normalisation amplifies rounding noise of near-zero gradients, so a tighter bound is not meaningful.
+"""
+import ast
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import learner_util as lu
+from legged_gym_custom_b200 import _lib
+from oracle import learner_oracle as lo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = np.load(os.path.join(gu.GOLDEN_DIR, "learner_small.npz"))
+HID = ast.literal_eval(str(GOLD["hid"]))
+
+
+def scale_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.pow(2).mean().sqrt().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 627), (333, 12, 128), (1000, 1, 128), (24576, 256, 512), (129, 30, 52), (64, 20, 36),
+                                   (500, 3, 128), (2048, 64, 29)])
+@pytest.mark.parametrize("precise", [1, 0])
+def test_linear_kernels(M, N, K, precise):
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = lambda k: (k + 3) // 4 * 4
+    X = torch.zeros(M, ld(K)); X[:, :K] = torch.randn(M, K, generator=g)
+    W = torch.zeros(N, ld(K)); W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    dY = torch.zeros(M, ld(N)); dY[:, :N] = torch.randn(M, N, generator=g)
+    Xd, Wd, bd, dYd = X.to(DEV), W.to(DEV), b.to(DEV), dY.to(DEV)
+    p = lambda t: t.data_ptr()
+    st = _lib.stream_ptr()
+    tol = 2e-5 if precise else 3e-3
+    # forward with ELU
+    Y = torch.zeros(M, ld(N), device=DEV)
+    _lib.check(lib.b200_linear_forward(p(Xd), ld(K), p(Wd), ld(K), p(bd), p(Y), ld(N), M, N, K, 1, precise, st))
+    Yref = torch.nn.functional.elu(X[:, :K] @ W[:, :K].t() + b)
+    assert scale_err(Y[:, :N], Yref) <= tol
+    assert float(Y[:, N:].abs().max()) == 0.0 if ld(N) > N else True
+    # dgrad with elu'(Yprev) and accumulate
+    Yprev = torch.randn(M, ld(K), generator=g)
+    dX = torch.ones(M, ld(K), device=DEV)
+    _lib.check(lib.b200_linear_dgrad(p(dYd), ld(N), p(Wd), ld(K), p(Yprev.to(DEV)), ld(K), p(dX), ld(K), M, N, K, 1, precise, st))
+    ref = 1.0 + (dY[:, :N] @ W[:, :K]) * torch.where(Yprev[:, :K] > 0, torch.ones(()), Yprev[:, :K] + 1.0)
+    assert scale_err(dX[:, :K], ref) <= tol
+    # wgrad accumulates into dW / db
+    dW, db = torch.full((N, ld(K)), 0.5, device=DEV), torch.full((N,), 0.25, device=DEV)
+    _lib.check(lib.b200_linear_wgrad(p(dYd), ld(N), p(Xd), ld(K), p(dW), ld(K), p(db), M, N, K, precise, st))
+    torch.cuda.synchronize()
+    assert scale_err(dW[:, :K], 0.5 + dY[:, :N].t() @ X[:, :K]) <= tol
+    assert scale_err(db, 0.25 + dY[:, :N].sum(0)) <= 1e-5
+
+
+def _build(hid, precise=True):
+    from legged_gym_custom_b200.networks import ActorCritic, MlpEstimator
+    ac = ActorCritic(52, 29, 736, 3, 132, 12, 10, actor_hidden_dims=hid["actor"], critic_hidden_dims=hid["critic"],
+                     priv_encoder_hidden_dims=hid["priv"], scan_encoder_hidden_dims=hid["scan"], latent_encoder_output_dim=20,
+                     scan_encoder_output_dim=32, activation='elu', init_noise_std=0.8, device=DEV, precise=precise)
+    est = MlpEstimator(52, 10, 3, hidden_dims=hid["est"], activation='elu', use_history=True, device=DEV, precise=precise)
+    return ac, est
+
+
+def _gold_sd(prefix):
+    return {k[len(prefix):]: torch.from_numpy(GOLD[k]) for k in GOLD.files if k.startswith(prefix)}
+
+
+def test_state_dict_roundtrip_and_forward_vs_reference_golden():
+    ac, est = _build(HID)
+    sd, sd_est = _gold_sd("init/ac/"), _gold_sd("init/est/")
+    ac.load_state_dict(sd)
+    est.load_state_dict(sd_est)
+    back = ac.state_dict()
+    assert list(back.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(back[k].cpu(), sd[k]), k
+    st = {k[len("storage/"):]: torch.from_numpy(GOLD[k]) for k in GOLD.files if k.startswith("storage/")}
+    b = {k: v.to(DEV) for k, v in lu.minibatch(st, torch.arange(32)).items()}
+    e = est(b["obs"])
+    assert scale_err(e, torch.from_numpy(GOLD["act/est"])) <= 1e-4
+    for mode in (False, True):
+        mu = ac.act_inference(b["obs"], b["priv"], e, b["scan"], adaptation_mode=mode)
+        assert scale_err(mu, torch.from_numpy(GOLD[f"act/mu_{int(mode)}"])) <= 1e-4, mode
+        ac.update_distribution(b["obs"], b["priv"], e, b["scan"], adaptation_mode=mode)
+        assert scale_err(ac.get_actions_log_prob(b["actions"]), torch.from_numpy(GOLD[f"act/logp_{int(mode)}"])) <= 1e-4
+    assert scale_err(ac.evaluate(b["critic_obs"]), torch.from_numpy(GOLD["act/value"])) <= 1e-4
+
+
+def _ppo(ac, est, N, T, epochs=2, mbs=2, resume=True):
+    from legged_gym_custom_b200.learner import PPO
+    ppo = PPO(ac, est, num_learning_epochs=epochs, num_mini_batches=mbs, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
+              entropy_coef=0.01, learning_rate=2e-4, estimator_learning_rate=1e-4, max_grad_norm=1.0, use_clipped_value_loss=True,
+              schedule='fixed', desired_kl=0.01, resume=resume, device=DEV, seed=3)
+    ppo.init_storage(N, T, [572], [29], [736], [3], [132], [12])
+    return ppo
+
+
+def _fill(ppo, st):
+    s = ppo.storage
+    d = lambda t: t.to(DEV)
+    s.observations.copy_(d(st["obs"])); s.privileged_observations.copy_(d(st["priv"])); s.critic_observations.copy_(d(st["critic_obs"]))
+    s.true_estimated_observations.copy_(d(st["true_est"])); s.scan_observations.copy_(d(st["scan"])); s.actions.copy_(d(st["actions"]))
+    s.values.copy_(d(st["values"])); s.returns.copy_(d(st["returns"])); s.advantages.copy_(d(st["adv"]))
+    s.actions_log_prob.copy_(d(st["old_logp"])); s.mu.copy_(d(st["mu"])); s.sigma.copy_(d(st["sigma"]))
+
+
+def test_update_matches_reference_golden():
+    """PPO.update on the reference's golden storage / weights / permutation."""
+    T, N = 6, 32
+    ac, est = _build(HID)
+    ac.load_state_dict(_gold_sd("init/ac/")); est.load_state_dict(_gold_sd("init/est/"))
+    ppo = _ppo(ac, est, N, T)
+    ppo.total_updates = 2.0
+    st = {k[len("storage/"):]: torch.from_numpy(GOLD[k]) for k in GOLD.files if k.startswith("storage/")}
+    _fill(ppo, st)
+    v, sur, reg, coef, el = ppo.update_with_indices(torch.from_numpy(GOLD["perm"]).to(DEV))
+    rv, rsur, rreg, rcoef, rel = GOLD["update/returned"]
+    assert coef == rcoef
+    for mine, ref in ((v, rv), (sur, rsur), (reg, rreg), (el, rel)):
+        assert abs(mine - ref) <= 1e-4 * abs(ref), (mine, ref)
+    move = 2e-4 * 4
+    after, sd = _gold_sd("update/ac/"), ac.state_dict()
+    for k in after:
+        assert float((sd[k].cpu() - after[k]).abs().max()) <= 0.02 * move, k
+    after_est, sde = _gold_sd("update/est/"), est.state_dict()
+    for k in after_est:
+        assert float((sde[k].cpu() - after_est[k]).abs().max()) <= 0.02 * (1e-4 * 4), k
+
+
+def test_dagger_matches_reference_golden():
+    T, N = 6, 32
+    ac, est = _build(HID)
+    ac.load_state_dict(_gold_sd("init/ac/")); est.load_state_dict(_gold_sd("init/est/"))
+    ppo = _ppo(ac, est, N, T)
+    st = {k[len("storage/"):]: torch.from_numpy(GOLD[k]) for k in GOLD.files if k.startswith("storage/")}
+    _fill(ppo, st)
+    loss = ppo.update_dagger_with_indices(torch.from_numpy(GOLD["perm"]).to(DEV))
+    ref = float(GOLD["dagger/returned"][0])
+    assert abs(loss - ref) <= 1e-4 * abs(ref)
+    after, sd = _gold_sd("dagger/ac/"), ac.state_dict()
+    for k in after:
+        assert float((sd[k].cpu() - after[k]).abs().max()) <= 0.02 * (2e-4 * 4), k
+
+
+@pytest.mark.parametrize("dagger", [False, True])
+def test_gradients_match_oracle_full_size(dagger):
+    """one minibatch at the real layer sizes (go2_parkour): flat gradients vs torch autograd on the oracle."""
+    hid = dict(actor=[512, 256, 128], critic=[512, 256, 128], priv=[64, 20], scan=[128, 64], est=[256, 128])
+    T, N = 4, 96
+    ac, est = _build(hid)
+    ppo = _ppo(ac, est, N, T, epochs=1, mbs=1)
+    st = lu.random_storage(T, N, seed=21)
+    _fill(ppo, st)
+    sd = {k: v.cpu() for k, v in ac.state_dict().items()}
+    sd_est = {k: v.cpu() for k, v in est.state_dict().items()}
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(2))
+    orc = lo.LearnerOracle(sd, sd_est)
+    ppo._adam = lambda group: None                      # keep the raw gradients in the flat buffers
+    ppo._gather_storage(perm.to(DEV))
+    ppo.reg_coef_dev.fill_(0.07)
+    ppo.loss_sums.zero_()
+    b = lu.minibatch(st, perm)
+    if dagger:
+        ppo._dagger_minibatch(0, T * N)
+        orc.dagger_minibatch(b)
+        groups = [(ac.adapt, ac, orc.adapt_keys)]
+    else:
+        ppo._minibatch(0, T * N)
+        logs = orc.minibatch(b, reg_coef=0.07)
+        groups = [(ac.main, ac, orc.main_keys), (est.group, est, orc.est_keys)]
+        sums = (ppo.loss_sums / (T * N)).tolist()
+        for mine, key in ((sums[0], "surrogate"), (sums[1], "value"), (sums[2], "reg"), (sums[3], "entropy"), (sums[4], "estimator")):
+            assert abs(mine - logs[key]) <= 1e-4 * abs(logs[key]), key
+    torch.cuda.synchronize()
+    for group, owner, keys in groups:
+        # read gradients back in checkpoint layout by viewing the grads buffer through state_dict()
+        saved = group.params
+        group.params = group.grads
+        gsd = {k: v.cpu() for k, v in owner.state_dict().items()}
+        group.params = saved
+        for k in keys:
+            ref = orc.last_grads[k]
+            assert scale_err(gsd[k], ref) <= 1e-3, (k, scale_err(gsd[k], ref))
+
+
+def test_act_and_storage_vs_oracle():
+    """PPO.act / process_env_step / compute_returns on the GPU vs the oracle (keyed action noise)."""
+    hid = dict(actor=[512, 256, 128], critic=[512, 256, 128], priv=[64, 20], scan=[128, 64], est=[256, 128])
+    T, N = 3, 200
+    ac, est = _build(hid)
+    ppo = _ppo(ac, est, N, T)
+    sd = {k: v.cpu() for k, v in ac.state_dict().items()}
+    sd_est = {k: v.cpu() for k, v in est.state_dict().items()}
+    st = lu.random_storage(T, N, seed=31)
+    g = torch.Generator().manual_seed(1)
+    rews, dones, tmo = torch.rand(T, N, generator=g), torch.rand(T, N, generator=g) < 0.1, torch.rand(T, N, generator=g) < 0.05
+    vals = []
+    for t in range(T):
+        mode = t == 1
+        a = ppo.act(*(st[k][t].to(DEV) for k in ("obs", "priv", "critic_obs", "true_est", "scan")), adaptation_mode=mode)
+        ra, rv, rlp, rmu, rsig = lo.ppo_act(sd, sd_est, st["obs"][t], st["priv"][t], st["critic_obs"][t], st["scan"][t], ppo.seed, t, mode)
+        assert scale_err(a, ra) <= 1e-4 and scale_err(ppo.storage.values[t], rv) <= 1e-4
+        assert scale_err(ppo.storage.actions_log_prob[t, :, 0], rlp) <= 1e-4 and scale_err(ppo.storage.mu[t], rmu) <= 1e-4
+        assert torch.equal(ppo.storage.observations[t].cpu(), st["obs"][t]) and torch.equal(ppo.storage.privileged_observations[t].cpu(), st["priv"][t])
+        assert torch.equal(ppo.storage.critic_observations[t].cpu(), st["critic_obs"][t]) and torch.equal(ppo.storage.scan_observations[t].cpu(), st["scan"][t])
+        ppo.process_env_step(rews[t].to(DEV), dones[t].to(DEV), {"time_outs": tmo[t].to(DEV)})
+        vals.append(ppo.storage.values[t].cpu())
+        ref_r = lo.bootstrap_rewards(rews[t], vals[-1], tmo[t], 0.99)
+        assert torch.equal(ppo.storage.rewards[t, :, 0].cpu(), ref_r)
+    ppo.compute_returns(st["critic_obs"][0].to(DEV))
+    torch.cuda.synchronize()
+    s = ppo.storage
+    ret, adv = lo.compute_returns(s.rewards.cpu(), s.dones.cpu(), s.values.cpu(), ppo.last_values.cpu(), 0.99, 0.95)
+    assert torch.equal(s.returns.cpu(), ret) and gu.rel_err(s.advantages.cpu().numpy(), adv.numpy()) <= 1e-5
