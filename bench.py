@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): env-steps/s of [rollout of T=24 env steps incl. policy inference
++ GAE + one PPO update] for go2_parkour at 4096 envs per GPU, PhysX replaced by replayed synthetic frames.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's CPU path, restated: oracle/)
+
+One "step" = one learning iteration (on_policy_runner.py:144-194).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+T_STEPS = 24
+ENV_BYTES_PER_ENV = 12618        # post-physics algorithmic bytes per env-step
+PD_BYTES_PER_ENV = 288           # one PD-torque pass
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tensor=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+
+
+class Profile:
+    """per-ABI-call CUDA-event timing + algorithmic work, installed as the library hook for ONE extra iteration."""
+
+    def __init__(self, num_envs):
+        self.n, self.recs, self.count = num_envs, [], 0
+        self.timing = False
+
+    def hook(self, name, raw, args):
+        from legged_gym_custom_b200 import _lib
+        if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version"):
+            return raw(*args)
+        self.count += _lib.LAUNCHES.get(name, 1)
+        if not self.timing:
+            return raw(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = raw(*args)
+        e1.record()
+        flops = bytes_ = 0
+        if name == "b200_linear_forward":
+            flops = 2.0 * args[7] * args[8] * args[9]
+        elif name == "b200_linear_dgrad":
+            flops = 2.0 * args[8] * args[9] * args[10]
+        elif name == "b200_linear_wgrad":
+            flops = 2.0 * args[7] * args[8] * args[9]
+        elif name == "b200_post_physics_step":
+            bytes_ = ENV_BYTES_PER_ENV * self.n
+        elif name == "b200_pd_torques":
+            bytes_ = PD_BYTES_PER_ENV * self.n
+        self.recs.append((name, e0, e1, flops, bytes_))
+        return rc
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, fl, by in self.recs:
+            a = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
+            a[0] += e0.elapsed_time(e1) * 1e-3
+            a[1] += 1
+            a[2] += fl
+            a[3] += by
+        return agg
+
+
+def build_runner(args, rank, world, device, host_physx=False):
+    from legged_gym_custom_b200 import configs
+    from legged_gym_custom_b200.env import Go2Env, HostPhysX
+    from legged_gym_custom_b200.runner import OnPolicyRunner, class_to_dict
+    env_cfg, train_cfg = configs.TASKS[args.task]
+
+    class Cfg(env_cfg):
+        class env(env_cfg.env):
+            num_envs = args.num_envs
+    pg = torch.distributed.group.WORLD if world > 1 else None
+    env = Go2Env(Cfg, sim_device=str(device), seed=1234 + rank)
+    if host_physx:
+        env.physx = HostPhysX(args.num_envs, env.bufs["env_origins"], device, seed=1234 + rank, decimation=env.params.decimation)
+    tc = class_to_dict(train_cfg)
+    tc["runner"]["resume"] = False
+    runner = OnPolicyRunner(env, tc, log_dir=None, device=device, process_group=pg)
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
+    return env, runner
+
+
+def timed_iterations(runner, first_it, k, world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(first_it, first_it + k):
+        runner.iteration(it)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_b200(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    device = torch.device(f"cuda:{local}")
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    from legged_gym_custom_b200 import _lib
+    prof = Profile(args.num_envs)
+    _lib.lib().hook = prof.hook
+    env, runner = build_runner(args, rank, world, device)
+    N, K, W = args.num_envs, args.steps, args.warmup
+    # iteration 0 is a DAgger iteration (it % 20 == 0); warm-up covers it, the timed ones are PPO updates
+    for it in range(W):
+        runner.iteration(it)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    prof.count = 0
+    elapsed = timed_iterations(runner, W, K, world)
+    launches = prof.count
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    value = T_STEPS * N * world * K / elapsed
+
+    # ---- per-kernel timing of ONE more iteration (CUDA events around every ABI call on the launching stream)
+    prof.timing = True
+    runner.iteration(W + K)
+    table = prof.table()
+    prof.timing = False
+    peaks = measured_peaks()
+    dom = max(table.items(), key=lambda kv: kv[1][0])
+    name, (tsec, n, fl, by) = dom
+    if fl > 0:
+        roof = {"kernel": name, "bound": "tensor", "achieved": fl / tsec / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                "frac": fl / tsec / 1e12 / peaks["tensor"], "traffic": None, "launches": n, "avg_us": tsec / n * 1e6}
+    else:
+        roof = {"kernel": name, "bound": "hbm", "achieved": by / tsec / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": by / tsec / 1e9 / peaks["hbm"], "traffic": None, "launches": n, "avg_us": tsec / n * 1e6}
+    roof["peak_source"] = peaks["source"]
+    total_prof = sum(v[0] for v in table.values())
+    breakdown = {k: {"ms": round(v[0] * 1e3, 3), "calls": v[1], "share": round(v[0] / total_prof, 4),
+                     **({"tflops": round(v[2] / v[0] / 1e12, 2)} if v[2] else {}), **({"gbs": round(v[3] / v[0] / 1e9, 1)} if v[3] else {})}
+                 for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])}
+
+    # ---- end to end: PhysX frames in pinned host memory copied in every substep, results read back every step
+    e2e = None
+    if args.e2e_steps > 0:
+        env2, runner2 = build_runner(args, rank, world, device, host_physx=True)
+        host_rew = torch.zeros(N).pin_memory()
+        host_done = torch.zeros(N, dtype=torch.bool).pin_memory()
+        d2h = [0]
+        orig_step = env2.step
+
+        def step_with_readback(actions):
+            out = orig_step(actions)
+            host_rew.copy_(out[5], non_blocking=True)
+            host_done.copy_(out[6], non_blocking=True)
+            d2h[0] += N * 5
+            return out
+        env2.step = step_with_readback
+        for it in range(2):
+            runner2.iteration(it)
+        env2.physx.h2d_bytes, d2h[0] = 0, 0
+        t2 = timed_iterations(runner2, 2, args.e2e_steps, world)
+        e2e = {"value": T_STEPS * N * world * args.e2e_steps / t2, "unit": "env-steps/s",
+               "h2d_bytes_per_step": env2.physx.h2d_bytes // args.e2e_steps, "d2h_bytes_per_step": d2h[0] // args.e2e_steps + 5 * 4,
+               "ms_per_step": t2 / args.e2e_steps * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_arm(args, budget_s=20.0, steps=1, warmup=0)["cpu_baseline"]
+
+    if rank == 0:
+        line = {"metric": "env-steps/s (env step + GAE + PPO update), go2_parkour, 4096 envs/GPU", "value": value, "unit": "env-steps/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (TF32 tensor-core GEMMs, fp32 accumulate; fp32 env/GAE kernels)", "data": "synthetic",
+                "config": {"workload": f"{args.task}: rollout of {T_STEPS} env steps (policy inference + 4 PD substeps + post-physics) "
+                                       f"+ GAE + PPO update (5 epochs x 4 minibatches of {T_STEPS * N // 4}), {N} envs/GPU, "
+                                       "PhysX replaced by a ring of replayed synthetic frames",
+                           "num_envs_per_gpu": N, "parallelism": f"dp{world} (envs sharded, flat-gradient NCCL all-reduce)",
+                           "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
+                           "timed_iterations": f"it {W}..{W + K - 1} (PPO updates; the DAgger iteration it=0 is in the warm-up)"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ---- CPU arm: the reference's CPU path restated (oracle/), timed on the host cores ---------------------------------
+def cpu_arm(args, budget_s, steps, warmup):
+    import golden_util as gu
+    import state_util as su
+    from legged_gym_custom_b200 import configs, synth
+    from legged_gym_custom_b200.params import NUM_DOF, env_params_from_cfg
+    from oracle import learner_oracle as lo
+    from oracle.go2_oracle import Go2Oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N = args.num_envs
+    cfg = configs.TASKS[args.task][0]
+    hs, origins = gu.terrain_for(args.task)
+    p = env_params_from_cfg(cfg, num_envs=N, seed=1234, hs_shape=None if hs is None else hs.shape)
+    rng = np.random.default_rng(0)
+    statics, st = su.random_statics(p, rng, hs, origins), su.random_state(p, rng, origins)
+    orc = Go2Oracle(p, statics, st)
+    g = torch.Generator().manual_seed(0)
+
+    def lin(n, k):
+        b = 1.0 / k ** 0.5
+        return (torch.rand(n, k, generator=g) * 2 - 1) * b, (torch.rand(n, generator=g) * 2 - 1) * b
+    sd, sd_est = {"std": torch.ones(12)}, {}
+    for pre, dims in (("actor", [627, 512, 256, 128, 12]), ("critic", [736, 512, 256, 128, 1]),
+                      ("privileged_encoder_.priv_encoder", [29, 64, 20, 20]), ("scan_encoder.scan_encoder", [132, 128, 64, 32])):
+        for i in range(len(dims) - 1):
+            sd[f"{pre}.{2 * i}.weight"], sd[f"{pre}.{2 * i}.bias"] = lin(dims[i + 1], dims[i])
+    sd["adaptation_encoder_.fc_encoder.0.weight"], sd["adaptation_encoder_.fc_encoder.0.bias"] = lin(30, 52)
+    w, b = lin(20, 120); sd["adaptation_encoder_.conv_layers.0.weight"], sd["adaptation_encoder_.conv_layers.0.bias"] = w.view(20, 30, 4), b
+    w, b = lin(10, 40); sd["adaptation_encoder_.conv_layers.2.weight"], sd["adaptation_encoder_.conv_layers.2.bias"] = w.view(10, 20, 2), b
+    sd["adaptation_encoder_.fc_final.0.weight"], sd["adaptation_encoder_.fc_final.0.bias"] = lin(20, 30)
+    for i, (k, n) in enumerate(((572, 256), (256, 128), (128, 3))):
+        sd_est[f"estimator.{2 * i}.weight"], sd_est[f"estimator.{2 * i}.bias"] = lin(n, k)
+    learner = lo.LearnerOracle(sd, sd_est)
+    full_iter_guess = 12.0 * 8 / max(cores, 1) + 2.0          # survey: 13.5 s on 8 cores
+    frac = max(min(1.0, budget_s / full_iter_guess), 1.0 / T_STEPS)
+    n_env_steps, n_mb = max(1, round(T_STEPS * frac)), max(1, round(20 * frac))
+    origins0 = st["env_origins"].numpy()
+    frames = [synth.make_frames(N, origins0, rng) for _ in range(2)]
+    B = T_STEPS * N
+    mb = B // 4
+    store = dict(obs=torch.randn(mb, 572) * 0.5, priv=torch.randn(mb, 29) * 0.3, true_est=torch.randn(mb, 3), scan=torch.randn(mb, 132).clamp(-1, 1),
+                 actions=torch.randn(mb, 12), values=torch.randn(mb, 1), returns=torch.randn(mb, 1), adv=torch.randn(mb, 1),
+                 old_logp=torch.randn(mb, 1) - 17.0)
+    store["critic_obs"] = torch.cat([store["obs"], store["priv"], store["true_est"], store["scan"]], -1)
+    rewards, values, dones = torch.rand(T_STEPS, N, 1), torch.randn(T_STEPS, N, 1), (torch.rand(T_STEPS, N, 1) < 0.02).byte()
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = orc.out if orc.out else None
+        obs = torch.zeros(N, 572) if out is None else out["obs_buf"]
+        for i in range(n_env_steps):
+            o = orc.out
+            if o:
+                a, *_ = lo.ppo_act(learner.sd, learner.sd_est, o["obs_buf"], o["privileged_obs_buf"], o["critic_obs_buf"], o["scan_obs_buf"], 1, i)
+            else:
+                a = torch.zeros(N, NUM_DOF)
+            orc.step(a, frames[i % 2])
+        t1 = time.perf_counter()
+        lo.compute_returns(rewards, dones, values, values[0], 0.99, 0.95)
+        t2 = time.perf_counter()
+        for i in range(n_mb):
+            learner.minibatch(store, reg_coef=0.0)
+        t3 = time.perf_counter()
+        it_time = (t1 - t0) * T_STEPS / n_env_steps + (t2 - t1) + (t3 - t2) * 20 / n_mb
+        if s >= warmup:
+            times.append(it_time)
+    it_time = float(np.mean(times))
+    value = T_STEPS * N / it_time
+    sample = (f"per step: {n_env_steps} of {T_STEPS} oracle env steps (with policy inference) + full GAE + {n_mb} of 20 PPO minibatches "
+              f"of {mb} samples, at {N} envs; iteration time extrapolated linearly")
+    return {"value": value, "ms_per_step": it_time * 1e3,
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = max(1, args.steps + args.warmup)
+    r = cpu_arm(args, budget_s=max(2.0, 150.0 / total), steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "env-steps/s (env step + GAE + PPO update), go2_parkour, 4096 envs/GPU", "value": r["value"],
+            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.task}: rollout of {T_STEPS} env steps + GAE + PPO update, {args.num_envs} envs, CPU "
+                                   "(the reference's --sim_device=cpu --rl_device=cpu torch path, restated in oracle/)"},
+            "cpu_baseline": r["cpu_baseline"],
+            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--task", default="go2_parkour")
+    ap.add_argument("--num-envs", type=int, default=4096)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,31 @@ class PpoLossArgs(C.Structure):
 
 _lib = None
 
+# kernels launched per ABI call (for bench.py's `gpu_launches` and per-kernel timing)
+LAUNCHES = {"b200_post_physics_step": 2, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
+
+
+class _Proxy:
+    """Forwards to the CDLL handle; when a hook is installed (bench.py), every compute call is reported to it."""
+
+    def __init__(self, handle):
+        object.__setattr__(self, "_h", handle)
+        object.__setattr__(self, "hook", None)
+        object.__setattr__(self, "_cache", {})
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._h, name)
+
+            def fn(*args, _raw=raw, _name=name):
+                hook = self.hook
+                if hook is None:
+                    return _raw(*args)
+                return hook(_name, _raw, args)
+            self._cache[name] = fn
+        return fn
+
 
 def lib():
     global _lib
@@ -69,7 +94,7 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if handle.b200_env_params_size() != C.sizeof(EnvParams) or handle.b200_env_buffers_size() != C.sizeof(EnvBuffers):
             raise RuntimeError("ctypes mirror of B200EnvParams/B200EnvBuffers is out of sync with the library")
-        _lib = handle
+        _lib = _Proxy(handle)
     return _lib
 
 

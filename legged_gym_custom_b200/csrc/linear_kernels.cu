@@ -185,11 +185,11 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(const GemmArgs g) {
 #pragma unroll
       for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ah[i][k] = PRECISE ? f2tf32(af[i][k]) : __float_as_uint(af[i][k]);
+        for (int k = 0; k < 4; ++k) ah[i][k] = f2tf32(af[i][k]);   // round-to-nearest, as cuBLAS TF32 does
 #pragma unroll
       for (int j = 0; j < NI; ++j)
 #pragma unroll
-        for (int k = 0; k < 2; ++k) bh[j][k] = PRECISE ? f2tf32(bf[j][k]) : __float_as_uint(bf[j][k]);
+        for (int k = 0; k < 2; ++k) bh[j][k] = f2tf32(bf[j][k]);
       if (PRECISE) {
         unsigned al[MI][4], bl[NI][2];
 #pragma unroll

@@ -299,3 +299,35 @@ for _name in ("obs_buf", "privileged_obs_buf", "critic_obs_buf", "estimated_obs_
               "feet_air_time", "jump_flags", "terrain_levels", "terrain_types", "env_origins", "measured_heights",
               "kp_kd_multipliers", "height_samples", "terrain_origins"):
     setattr(Go2Env, _name, _buffer_property(_name))
+
+
+class HostPhysX:
+    """PhysX frames living in PINNED HOST memory (the reference's --sim_device=cpu pipeline hands the env host
+    tensors): every substep / refresh copies that step's frame host->device on the current stream.  Used by
+    bench.py's end-to-end measurement; `h2d_bytes` counts what was copied."""
+
+    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, **frame_kw):
+        rng = np.random.default_rng(seed)
+        origins = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
+        self.frames = []
+        for _ in range(ring):
+            f = synth.make_frames(num_envs, origins, rng, decimation=decimation, **frame_kw)
+            self.frames.append({k: torch.from_numpy(v).pin_memory() for k, v in f.items()})
+        self.cursor, self.h2d_bytes = -1, 0
+
+    def begin_step(self, env):
+        self.cursor = (self.cursor + 1) % len(self.frames)
+
+    def simulate(self, env, substep):
+        src = self.frames[self.cursor]["dof"][substep]
+        env.bufs["dof_state"].copy_(src, non_blocking=True)
+        self.h2d_bytes += src.numel() * 4
+
+    def refresh(self, env):
+        f = self.frames[self.cursor]
+        for name, key in (("root_states", "root"), ("contact_forces", "contact"), ("rigid_body_states", "rigid")):
+            env.bufs[name].copy_(f[key], non_blocking=True)
+            self.h2d_bytes += f[key].numel() * 4
+
+    def push_state(self, env):
+        pass

@@ -1,0 +1,171 @@
+"""`OnPolicyRunner`: drop-in for rsl_rl/runners/on_policy_runner.py (same constructor, `learn`, `save`,
+`load`, `get_inference_policy`), driving `Go2Env` and the kernel-backed `PPO`.
+
+Differences that are deliberate: episode statistics are accumulated on the
+device and read once per iteration instead of `.cpu().numpy()` every env step, and checkpoints additionally
+carry the estimator, the auxiliary optimisers and `total_updates` (the reference silently drops them); the
+reference's keys ('model_state_dict', 'optimizer_state_dict', 'iter', 'infos') are unchanged.
+"""
+import os
+import time
+from collections import deque
+
+import torch
+
+from .learner import PPO
+from .networks import ActorCritic, MlpEstimator
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg, log_dir=None, device="cuda:0", process_group=None, precise=False):
+        self.cfg, self.alg_cfg, self.policy_cfg = train_cfg["runner"], train_cfg["algorithm"], train_cfg["policy"]
+        self.device, self.env = torch.device(device), env
+        pc, ac_ = self.policy_cfg, self.alg_cfg
+        seed = int(train_cfg.get("seed", 1))
+        actor_critic = ActorCritic(num_proprio=env.num_proprio, num_privileged_obs=env.num_privileged_obs,
+                                   num_critic_obs=env.num_critic_obs, num_estimated_obs=env.num_estimated_obs,
+                                   num_scan_obs=env.num_scan_obs, num_actions=env.num_actions,
+                                   history_buffer_length=env.history_buffer_length, actor_hidden_dims=pc["actor_hidden_dims"],
+                                   critic_hidden_dims=pc["critic_hidden_dims"], priv_encoder_hidden_dims=pc["priv_encoder_hidden_dims"],
+                                   scan_encoder_hidden_dims=pc["scan_encoder_hidden_dims"],
+                                   latent_encoder_output_dim=pc["latent_encoder_output_dim"],
+                                   scan_encoder_output_dim=pc["scan_encoder_output_dim"], activation=pc["activation"],
+                                   init_noise_std=pc["init_noise_std"], device=self.device, seed=seed, precise=precise,
+                                   learning_rate=ac_["learning_rate"])
+        estimator = MlpEstimator(num_proprio=env.num_proprio, history_buffer_length=env.history_buffer_length,
+                                 output_dim=env.num_estimated_obs, hidden_dims=pc["estimator_hidden_dims"], activation=pc["activation"],
+                                 use_history=pc["use_history"], device=self.device, seed=seed + 1, precise=precise,
+                                 learning_rate=ac_["estimator_learning_rate"])
+        self.alg = PPO(actor_critic=actor_critic, estimator=estimator, num_learning_epochs=ac_["num_learning_epochs"],
+                       num_mini_batches=ac_["num_mini_batches"], clip_param=ac_["clip_param"], gamma=ac_["gamma"], lam=ac_["lam"],
+                       value_loss_coef=ac_["value_loss_coef"], entropy_coef=ac_["entropy_coef"], learning_rate=ac_["learning_rate"],
+                       estimator_learning_rate=ac_["estimator_learning_rate"], max_grad_norm=ac_["max_grad_norm"],
+                       use_clipped_value_loss=ac_["use_clipped_value_loss"], schedule=ac_["schedule"], desired_kl=ac_["desired_kl"],
+                       resume=self.cfg["resume"], device=self.device, seed=seed, process_group=process_group)
+        self.dagger_update_freq = ac_["dagger_update_freq"]
+        self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
+        self.alg.init_storage(num_envs=env.num_envs, num_transitions_per_env=self.num_steps_per_env, total_obs_shape=[env.num_obs],
+                              privileged_obs_shape=[env.num_privileged_obs], critic_obs_shape=[env.num_critic_obs],
+                              estimated_obs_shape=[env.num_estimated_obs], scan_obs_shape=[env.num_scan_obs],
+                              action_shape=[env.num_actions])
+        self.log_dir, self.writer = log_dir, None
+        self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0, 0
+        self.env.reset()
+        N = env.num_envs
+        self._cur_rew, self._cur_len = torch.zeros(N, device=self.device), torch.zeros(N, device=self.device)
+        self._ep_stats = torch.zeros(3, device=self.device)      # finished episodes: sum reward, sum length, count
+        self.rewbuffer, self.lenbuffer = deque(maxlen=100), deque(maxlen=100)
+        self.last_losses = {}
+
+    # ---- one iteration = rollout + GAE + update (on_policy_runner.py:144-194) -----------------------------
+    def rollout(self, use_adaptation_mode):
+        env, alg = self.env, self.alg
+        obs, priv, crit = env.get_observations(), env.get_privileged_observations(), env.get_critic_observations()
+        est, scan = env.get_estimated_observations(), env.get_scan_observations()
+        for _ in range(self.num_steps_per_env):
+            actions = alg.act(obs, priv, crit, est, scan, adaptation_mode=use_adaptation_mode)
+            obs, priv, crit, est, scan, rewards, dones, infos = env.step(actions)
+            alg.process_env_step(rewards, dones, infos)
+            if self.log_dir is not None:
+                self._cur_rew += rewards
+                self._cur_len += 1
+                d = dones.float()
+                self._ep_stats += torch.stack(((self._cur_rew * d).sum(), (self._cur_len * d).sum(), d.sum()))
+                self._cur_rew *= 1 - d
+                self._cur_len *= 1 - d
+        alg.compute_returns(crit)
+
+    def iteration(self, it):
+        use_adaptation_mode = it % self.dagger_update_freq == 0
+        self.rollout(use_adaptation_mode)
+        if use_adaptation_mode:
+            self.last_losses = {"adaptation": self.alg.update_dagger()}
+        else:
+            v, s, r, c, e = self.alg.update()
+            self.last_losses = {"value": v, "surrogate": s, "regularization": r, "reg_coef": c, "estimator": e}
+        return self.last_losses
+
+    def learn(self, num_learning_iterations, init_at_random_ep_len=False):
+        if self.log_dir is not None and self.writer is None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self.writer = SummaryWriter(log_dir=self.log_dir, flush_secs=10)
+            except Exception:
+                self.writer = None
+        if init_at_random_ep_len:
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+        tot = self.current_learning_iteration + num_learning_iterations
+        for it in range(self.current_learning_iteration, tot):
+            start = time.time()
+            losses = self.iteration(it)
+            torch.cuda.synchronize()
+            dt = time.time() - start
+            self.tot_time += dt
+            self.tot_timesteps += self.num_steps_per_env * self.env.num_envs
+            if self.log_dir is not None:
+                self.log(it, losses, dt)
+                if it % self.save_interval == 0:
+                    self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
+        self.current_learning_iteration += num_learning_iterations
+        if self.log_dir is not None:
+            self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+
+    def log(self, it, losses, dt):
+        srew, slen, cnt = self._ep_stats.tolist()
+        self._ep_stats.zero_()
+        if cnt > 0:
+            self.rewbuffer.append(srew / cnt)
+            self.lenbuffer.append(slen / cnt)
+        fps = int(self.num_steps_per_env * self.env.num_envs / dt)
+        if self.writer is not None:
+            for k, v in losses.items():
+                self.writer.add_scalar("Loss/" + k, v, it)
+            self.writer.add_scalar("Loss/learning_rate", self.alg.learning_rate, it)
+            self.writer.add_scalar("Perf/total_fps", fps, it)
+            self.writer.add_scalar("Policy/mean_noise_std", float(self.alg.actor_critic.std.mean()), it)
+            for k, v in self.env.extras.get("episode", {}).items():
+                self.writer.add_scalar("Episode/" + k, float(v), it)
+            if self.rewbuffer:
+                self.writer.add_scalar("Train/mean_reward", sum(self.rewbuffer) / len(self.rewbuffer), it)
+                self.writer.add_scalar("Train/mean_episode_length", sum(self.lenbuffer) / len(self.lenbuffer), it)
+        body = " ".join(f"{k}={v:.4f}" for k, v in losses.items())
+        print(f"it {it} fps {fps} {body}" + (f" mean_reward {self.rewbuffer[-1]:.3f}" if self.rewbuffer else ""))
+
+    def save(self, path, infos=None):
+        alg = self.alg
+        torch.save({"model_state_dict": alg.actor_critic.state_dict(), "optimizer_state_dict": alg.optimizer.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos,
+                    "estimator_state_dict": alg.estimator.state_dict(),
+                    "estimator_optimizer_state_dict": alg.estimator_optimizer.state_dict(),
+                    "adaptation_optimizer_state_dict": alg.adaptation_optimizer.state_dict(), "total_updates": alg.total_updates}, path)
+
+    def load(self, path, load_optimizer=True):
+        d = torch.load(path, map_location="cpu")
+        alg = self.alg
+        alg.actor_critic.load_state_dict(d["model_state_dict"])
+        if "estimator_state_dict" in d:
+            alg.estimator.load_state_dict(d["estimator_state_dict"])
+        if load_optimizer and isinstance(d.get("optimizer_state_dict"), dict) and "flat_exp_avg" in d["optimizer_state_dict"]:
+            alg.optimizer.load_state_dict(d["optimizer_state_dict"])
+            if "estimator_optimizer_state_dict" in d:
+                alg.estimator_optimizer.load_state_dict(d["estimator_optimizer_state_dict"])
+                alg.adaptation_optimizer.load_state_dict(d["adaptation_optimizer_state_dict"])
+        alg.total_updates = d.get("total_updates", alg.total_updates)
+        self.current_learning_iteration = d["iter"]
+        return d["infos"]
+
+    def get_inference_policy(self, device=None):
+        return self.alg.actor_critic.act_inference
+
+
+def class_to_dict(obj):
+    """helpers.py:41-56 for the class-namespace configs."""
+    if not hasattr(obj, "__dict__"):
+        return obj
+    out = {}
+    for key in dir(obj):
+        if key.startswith("_"):
+            continue
+        val = getattr(obj, key)
+        out[key] = [class_to_dict(v) for v in val] if isinstance(val, list) else class_to_dict(val)
+    return out
