@@ -291,6 +291,16 @@ int b200_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const 
 int b200_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int ldw, float* db, int M, int N,
                       int K, int precise, void* stream);
 
+/* ---- learner: the same three GEMMs on the tcgen05 / TMEM / TMA path (csrc/mlp_tcgen05.cu, kind::tf32) ----------
+ * Same argument meaning as b200_linear_*; bias gradients stay with b200_linear_wgrad / the caller. */
+int b200_tc_linear_supported(int M, int N, int K);
+int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                           int M, int N, int K, int act, void* stream);
+int b200_tc_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX,
+                         int lddx, int M, int N, int K, int accumulate, void* stream);
+int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int ldw, int M, int N, int K,
+                         void* stream);
+
 /* ---- learner: storage traffic, heads, optimiser (csrc/learner_kernels.cu) ---------------------- */
 typedef struct B200CopySeg {
   const float* src;
