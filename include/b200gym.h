@@ -350,6 +350,8 @@ int b200_elu_backward(float* dY, int lddy, const float* Y, int ldy, int M, int N
  * by the call itself so a captured CUDA graph replays correctly (initialise to {0, 0, 1, 1, lr}). */
 int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
                    float grad_scale, float max_norm, float beta1, float beta2, float eps, void* stream);
+/* db[N] += column sums of dY[M,N] (bias gradient, companion of b200_tc_linear_wgrad) */
+int b200_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream);
 int b200_fill(float* p, float value, int64_t n, void* stream);
 
 #ifdef __cplusplus

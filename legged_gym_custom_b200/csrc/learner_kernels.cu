@@ -276,6 +276,26 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
+// db[n] += sum_m dY[m,n]: lane = column, warps stride over a slab of rows, one atomic per column per CTA.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dY, int lddy, float* __restrict__ db, int M, int N, int rows_per_cta) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float s = 0.0f;
+  if (col < N)
+    for (int r = r0 + warp; r < r1; r += 8) s += dY[(int64_t)r * lddy + col];
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && col < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    atomicAdd(db + col, t);
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, float value, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = value;
 }
@@ -369,6 +389,18 @@ int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
   B200_CHECK_LAUNCH("sumsq_kernel");
   clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, grad_scale, max_norm, beta1, beta2, eps);
   B200_CHECK_LAUNCH("clip_adam_kernel");
+  return 0;
+}
+
+int b200_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream) {
+  B200_CHECK_ARG(dY && db && M > 0 && N > 0 && lddy >= N, "b200_colsum: bad argument");
+  const int col_blocks = (N + 31) / 32;
+  int row_blocks = (148 * 4 + col_blocks - 1) / col_blocks;
+  const int max_rb = (M + 63) / 64;
+  row_blocks = row_blocks < 1 ? 1 : (row_blocks > max_rb ? max_rb : row_blocks);
+  const int rows_per_cta = (M + row_blocks - 1) / row_blocks;
+  colsum_kernel<<<dim3(col_blocks, (M + rows_per_cta - 1) / rows_per_cta), 256, 0, (cudaStream_t)stream>>>(dY, lddy, db, M, N, rows_per_cta);
+  B200_CHECK_LAUNCH("colsum_kernel");
   return 0;
 }
 

@@ -7,11 +7,11 @@
 // kind::tf32 with fp32 accumulation in TMEM: fp32 tensors are consumed in place (no conversion
 // pass), which is the reference's own GPU matmul precision (TF32, train.py:39).
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0  (one elected lane) TMA producer: cp.async.bulk.tensor 128-byte-swizzled boxes into a 4-stage ring
 //   warp 1  (one elected lane) MMA issuer:   tcgen05.mma cta_group::1, M=128, N=BN, K=8 per instruction,
 //                                             tcgen05.commit frees the smem stage / publishes the accumulator
-//   warps 2-5                  epilogue:      tcgen05.ld 32x32b -> registers -> bias / ELU / ELU' -> global
+//   warps 2-9                  epilogue:      tcgen05.ld 32x32b -> registers -> bias / ELU / ELU' -> global
 // Two accumulators (2 x BN TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Shared-memory operand layouts are exactly what TMA SWIZZLE_128B writes (1024-byte aligned stages):
@@ -27,7 +27,7 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // 32 fp32 = 128 B = one swizzle row
 constexpr int STAGES = 4;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,14 +107,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_128B, version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout for MN-major tf32 operands)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
-  d |= (uint64_t)2 << 61;   // layout_type = SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32
@@ -174,7 +175,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, 4);      // one arrive per epilogue warp
+      mbar_init(tmem_empty + a, 8);      // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -228,8 +229,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t da = A_MN ? make_desc(sa + k * 1024, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * 1024, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
+            // K-major: 8-row x 128 B atoms (SBO 1024), a K=8 step is 32 B inside the row.
+            // MN-major (tf32): 4-k-row x 128 B atoms swizzled in 32 B chunks (SBO 512 between atoms along K,
+            // LBO between 32-element chunks along MN), a K=8 step is 8 rows = 1024 B.
+            const uint64_t da = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
             umma_tf32(tmem_d, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar + s);               // smem stage reusable once these MMAs retire
@@ -238,8 +242,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-    const int quarter = warp & 3;
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4; the two warps of a quarter split the columns =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
     uint32_t local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const uint32_t acc = local_tile & 1, acc_ph = (local_tile >> 1) & 1;
@@ -248,25 +253,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int ci = half * CH_PER_HALF; ci < min(CHUNKS, (half + 1) * CH_PER_HALF); ++ci) {
+        const int c = ci * 32;
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
-        if (row < g.M) {
-          const int col0 = n0 + c;
-          float* crow = g.C + (int64_t)row * g.ldc + col0;
-          if (MODE == NT) {
+        if (row >= g.M) continue;
+        const int col0 = n0 + c;
+        if (col0 >= g.N) continue;
+        float* crow = g.C + (int64_t)row * g.ldc + col0;
+        const bool full = (col0 + 32 <= g.N);
+        if (MODE == NT) {
+          if (g.bias) {
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = v[j];
-              if (col0 + j < g.N) {
-                if (g.bias) x += __ldg(g.bias + col0 + j);
-                if (g.act == 1) x = x > 0.0f ? x : expf(x) - 1.0f;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
               }
-              v[j] = x;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < g.N) v[j] += __ldg(g.bias + col0 + j);
             }
-          } else if (MODE == NN) {
-            if (g.aux) {
-              const float* yrow = g.aux + (int64_t)row * g.ldaux + col0;
+          }
+          if (g.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {                    // ELU, branch-free: exp only ever sees x <= 0
+              const float e = __expf(fminf(v[j], 0.0f)) - 1.0f;
+              v[j] = v[j] > 0.0f ? v[j] : e;
+            }
+          }
+        } else if (MODE == NN) {
+          if (g.aux) {
+            const float* yrow = g.aux + (int64_t)row * g.ldaux + col0;
+            if (full && (((uintptr_t)yrow) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 y4 = *reinterpret_cast<const float4*>(yrow + j);
+                v[j] *= (y4.x > 0.0f ? 1.0f : y4.x + 1.0f);
+                v[j + 1] *= (y4.y > 0.0f ? 1.0f : y4.y + 1.0f);
+                v[j + 2] *= (y4.z > 0.0f ? 1.0f : y4.z + 1.0f);
+                v[j + 3] *= (y4.w > 0.0f ? 1.0f : y4.w + 1.0f);
+              }
+            } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < g.N) {
@@ -274,29 +303,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   v[j] *= (y > 0.0f ? 1.0f : y + 1.0f);
                 }
             }
-            if (g.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) v[j] += crow[j];
-            }
           }
-          if (MODE == TN) {
-            if (col0 + 32 <= g.N && (((uintptr_t)crow) & 15) == 0) {
+          if (g.accumulate) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) v[j] += crow[j];
+          }
+        }
+        const bool vec = full && (((uintptr_t)crow) & 15) == 0;
+        if (MODE == TN) {
+          if (vec) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) atomicAdd(crow + j, v[j]);
-            }
-          } else if (col0 + 32 <= g.N && (((uintptr_t)crow) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) crow[j] = v[j];
+              if (col0 + j < g.N) atomicAdd(crow + j, v[j]);
           }
+        } else if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) crow[j] = v[j];
         }
       }
       tc_fence_before();
@@ -325,8 +355,9 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major tensor [rows][cols] with leading dimension ld; box = [box_rows][32 cols], 128-byte swizzle
-int make_tmap(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp32 row-major tensor [rows][cols] with leading dimension ld; box = [box_rows][32 cols].
+// mn_major = 0: SWIZZLE_128B (16 B chunks);  1: SWIZZLE_128B_ATOM_32B (32 B chunks, for MN-major tf32 operands)
+int make_tmap(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     b200_set_error("cuTensorMapEncodeTiled is unavailable");
@@ -337,7 +368,7 @@ int make_tmap(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b200_set_error("cuTensorMapEncodeTiled failed with %d (base %p rows %lld cols %lld ld %lld)", (int)r, (const void*)base, (long long)rows,
                    (long long)cols, (long long)ld);
@@ -380,6 +411,19 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// widest N tile that divides the (32-padded) output width while still giving ~a wave of tiles
+int pick_bn(int rows, int cols) {
+  const int nc = (cols + 31) / 32 * 32;
+  const int m_tiles = (rows + BM - 1) / BM;
+  int bn = 32;
+  for (int cand : {256, 128, 64, 32}) {
+    if (nc % cand) continue;
+    bn = cand;
+    if (m_tiles * (nc / cand) >= (num_sms() * 3) / 4) break;
+  }
+  return bn;
+}
+
 }  // namespace
 
 extern "C" {
@@ -392,11 +436,10 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
   B200_CHECK_ARG(X && W && Y && M > 0 && N > 0 && K > 0, "b200_tc_linear_forward: bad argument");
   B200_CHECK_ARG(b200_tc_linear_supported(M, N, K), "b200_tc_linear_forward: needs N >= 8 and K >= 8 (N=%d K=%d)", N, K);
   B200_CHECK_ARG(ldx % 4 == 0 && ldw % 4 == 0 && aligned16(X) && aligned16(W), "b200_tc_linear_forward: operands need 16-byte rows");
-  const int nc = (N + 31) / 32 * 32;
-  const int bn = nc % 256 == 0 ? 256 : (nc % 128 == 0 ? 128 : (nc % 64 == 0 ? 64 : 32));
+  const int bn = pick_bn(M, N);
   CUtensorMap ta, tb;
-  if (int rc = make_tmap(&ta, X, M, K, ldx, BM)) return rc;
-  if (int rc = make_tmap(&tb, W, N, K, ldw, bn)) return rc;
+  if (int rc = make_tmap(&ta, X, M, K, ldx, BM, 0)) return rc;
+  if (int rc = make_tmap(&tb, W, N, K, ldw, bn, 0)) return rc;
   TcArgs g{};
   g.C = Y; g.bias = bias; g.ldc = ldy; g.M = M; g.N = N; g.K = K; g.act = act;
   cudaStream_t st = (cudaStream_t)stream;
@@ -413,11 +456,10 @@ int b200_tc_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, con
                          int N, int K, int accumulate, void* stream) {
   B200_CHECK_ARG(dY && W && dX && M > 0 && N > 0 && K > 0, "b200_tc_linear_dgrad: bad argument");
   B200_CHECK_ARG(lddy % 4 == 0 && ldw % 4 == 0 && aligned16(dY) && aligned16(W), "b200_tc_linear_dgrad: operands need 16-byte rows");
-  const int kc = (K + 31) / 32 * 32;
-  const int bn = kc % 256 == 0 ? 256 : (kc % 128 == 0 ? 128 : (kc % 64 == 0 ? 64 : 32));
+  const int bn = pick_bn(M, K);
   CUtensorMap ta, tb;
-  if (int rc = make_tmap(&ta, dY, M, N, lddy, BM)) return rc;          // A K-major: [M rows][N reduction]
-  if (int rc = make_tmap(&tb, W, N, K, ldw, BK)) return rc;            // B MN-major: box [32 n][32 k]
+  if (int rc = make_tmap(&ta, dY, M, N, lddy, BM, 0)) return rc;          // A K-major: [M rows][N reduction]
+  if (int rc = make_tmap(&tb, W, N, K, ldw, BK, 1)) return rc;            // B MN-major: box [32 n][32 k]
   TcArgs g{};
   g.C = dX; g.aux = Yprev; g.ldc = lddx; g.ldaux = ldyp; g.M = M; g.N = K; g.K = N; g.accumulate = accumulate;
   cudaStream_t st = (cudaStream_t)stream;
@@ -438,8 +480,8 @@ int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, flo
   const int kc = (K + 31) / 32 * 32;
   const int bn = kc % 256 == 0 ? 256 : (kc % 128 == 0 ? 128 : (kc % 64 == 0 ? 64 : 32));
   CUtensorMap ta, tb;
-  if (int rc = make_tmap(&ta, dY, M, N, lddy, BK)) return rc;          // A MN-major: box [32 m][32 n]
-  if (int rc = make_tmap(&tb, X, M, K, ldx, BK)) return rc;            // B MN-major: box [32 m][32 k]
+  if (int rc = make_tmap(&ta, dY, M, N, lddy, BK, 1)) return rc;          // A MN-major: box [32 m][32 n]
+  if (int rc = make_tmap(&tb, X, M, K, ldx, BK, 1)) return rc;            // B MN-major: box [32 m][32 k]
   TcArgs g{};
   g.C = dW; g.ldc = ldw; g.M = N; g.N = K; g.K = M;
   const int tiles = ((N + BM - 1) / BM) * ((K + bn - 1) / bn);

@@ -117,24 +117,43 @@ def _p(t, col=0):
 
 
 class Kernels:
-    """Thin typed wrappers over the C ABI (addresses are plain ints)."""
+    """Thin typed wrappers over the C ABI (addresses are plain ints).
 
-    def __init__(self, precise=False):
+    precise=False (production): the tcgen05 / TMEM / TMA kernels (kind::tf32) wherever the shape allows
+    (N >= 8, K >= 8), the mma.sync TF32 kernels otherwise.  precise=True (parity runs against the fp32 oracle):
+    the 3xTF32 mma.sync kernels everywhere."""
+
+    def __init__(self, precise=False, use_tc=True):
         self.lib = _lib.lib()
         self.precise = int(precise)
+        self.use_tc = bool(use_tc) and not precise
 
     def fwd(self, lin, X, ldx, Y, ldy, M, act=None):
-        _lib.check(self.lib.b200_linear_forward(X, ldx, lin.w(), lin.ldw, lin.b(), Y, ldy, M, lin.N, lin.K,
-                                                lin.act if act is None else act, self.precise, _lib.stream_ptr()))
+        act = lin.act if act is None else act
+        if self.use_tc and lin.N >= 8 and lin.K >= 8:
+            _lib.check(self.lib.b200_tc_linear_forward(X, ldx, lin.w(), lin.ldw, lin.b(), Y, ldy, M, lin.N, lin.K, act, _lib.stream_ptr()))
+        else:
+            _lib.check(self.lib.b200_linear_forward(X, ldx, lin.w(), lin.ldw, lin.b(), Y, ldy, M, lin.N, lin.K, act, self.precise,
+                                                    _lib.stream_ptr()))
 
     def dgrad(self, lin, dY, lddy, Yprev, ldyp, dX, lddx, M, accumulate=0, wcol=0, K=None):
         """dX[M,K] (+)= dY[M,N] . W[:, wcol:wcol+K] * elu'(Yprev)"""
-        _lib.check(self.lib.b200_linear_dgrad(dY, lddy, lin.w(col=wcol), lin.ldw, Yprev, ldyp, dX, lddx, M, lin.N,
-                                              lin.K if K is None else K, accumulate, self.precise, _lib.stream_ptr()))
+        K = lin.K if K is None else K
+        if self.use_tc and lin.N >= 8 and K >= 8:
+            _lib.check(self.lib.b200_tc_linear_dgrad(dY, lddy, lin.w(col=wcol), lin.ldw, Yprev, ldyp, dX, lddx, M, lin.N, K, accumulate,
+                                                     _lib.stream_ptr()))
+        else:
+            _lib.check(self.lib.b200_linear_dgrad(dY, lddy, lin.w(col=wcol), lin.ldw, Yprev, ldyp, dX, lddx, M, lin.N, K, accumulate,
+                                                  self.precise, _lib.stream_ptr()))
 
     def wgrad(self, lin, dY, lddy, X, ldx, M, K=None):
-        _lib.check(self.lib.b200_linear_wgrad(dY, lddy, X, ldx, lin.w("grads"), lin.ldw, lin.b("grads"), M, lin.N,
-                                              lin.K if K is None else K, self.precise, _lib.stream_ptr()))
+        K = lin.K if K is None else K
+        if self.use_tc and lin.N >= 8 and K >= 8 and M >= 32:
+            _lib.check(self.lib.b200_tc_linear_wgrad(dY, lddy, X, ldx, lin.w("grads"), lin.ldw, M, lin.N, K, _lib.stream_ptr()))
+            _lib.check(self.lib.b200_colsum(dY, lddy, lin.b("grads"), M, lin.N, _lib.stream_ptr()))
+        else:
+            _lib.check(self.lib.b200_linear_wgrad(dY, lddy, X, ldx, lin.w("grads"), lin.ldw, lin.b("grads"), M, lin.N, K, self.precise,
+                                                  _lib.stream_ptr()))
 
 
 def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M):

@@ -68,6 +68,42 @@ def test_linear_kernels(M, N, K, precise):
     assert scale_err(db, 0.25 + dY[:, :N].sum(0)) <= 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 627), (333, 12, 128), (24576, 256, 512), (129, 30, 52), (64, 20, 36), (500, 32, 128),
+                                   (2048, 64, 29), (1000, 128, 132), (4096, 512, 736)])
+def test_tcgen05_linear_kernels(M, N, K):
+    """the tcgen05 / TMEM / TMA GEMMs (kind::tf32) vs torch fp32: forward (bias + ELU), dgrad (elu' + accumulate),
+    wgrad (split-K accumulation) + colsum bias gradient.  TMA zero-fill covers the K / N / M tails."""
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = lambda k: (k + 3) // 4 * 4
+    X = torch.zeros(M, ld(K)); X[:, :K] = torch.randn(M, K, generator=g)
+    W = torch.zeros(N, ld(K)); W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    dY = torch.zeros(M, ld(N)); dY[:, :N] = torch.randn(M, N, generator=g)
+    Xd, Wd, bd, dYd = X.to(DEV), W.to(DEV), b.to(DEV), dY.to(DEV)
+    p = lambda t: t.data_ptr()
+    st = _lib.stream_ptr()
+    tol = 3e-3
+    Y = torch.zeros(M, ld(N), device=DEV)
+    _lib.check(lib.b200_tc_linear_forward(p(Xd), ld(K), p(Wd), ld(K), p(bd), p(Y), ld(N), M, N, K, 1, st))
+    assert scale_err(Y[:, :N], torch.nn.functional.elu(X[:, :K] @ W[:, :K].t() + b)) <= tol
+    if ld(N) > N:
+        assert float(Y[:, N:].abs().max()) == 0.0
+    Yprev = torch.randn(M, ld(K), generator=g)
+    dX = torch.ones(M, ld(K), device=DEV)
+    _lib.check(lib.b200_tc_linear_dgrad(p(dYd), ld(N), p(Wd), ld(K), p(Yprev.to(DEV)), ld(K), p(dX), ld(K), M, N, K, 1, st))
+    ref = 1.0 + (dY[:, :N] @ W[:, :K]) * torch.where(Yprev[:, :K] > 0, torch.ones(()), Yprev[:, :K] + 1.0)
+    assert scale_err(dX[:, :K], ref) <= tol
+    dW, db = torch.full((N, ld(K)), 0.5, device=DEV), torch.full((N,), 0.25, device=DEV)
+    _lib.check(lib.b200_tc_linear_wgrad(p(dYd), ld(N), p(Xd), ld(K), p(dW), ld(K), M, N, K, st))
+    _lib.check(lib.b200_colsum(p(dYd), ld(N), p(db), M, N, st))
+    torch.cuda.synchronize()
+    assert scale_err(dW[:, :K], 0.5 + dY[:, :N].t() @ X[:, :K]) <= tol
+    if ld(K) > K:
+        assert float((dW[:, K:] - 0.5).abs().max()) == 0.0
+    assert scale_err(db, 0.25 + dY[:, :N].sum(0)) <= 1e-5
+
+
 def assert_params_close(mine, ref, move, name):
     d = (mine.cpu() - ref).abs()
     frac = float((d > 0.02 * move).float().mean())
@@ -164,12 +200,14 @@ def test_dagger_matches_reference_golden():
         assert_params_close(sd[k], after[k], 2e-4 * 4, k)
 
 
-@pytest.mark.parametrize("dagger", [False, True])
-def test_gradients_match_oracle_full_size(dagger):
-    """one minibatch at the real layer sizes (go2_parkour): flat gradients vs torch autograd on the oracle."""
+@pytest.mark.parametrize("dagger,precise", [(False, True), (True, True), (False, False), (True, False)])
+def test_gradients_match_oracle_full_size(dagger, precise):
+    """one minibatch at the real layer sizes (go2_parkour): flat gradients vs torch autograd on the oracle.
+    precise=True: 3xTF32 mma.sync kernels (1e-3 of each tensor's rms); precise=False: the production tcgen05 TF32
+    path (3e-2 of each tensor's rms: TF32 inputs through 4-layer forward + backward chains)."""
     hid = dict(actor=[512, 256, 128], critic=[512, 256, 128], priv=[64, 20], scan=[128, 64], est=[256, 128])
     T, N = 4, 96
-    ac, est = _build(hid)
+    ac, est = _build(hid, precise=precise)
     ppo = _ppo(ac, est, N, T, epochs=1, mbs=1)
     st = lu.random_storage(T, N, seed=21)
     _fill(ppo, st)
@@ -192,7 +230,7 @@ def test_gradients_match_oracle_full_size(dagger):
         groups = [(ac.main, ac, orc.main_keys), (est.group, est, orc.est_keys)]
         sums = (ppo.loss_sums / (T * N)).tolist()
         for mine, key in ((sums[0], "surrogate"), (sums[1], "value"), (sums[2], "reg"), (sums[3], "entropy"), (sums[4], "estimator")):
-            assert abs(mine - logs[key]) <= 1e-4 * abs(logs[key]), key
+            assert abs(mine - logs[key]) <= (1e-4 if precise else 5e-3) * abs(logs[key]), key
     torch.cuda.synchronize()
     for group, owner, keys in groups:
         # read gradients back in checkpoint layout by viewing the grads buffer through state_dict()
@@ -202,7 +240,7 @@ def test_gradients_match_oracle_full_size(dagger):
         group.params = saved
         for k in keys:
             ref = orc.last_grads[k]
-            assert scale_err(gsd[k], ref) <= 1e-3, (k, scale_err(gsd[k], ref))
+            assert scale_err(gsd[k], ref) <= (1e-3 if precise else 3e-2), (k, scale_err(gsd[k], ref))
 
 
 def test_act_and_storage_vs_oracle():

@@ -13,6 +13,7 @@ import tempfile
 
 rep, obj, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+ncu_filter = sys.argv[5] if len(sys.argv) > 5 else kname     # demangled-name regex for ncu (kname matches the MANGLED name)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
@@ -31,7 +32,7 @@ for l in txt:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m and func and kname in func:
         line_of.append((int(m.group(1), 16), cur, m.group(2)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kname], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + ncu_filter], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
 hdr_i = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hdr_i]
@@ -54,6 +55,12 @@ for r in data:
         per_line[line_of[idx][1]] += n
         samp[line_of[idx][1]] += s
     ops[r[1].split()[0] if not r[1].strip().startswith("@") else r[1].split()[1]] += n
+stalls = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
+stall_tot = collections.Counter()
+for r in data[:len(seen)]:
+    for c in stalls:
+        stall_tot[c] += int(r[h.index(c)] or 0)
+print("stall samples:", ", ".join(f"{k}:{v}" for k, v in stall_tot.most_common(8)))
 print(f"{len(line_of)} SASS instructions, {tot} executed warp-instructions, {tots} samples")
 for k, v in per_line.most_common(top):
     print(f"{str(k):32s} {v:10d} {100 * v / tot:5.1f}%  samples {100 * samp[k] / max(tots, 1):5.1f}%")

@@ -48,9 +48,10 @@ for M, N, K in shapes:
         torch.cuda.synchronize()
         assert rc == 0, lib.b200_last_error()
         ref = torch.nn.functional.elu(X[:, :K] @ W[:, :K].t() + b)
+        e = err(Y[:, :N], ref)
         t_tc = timeit(lambda: lib.b200_tc_linear_forward(p(X), ld(K), p(W), ld(K), p(b), p(Y), ld(N), M, N, K, 1, st))
         t_mma = timeit(lambda: lib.b200_linear_forward(p(X), ld(K), p(W), ld(K), p(b), p(Y), ld(N), M, N, K, 1, 0, st))
-        line += f" fwd err {err(Y[:, :N], ref):.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us |"
+        line += f" fwd err {e:.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us |"
     if "dgrad" in modes:
         Yp = torch.randn(M, ld(K), device=DEV, generator=g)
         dX = torch.ones(M, ld(K), device=DEV)
@@ -58,17 +59,19 @@ for M, N, K in shapes:
         torch.cuda.synchronize()
         assert rc == 0, lib.b200_last_error()
         ref = 1.0 + (dY[:, :N] @ W[:, :K]) * torch.where(Yp[:, :K] > 0, torch.ones((), device=DEV), Yp[:, :K] + 1.0)
+        e = err(dX[:, :K], ref)
         t_tc = timeit(lambda: lib.b200_tc_linear_dgrad(p(dY), ld(N), p(W), ld(K), p(Yp), ld(K), p(dX), ld(K), M, N, K, 0, st))
         t_mma = timeit(lambda: lib.b200_linear_dgrad(p(dY), ld(N), p(W), ld(K), p(Yp), ld(K), p(dX), ld(K), M, N, K, 0, 0, st))
-        line += f" dgrad err {err(dX[:, :K], ref):.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us |"
+        line += f" dgrad err {e:.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us |"
     if "wgrad" in modes:
         dW = torch.full((N, ld(K)), 0.5, device=DEV)
         rc = lib.b200_tc_linear_wgrad(p(dY), ld(N), p(X), ld(K), p(dW), ld(K), M, N, K, st)
         torch.cuda.synchronize()
         assert rc == 0, lib.b200_last_error()
         ref = 0.5 + dY[:, :N].t() @ X[:, :K]
+        e = err(dW[:, :K], ref)
         t_tc = timeit(lambda: lib.b200_tc_linear_wgrad(p(dY), ld(N), p(X), ld(K), p(dW), ld(K), M, N, K, st))
         db = torch.zeros(N, device=DEV)
         t_mma = timeit(lambda: lib.b200_linear_wgrad(p(dY), ld(N), p(X), ld(K), p(dW), ld(K), p(db), M, N, K, 0, st))
-        line += f" wgrad err {err(dW[:, :K], ref):.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us"
+        line += f" wgrad err {e:.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us"
     print(line, flush=True)
