@@ -81,12 +81,14 @@ class Profile:
         rc = raw(*args)
         e1.record()
         flops = bytes_ = 0
-        if name == "b200_linear_forward":
+        if name in ("b200_linear_forward", "b200_tc_linear_forward"):
             flops = 2.0 * args[7] * args[8] * args[9]
-        elif name == "b200_linear_dgrad":
+        elif name in ("b200_linear_dgrad", "b200_tc_linear_dgrad"):
             flops = 2.0 * args[8] * args[9] * args[10]
         elif name == "b200_linear_wgrad":
             flops = 2.0 * args[7] * args[8] * args[9]
+        elif name == "b200_tc_linear_wgrad":
+            flops = 2.0 * args[6] * args[7] * args[8]
         elif name == "b200_post_physics_step":
             bytes_ = ENV_BYTES_PER_ENV * self.n
         elif name == "b200_pd_torques":
@@ -123,6 +125,8 @@ def build_runner(args, rank, world, device, host_physx=False):
     tc["runner"]["resume"] = False
     runner = OnPolicyRunner(env, tc, log_dir=None, device=device, process_group=pg)
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
+    if not args.no_graphs:
+        runner.enable_graphs()
     return env, runner
 
 
@@ -166,18 +170,22 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    prof.count = 0
     elapsed = timed_iterations(runner, W, K, world)
-    launches = prof.count
     sampler.stop_flag = True
     sampler.join(timeout=3)
     value = T_STEPS * N * world * K / elapsed
 
-    # ---- per-kernel timing of ONE more iteration (CUDA events around every ABI call on the launching stream)
+    # ---- per-kernel timing of ONE more iteration, launched eagerly (no graph replay) with CUDA events around every
+    #      ABI call on the launching stream; also counts the kernels one iteration launches
+    graphs = getattr(runner, "use_graphs", False)
+    runner.use_graphs = runner.alg.use_graphs = False
+    prof.count = 0
     prof.timing = True
     runner.iteration(W + K)
     table = prof.table()
     prof.timing = False
+    launches = prof.count * K          # the timed iterations replay exactly these launches (as CUDA graphs when enabled)
+    runner.use_graphs = runner.alg.use_graphs = graphs
     peaks = measured_peaks()
     dom = max(table.items(), key=lambda kv: kv[1][0])
     name, (tsec, n, fl, by) = dom
@@ -209,12 +217,11 @@ def run_b200(args):
             d2h[0] += N * 5
             return out
         env2.step = step_with_readback
-        for it in range(2):
+        for it in range(3):
             runner2.iteration(it)
-        env2.physx.h2d_bytes, d2h[0] = 0, 0
-        t2 = timed_iterations(runner2, 2, args.e2e_steps, world)
+        t2 = timed_iterations(runner2, 3, args.e2e_steps, world)
         e2e = {"value": T_STEPS * N * world * args.e2e_steps / t2, "unit": "env-steps/s",
-               "h2d_bytes_per_step": env2.physx.h2d_bytes // args.e2e_steps, "d2h_bytes_per_step": d2h[0] // args.e2e_steps + 5 * 4,
+               "h2d_bytes_per_step": env2.physx.bytes_per_step * T_STEPS, "d2h_bytes_per_step": T_STEPS * N * 5 + 5 * 4,
                "ms_per_step": t2 / args.e2e_steps * 1e3}
 
     cpu = None
@@ -230,7 +237,8 @@ def run_b200(args):
                                        "PhysX replaced by a ring of replayed synthetic frames",
                            "num_envs_per_gpu": N, "parallelism": f"dp{world} (envs sharded, flat-gradient NCCL all-reduce)",
                            "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
-                           "timed_iterations": f"it {W}..{W + K - 1} (PPO updates; the DAgger iteration it=0 is in the warm-up)"},
+                           "timed_iterations": f"it {W}..{W + K - 1} (PPO updates; the DAgger iteration it=0 is in the warm-up)",
+                           "launch": "CUDA graphs (rollout+GAE: 1 graph; update: 1 graph per minibatch slot)" if not args.no_graphs else "eager"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}
         print(json.dumps(line))
@@ -339,6 +347,7 @@ def main():
     ap.add_argument("--num-envs", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -251,6 +251,11 @@ int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actio
 int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter,
                            void* stream);
 
+/* Same, with `common_step_counter` kept in DEVICE memory: the call increments *step_counter_dev and then uses
+ * it, so a captured CUDA graph of the rollout replays with advancing step numbers. */
+int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream);
+int b200_counter_add(int64_t* counter_dev, int64_t delta, void* stream);
+
 /* Replaces BaseTask.reset's reset_idx(arange(N)) (base_task.py:131-135): resets every env
  * with the curriculum update skipped when `init_done` == 0 (legged_robot.py:551-552). */
 int b200_reset_all(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter,
@@ -315,6 +320,10 @@ int b200_gather_bytes(const uint8_t* src, const int64_t* idx, uint8_t* dst, int6
 /* ActorCritic.act + get_actions_log_prob (actor_critic.py:190-226): a = mu + std*z, z keyed by (seed, step, env, action). */
 int b200_sample_actions(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t step, float* actions, float* logp,
                         float* mu_out, float* sigma_out, int N, int A, void* stream);
+
+/* Same with the noise step counter in device memory (read, then incremented by the call). */
+int b200_sample_actions_dev(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t* step_counter_dev, float* actions,
+                            float* logp, float* mu_out, float* sigma_out, int N, int A, void* stream);
 
 /* PPO.update's loss head, forward + backward (ppo.py:199-270). `sums` receives SUMS over the minibatch of
  * surrogate, value, regularisation and entropy terms (divide by M for the reference's means). */

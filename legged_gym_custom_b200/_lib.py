@@ -17,6 +17,8 @@ SYMBOLS = {
     "b200_env_destroy": (C.c_int, [C.c_void_p]),
     "b200_pd_torques": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_int, C.c_void_p]),
     "b200_post_physics_step": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_void_p]),
+    "b200_post_physics_step_dev": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_void_p]),
+    "b200_counter_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "b200_reset_all": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_int, C.c_void_p]),
     "b200_get_heights": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p]),
     "b200_gae_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
@@ -34,6 +36,8 @@ SYMBOLS = {
     "b200_gather_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200_sample_actions": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p]),
+    "b200_sample_actions_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_void_p]),
     "b200_ppo_loss": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_mse_rows_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200_l2_rows_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -62,7 +66,7 @@ class PpoLossArgs(C.Structure):
 _lib = None
 
 # kernels launched per ABI call (for bench.py's `gpu_launches` and per-kernel timing)
-LAUNCHES = {"b200_post_physics_step": 2, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
+LAUNCHES = {"b200_post_physics_step": 2, "b200_post_physics_step_dev": 3, "b200_sample_actions_dev": 2, "b200_tc_linear_wgrad": 1, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
 
 
 class _Proxy:

@@ -25,9 +25,12 @@ void b200_set_error(const char* fmt, ...) {
 
 constexpr int kWarpsPerCta = 4;
 
+// `step_dev` != nullptr: the step counter lives in device memory (CUDA-graph replay); else `step` is used.
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step) {
+post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
+                    const int64_t* __restrict__ step_dev) {
   __shared__ EnvScratch scratch[kWarpsPerCta];
+  if (step_dev) step = *step_dev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * kWarpsPerCta + warp;
   if (e >= P.num_envs) return;
@@ -190,7 +193,30 @@ int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actio
 int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, void* stream) {
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step")) return rc;
   const int ctas = (env->p.num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
-  post_physics_kernel<<<ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter);
+  post_physics_kernel<<<ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter, nullptr);
+  B200_CHECK_LAUNCH("post_physics_kernel");
+  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+  B200_CHECK_LAUNCH("extras_kernel");
+  return 0;
+}
+
+__global__ void counter_add_kernel(int64_t* c, int64_t delta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *c += delta;
+}
+
+int b200_counter_add(int64_t* counter, int64_t delta, void* stream) {
+  B200_CHECK_ARG(counter, "b200_counter_add: null counter");
+  counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, delta);
+  B200_CHECK_LAUNCH("counter_add_kernel");
+  return 0;
+}
+
+int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream) {
+  if (int rc = check_bufs(env, bufs, "b200_post_physics_step_dev")) return rc;
+  B200_CHECK_ARG(step_counter_dev, "b200_post_physics_step_dev: null counter");
+  counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev, 1);       // go2.py:355
+  const int ctas = (env->p.num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
+  post_physics_kernel<<<ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(env->p, *bufs, 0, step_counter_dev);
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");

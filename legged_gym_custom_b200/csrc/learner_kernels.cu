@@ -92,10 +92,11 @@ gather_bytes_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__
 // actions ~ Normal(mu, std): z from two keyed uniforms (Box-Muller); log_prob summed over actions.
 __global__ void __launch_bounds__(256)
 sample_actions_kernel(const float* __restrict__ mu, int ldmu, const float* __restrict__ std, uint64_t seed, uint32_t step,
-                      float* __restrict__ actions, float* __restrict__ logp, float* __restrict__ mu_out, float* __restrict__ sigma_out,
-                      int N, int A) {
+                      const int64_t* __restrict__ step_dev, float* __restrict__ actions, float* __restrict__ logp,
+                      float* __restrict__ mu_out, float* __restrict__ sigma_out, int N, int A) {
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= N) return;
+  if (step_dev) step = (uint32_t)*step_dev;
   float lp = 0.0f;
   for (int a = 0; a < A; ++a) {
     const float u1 = ((float)(keyed_u32(seed, SITE_ACTION_NOISE, step, e, 2 * a) >> 8) + 0.5f) * 5.9604644775390625e-08f;
@@ -338,9 +339,25 @@ int b200_gather_bytes(const uint8_t* src, const int64_t* idx, uint8_t* dst, int6
 int b200_sample_actions(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t step, float* actions, float* logp,
                         float* mu_out, float* sigma_out, int N, int A, void* stream) {
   B200_CHECK_ARG(mu && std && actions && logp && N > 0 && A > 0 && A <= 16 && ldmu >= A, "b200_sample_actions: bad argument");
-  sample_actions_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, seed, (uint32_t)step, actions, logp, mu_out,
+  sample_actions_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, seed, (uint32_t)step, nullptr, actions, logp,
+                                                                         mu_out, sigma_out, N, A);
+  B200_CHECK_LAUNCH("sample_actions_kernel");
+  return 0;
+}
+
+__global__ void counter_inc_kernel(int64_t* c) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1;
+}
+
+// same, with the noise step counter in device memory; the call increments it afterwards (CUDA-graph replay)
+int b200_sample_actions_dev(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t* step_counter_dev, float* actions,
+                            float* logp, float* mu_out, float* sigma_out, int N, int A, void* stream) {
+  B200_CHECK_ARG(mu && std && actions && logp && step_counter_dev && N > 0 && A > 0 && A <= 16 && ldmu >= A, "b200_sample_actions_dev: bad argument");
+  sample_actions_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, seed, 0, step_counter_dev, actions, logp, mu_out,
                                                                          sigma_out, N, A);
   B200_CHECK_LAUNCH("sample_actions_kernel");
+  counter_inc_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev);
+  B200_CHECK_LAUNCH("counter_inc_kernel");
   return 0;
 }
 

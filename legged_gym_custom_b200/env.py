@@ -121,6 +121,8 @@ class Go2Env:
         self.max_episode_length_s = cfg.env.episode_length_s
         self.max_episode_length = float(np.ceil(self.max_episode_length_s / self.dt))
         self.common_step_counter = 0
+        self.step_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.use_device_counter = False        # True: common_step_counter lives on the device (CUDA-graph replay of the rollout)
         self.init_done = False
         self.reward_names = p.reward_names()
         self.feet_indices = torch.tensor(list(p.feet), device=self.device)
@@ -193,10 +195,17 @@ class Go2Env:
             self.physx.simulate(self, k)
         self.physx.refresh(self)
         self.common_step_counter += 1
-        _lib.check(self.lib.b200_post_physics_step(self._handle, C.byref(b.struct), self.common_step_counter, st))
+        if self.use_device_counter:
+            _lib.check(self.lib.b200_post_physics_step_dev(self._handle, C.byref(b.struct), C.c_void_p(self.step_counter_dev.data_ptr()), st))
+        else:
+            _lib.check(self.lib.b200_post_physics_step(self._handle, C.byref(b.struct), self.common_step_counter, st))
         self.physx.push_state(self)
         return (b["obs_buf"], b["privileged_obs_buf"], b["critic_obs_buf"], b["estimated_obs_buf"], b["scan_obs_buf"],
                 b["rew_buf"], b["reset_buf"], self.extras)
+
+    def set_device_counter(self, enabled=True):
+        self.step_counter_dev.fill_(self.common_step_counter)
+        self.use_device_counter = bool(enabled)
 
     def step5(self, actions):
         """upstream rsl_rl VecEnv 5-tuple (rsl_rl/env/vec_env.py:28): obs, privileged_obs, rew, done, info."""
@@ -314,6 +323,8 @@ class HostPhysX:
             f = synth.make_frames(num_envs, origins, rng, decimation=decimation, **frame_kw)
             self.frames.append({k: torch.from_numpy(v).pin_memory() for k, v in f.items()})
         self.cursor, self.h2d_bytes = -1, 0
+        f0 = self.frames[0]
+        self.bytes_per_step = 4 * (f0["dof"].numel() + f0["root"].numel() + f0["contact"].numel() + f0["rigid"].numel())
 
     def begin_step(self, env):
         self.cursor = (self.cursor + 1) % len(self.frames)

@@ -180,7 +180,10 @@ class PPO:
         self.process_group = process_group            # torch.distributed group for the gradient all-reduce, or None
         self.world_size = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self._perm_gen = torch.Generator(device=self.device).manual_seed(seed + 12345)
-        self.launches = 0
+        self.act_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.use_device_counter = False
+        self.use_graphs = False
+        self._graphs, self._graph_calls = {}, {}
 
     # ---- storage ------------------------------------------------------------------------------------
     def init_storage(self, num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
@@ -244,8 +247,13 @@ class PPO:
         mu = ws.get("mu", N, s.d_act)
         ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
         ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
-        _lib.check(self.lib.b200_sample_actions(_p(mu), s.d_act, ac.main.ptr("std"), self.seed, self.act_counter, _p(s.actions[t]),
-                                                _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act, _lib.stream_ptr()))
+        if self.use_device_counter:
+            _lib.check(self.lib.b200_sample_actions_dev(_p(mu), s.d_act, ac.main.ptr("std"), self.seed, C.c_void_p(self.act_counter_dev.data_ptr()),
+                                                        _p(s.actions[t]), _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act,
+                                                        _lib.stream_ptr()))
+        else:
+            _lib.check(self.lib.b200_sample_actions(_p(mu), s.d_act, ac.main.ptr("std"), self.seed, self.act_counter, _p(s.actions[t]),
+                                                    _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act, _lib.stream_ptr()))
         self.act_counter += 1
         self.transition.actions, self.transition.values = s.actions[t], s.values[t]
         return s.actions[t]
@@ -347,6 +355,27 @@ class PPO:
         chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dscan), ac.scan_latent_dim, M)
         self._adam(ac.main)
 
+    # ---- CUDA graphs: a minibatch is ~90 launches with fixed pointers -> capture once per minibatch slot, replay ----
+    def set_device_counter(self, enabled=True):
+        self.act_counter_dev.fill_(self.act_counter)
+        self.use_device_counter = bool(enabled)
+
+    def _run_captured(self, key, fn):
+        """1st call eager (allocates workspaces, sets kernel attributes), 2nd call captures + replays, then replays."""
+        if not self.use_graphs:
+            return fn()
+        n = self._graph_calls.get(key, 0)
+        self._graph_calls[key] = n + 1
+        if n == 0:
+            return fn()
+        if key not in self._graphs:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+        self._graphs[key].replay()
+
     def update(self):
         """ppo.py:182-293 -> (value_loss, surrogate_loss, reg_loss, reg_coef, estimator_loss)."""
         indices = torch.randperm(self.num_mini_batches * self.mb, device=self.device, generator=self._perm_gen)
@@ -359,7 +388,7 @@ class PPO:
         self.loss_sums.zero_()
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                self._minibatch(i * self.mb, self.mb)
+                self._run_captured(("ppo", i), lambda i=i: self._minibatch(i * self.mb, self.mb))
         n = self.num_learning_epochs * self.num_mini_batches
         sums = (self.loss_sums / (n * self.mb)).tolist()              # the only host read-back of the update
         self.storage.clear()
@@ -396,7 +425,7 @@ class PPO:
         self.loss_sums.zero_()
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                self._dagger_minibatch(i * self.mb, self.mb)
+                self._run_captured(("dagger", i), lambda i=i: self._dagger_minibatch(i * self.mb, self.mb))
         n = self.num_learning_epochs * self.num_mini_batches
         loss = float(self.loss_sums[5].item()) / (n * self.mb)
         self.storage.clear()

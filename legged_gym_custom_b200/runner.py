@@ -57,8 +57,48 @@ class OnPolicyRunner:
         self.rewbuffer, self.lenbuffer = deque(maxlen=100), deque(maxlen=100)
         self.last_losses = {}
 
-    # ---- one iteration = rollout + GAE + update (on_policy_runner.py:144-194) -----------------------------
+    # ---- CUDA graphs ----------------------------------------------------------------------------------------
+    def enable_graphs(self, enabled=True):
+        """Capture the whole rollout (T x [policy inference, 4 PD substeps, post-physics, storage writes] + GAE) and every
+        minibatch of the update as CUDA graphs and replay them: ~2 400 launches per iteration become a handful of
+        graph launches.  Step counters move to device memory so replays see advancing step numbers; the PhysX frame
+        ring must divide T (the replay re-reads the frames baked at capture time in the same order)."""
+        ring = len(getattr(self.env.physx, "frames", [None]))
+        if enabled and self.num_steps_per_env % ring != 0:
+            raise ValueError("PhysX frame ring must divide num_steps_per_env for graph replay")
+        self.use_graphs = bool(enabled)
+        self.env.set_device_counter(enabled)
+        self.alg.set_device_counter(enabled)
+        self.alg.use_graphs = bool(enabled)
+        self._rollout_graphs, self._rollout_calls = {}, {}
+
     def rollout(self, use_adaptation_mode):
+        if not getattr(self, "use_graphs", False):
+            return self._rollout_eager(use_adaptation_mode)
+        key = bool(use_adaptation_mode)
+        n = self._rollout_calls.get(key, 0)
+        self._rollout_calls[key] = n + 1
+        if n == 0:
+            return self._rollout_eager(use_adaptation_mode)          # warm-up: allocations, kernel attributes
+        T = self.num_steps_per_env
+        if key not in self._rollout_graphs:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._rollout_eager(use_adaptation_mode)              # host-side counters advance here, kernels do not run yet
+            self._rollout_graphs[key] = g
+        else:                                                         # replay: advance the host mirrors by hand
+            self.env.common_step_counter += T
+            self.alg.act_counter += T
+            self.alg.storage.step = T
+            if hasattr(self.env.physx, "cursor"):
+                self.env.physx.cursor = (self.env.physx.cursor + T) % len(self.env.physx.frames)
+            if hasattr(self.env.physx, "h2d_bytes"):
+                self.env.physx.h2d_bytes += self.env.physx.bytes_per_step * T
+        self._rollout_graphs[key].replay()
+
+    # ---- one iteration = rollout + GAE + update (on_policy_runner.py:144-194) -----------------------------
+    def _rollout_eager(self, use_adaptation_mode):
         env, alg = self.env, self.alg
         obs, priv, crit = env.get_observations(), env.get_privileged_observations(), env.get_critic_observations()
         est, scan = env.get_estimated_observations(), env.get_scan_observations()

@@ -2,7 +2,7 @@
 
 Tolerances, stated per check:
   * GEMMs in 3xTF32 ('precise') mode are fp32-accurate: <= 5e-5 relative to the output scale vs torch fp32;
-    in TF32 mode (the reference's own GPU matmul precision, train.py:39) <= 3e-3;
+    in TF32 mode (the reference's own GPU matmul precision, train.py:39) <= 3e-3 (mma.sync, rounded) / 1e-2 (tcgen05, truncated);
   * network outputs / losses in precise mode: <= 1e-4 relative;
   * gradients: <= 1e-3 relative to each tensor's rms (fp32 atomics in split-K reorder the sums);
   * post-Adam parameters: 99.9% of the elements within 2% of the largest possible movement (lr * steps) and
@@ -83,7 +83,7 @@ def test_tcgen05_linear_kernels(M, N, K):
     Xd, Wd, bd, dYd = X.to(DEV), W.to(DEV), b.to(DEV), dY.to(DEV)
     p = lambda t: t.data_ptr()
     st = _lib.stream_ptr()
-    tol = 3e-3
+    tol = 1e-2      # kind::tf32 consumes the raw fp32 bits (10-bit mantissa by truncation, as cuBLAS TF32 does)
     Y = torch.zeros(M, ld(N), device=DEV)
     _lib.check(lib.b200_tc_linear_forward(p(Xd), ld(K), p(Wd), ld(K), p(bd), p(Y), ld(N), M, N, K, 1, st))
     assert scale_err(Y[:, :N], torch.nn.functional.elu(X[:, :K] @ W[:, :K].t() + b)) <= tol
