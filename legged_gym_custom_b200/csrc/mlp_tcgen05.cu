@@ -411,15 +411,16 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-// widest N tile that divides the (32-padded) output width while still giving ~a wave of tiles
-int pick_bn(int rows, int cols) {
-  const int nc = (cols + 31) / 32 * 32;
+// N-tile width: the widest of {256,128,64,32} whose padding of `cols` (TMA zero-fills, stores are guarded) wastes
+// <= 13 % of the MMA work, narrowed while the problem would otherwise leave most SMs without a tile.
+int pick_bn(int rows, int cols, int splits_hint = 1) {
   const int m_tiles = (rows + BM - 1) / BM;
   int bn = 32;
   for (int cand : {256, 128, 64, 32}) {
-    if (nc % cand) continue;
+    const int padded = (cols + cand - 1) / cand * cand;
+    if (cand > 32 && padded * 100 > cols * 113) continue;
     bn = cand;
-    if (m_tiles * (nc / cand) >= (num_sms() * 3) / 4) break;
+    if (m_tiles * (padded / cand) * splits_hint >= (num_sms() * 3) / 4) break;
   }
   return bn;
 }
@@ -477,8 +478,7 @@ int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, flo
   B200_CHECK_ARG(M >= 32, "b200_tc_linear_wgrad: needs M >= 32");
   B200_CHECK_ARG(lddy % 4 == 0 && ldx % 4 == 0 && aligned16(dY) && aligned16(X), "b200_tc_linear_wgrad: operands need 16-byte rows");
   // output rows = N (UMMA M, tiles of 128), output cols = K (UMMA N), reduction = M
-  const int kc = (K + 31) / 32 * 32;
-  const int bn = kc % 256 == 0 ? 256 : (kc % 128 == 0 ? 128 : (kc % 64 == 0 ? 64 : 32));
+  const int bn = pick_bn(N, K, 8);      // split-K supplies the parallelism: prefer wide tiles (A is re-read per N tile)
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, dY, M, N, lddy, BK, 1)) return rc;          // A MN-major: box [32 m][32 n]
   if (int rc = make_tmap(&tb, X, M, K, ldx, BK, 1)) return rc;            // B MN-major: box [32 m][32 k]

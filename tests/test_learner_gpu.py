@@ -204,7 +204,7 @@ def test_dagger_matches_reference_golden():
 def test_gradients_match_oracle_full_size(dagger, precise):
     """one minibatch at the real layer sizes (go2_parkour): flat gradients vs torch autograd on the oracle.
     precise=True: 3xTF32 mma.sync kernels (1e-3 of each tensor's rms); precise=False: the production tcgen05 TF32
-    path (3e-2 of each tensor's rms: TF32 inputs through 4-layer forward + backward chains)."""
+    path (5e-2 of each tensor's rms: TF32 inputs through 4-layer forward + backward chains)."""
     hid = dict(actor=[512, 256, 128], critic=[512, 256, 128], priv=[64, 20], scan=[128, 64], est=[256, 128])
     T, N = 4, 96
     ac, est = _build(hid, precise=precise)
@@ -240,7 +240,7 @@ def test_gradients_match_oracle_full_size(dagger, precise):
         group.params = saved
         for k in keys:
             ref = orc.last_grads[k]
-            assert scale_err(gsd[k], ref) <= (1e-3 if precise else 3e-2), (k, scale_err(gsd[k], ref))
+            assert scale_err(gsd[k], ref) <= (1e-3 if precise else 5e-2), (k, scale_err(gsd[k], ref))
 
 
 def test_act_and_storage_vs_oracle():
