@@ -359,6 +359,13 @@ int b200_elu_backward(float* dY, int lddy, const float* Y, int ldy, int M, int N
  * by the call itself so a captured CUDA graph replays correctly (initialise to {0, 0, 1, 1, lr}). */
 int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
                    float grad_scale, float max_norm, float beta1, float beta2, float eps, void* stream);
+/* AdaptationEncoder.forward (support_networks.py:128-175) fused into one fp32 kernel.  X [M, >=520] = observation rows
+ * whose first 10*52 columns are the proprio history.  Weights in the kernel layouts of networks.py: W1 [30][52],
+ * W2 [20][4*32] (tap*32 + channel), W3 [10][2*20], W4 [20][3*12] (step*12 + channel).  proj/c1/c2: optional
+ * [M,320] / [M,80] / [M,36] copies of the hidden activations for the backward pass. */
+int b200_adaptation_forward(const float* X, int ldx, const float* W1, const float* b1, const float* W2, const float* b2,
+                            const float* W3, const float* b3, const float* W4, const float* b4, float* out, int ldo,
+                            float* proj, float* c1, float* c2, int M, void* stream);
 /* db[N] += column sums of dY[M,N] (bias gradient, companion of b200_tc_linear_wgrad) */
 int b200_colsum(const float* dY, int lddy, float* db, int M, int N, void* stream);
 int b200_fill(float* p, float value, int64_t n, void* stream);

@@ -115,21 +115,42 @@ sample_actions_kernel(const float* __restrict__ mu, int ldmu, const float* __res
 
 typedef B200PpoLossArgs PpoLossArgs;
 
-__global__ void __launch_bounds__(256) ppo_loss_kernel(const __grid_constant__ PpoLossArgs p) {
+constexpr int kLossThreads = 128;
+constexpr int kMaxA = 16;
+
+__global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const __grid_constant__ PpoLossArgs p) {
   __shared__ float red[4 * 32];
-  __shared__ float dstd_s[16];
-  if (threadIdx.x < 16) dstd_s[threadIdx.x] = 0.0f;
+  __shared__ float dstd_s[kMaxA];
+  __shared__ float c_s[kMaxA], c_inv2s2[kMaxA], c_logs[kMaxA], c_invs2[kMaxA], c_invs3[kMaxA];
+  if (threadIdx.x < kMaxA) {
+    dstd_s[threadIdx.x] = 0.0f;
+    if (threadIdx.x < p.A) {
+      const float s = p.std[threadIdx.x];
+      c_s[threadIdx.x] = s;
+      c_inv2s2[threadIdx.x] = 1.0f / (2.0f * s * s);
+      c_logs[threadIdx.x] = logf(s);
+      c_invs2[threadIdx.x] = 1.0f / (s * s);
+      c_invs3[threadIdx.x] = 1.0f / (s * s * s);
+    }
+  }
   __syncthreads();
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.x * kLossThreads + threadIdx.x;
   const float invM = 1.0f / (float)p.M;
   float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float dsig[kMaxA];
+#pragma unroll
+  for (int a = 0; a < kMaxA; ++a) dsig[a] = 0.0f;
   if (i < p.M) {
     // log-prob and entropy of Normal(mu, std) (torch.distributions.Normal)
+    float d[kMaxA];
     float lp = 0.0f, ent = 0.0f;
-    for (int a = 0; a < p.A; ++a) {
-      const float s = p.std[a], d = p.actions[(int64_t)i * p.A + a] - p.mu[(int64_t)i * p.ldmu + a];
-      lp += -(d * d) / (2.0f * s * s) - logf(s) - 0.9189385332046727f;
-      ent += 1.4189385332046727f + logf(s);
+#pragma unroll
+    for (int a = 0; a < kMaxA; ++a) {
+      if (a < p.A) {
+        d[a] = p.actions[(int64_t)i * p.A + a] - p.mu[(int64_t)i * p.ldmu + a];
+        lp += -(d[a] * d[a]) * c_inv2s2[a] - c_logs[a] - 0.9189385332046727f;
+        ent += 1.4189385332046727f + c_logs[a];
+      }
     }
     const float adv = p.adv[i];
     const float ratio = expf(lp - p.old_logp[i]);
@@ -140,12 +161,13 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const __grid_constant__ P
     const bool inside = (ratio >= 1.0f - p.clip) && (ratio <= 1.0f + p.clip);
     // d max(s1,s2)/d logp: both branches carry -adv*ratio inside the clip range; outside only s1 does
     const float dlp = (inside || s1 > s2) ? (-adv * ratio) * invM : 0.0f;
-    float dsig_entropy = -p.entropy_coef * invM;
-    for (int a = 0; a < p.A; ++a) {
-      const float s = p.std[a], d = p.actions[(int64_t)i * p.A + a] - p.mu[(int64_t)i * p.ldmu + a];
-      p.dmu[(int64_t)i * p.lddmu + a] = dlp * d / (s * s);
-      const float dsig = dlp * (d * d - s * s) / (s * s * s) + dsig_entropy / s;
-      atomicAdd(&dstd_s[a], dsig);
+    const float dsig_entropy = -p.entropy_coef * invM;
+#pragma unroll
+    for (int a = 0; a < kMaxA; ++a) {
+      if (a < p.A) {
+        p.dmu[(int64_t)i * p.lddmu + a] = dlp * d[a] * c_invs2[a];
+        dsig[a] = dlp * (d[a] * d[a] - c_s[a] * c_s[a]) * c_invs3[a] + dsig_entropy / c_s[a];
+      }
     }
     // value loss (ppo.py:256-264)
     const float v = p.value[(int64_t)i * p.ldv], R = p.returns[i];
@@ -167,8 +189,8 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const __grid_constant__ P
     // ROA regulariser: mean ||latent_p - latent_a||_2 (ppo.py:216)
     float n2 = 0.0f;
     for (int l = 0; l < p.L; ++l) {
-      const float d = p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l];
-      n2 += d * d;
+      const float e = p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l];
+      n2 += e * e;
     }
     const float nrm = sqrtf(n2);
     part[2] = nrm;
@@ -177,6 +199,14 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const __grid_constant__ P
     for (int l = 0; l < p.L; ++l)
       p.dlatent_p[(int64_t)i * p.lddlp + l] = g * (p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l]);
     part[3] = ent;
+  }
+  // d(loss)/d(std): warp shuffle reduction, one shared-memory atomic per warp and action
+#pragma unroll
+  for (int a = 0; a < kMaxA; ++a) {
+    if (a < p.A) {
+      const float t = warp_sum_f(dsig[a]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&dstd_s[a], t);
+    }
   }
   cta_sum<4>(part, red);
   __syncthreads();
@@ -277,6 +307,115 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   }
 }
 
+// ---- fused AdaptationEncoder forward (support_networks.py:128-175): Linear(52,30)+ELU on each of the 10 history
+// steps -> Conv1d(30,20,k4,s2)+ELU -> Conv1d(20,10,k2)+ELU -> Flatten -> Linear(30,20)+ELU, all in fp32 FMAs.
+// 27 k MAC per sample and 5 k parameters: too small for tensor-core tiles (it was 18 GEMM launches), so one CTA
+// keeps all weights in shared memory and walks SAMPLES rows through the four stages.  Weight layouts are the
+// kernel layouts of networks.py: W1 [30][52], W2 [20][4*32] (k*32+ci), W3 [10][2*20] (k*20+ci), W4 [20][3*12] (t*12+c).
+// With save != 0 the intermediate activations are also written in the [M,320] / [M,80] / [M,36] layouts the
+// GEMM-decomposed backward (DAgger) consumes.
+struct AdaptArgs {
+  const float* X; int ldx;
+  const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4;
+  float* out; int ldo;
+  float *proj, *c1, *c2;      // optional [M,320], [M,80], [M,36]
+  int M;
+};
+constexpr int AD_S = 16;       // samples per CTA (static shared memory stays under 48 KB)
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : expf(x) - 1.0f; }
+
+__global__ void __launch_bounds__(256) adapt_forward_kernel(const __grid_constant__ AdaptArgs a) {
+  __shared__ float W1[30 * 53], W2[20 * 121], W3[10 * 41], W4[20 * 31];
+  __shared__ float B1[32], B2[20], B3[12], B4[20];
+  __shared__ float proj[AD_S][10][31];
+  __shared__ float c1[AD_S][4][21];
+  __shared__ float c2[AD_S][3][11];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 30 * 52; i += 256) W1[(i / 52) * 53 + i % 52] = a.W1[i];
+  for (int i = tid; i < 20 * 120; i += 256) {           // drop the two zero-pad channels of each tap
+    const int co = i / 120, r = i % 120, k = r / 30, ci = r % 30;
+    W2[co * 121 + r] = a.W2[co * 128 + k * 32 + ci];
+  }
+  for (int i = tid; i < 10 * 40; i += 256) W3[(i / 40) * 41 + i % 40] = a.W3[i];
+  for (int i = tid; i < 20 * 30; i += 256) {
+    const int o = i / 30, r = i % 30, t = r / 10, c = r % 10;
+    W4[o * 31 + r] = a.W4[o * 36 + t * 12 + c];
+  }
+  if (tid < 30) B1[tid] = a.b1[tid];
+  if (tid < 20) { B2[tid] = a.b2[tid]; B4[tid] = a.b4[tid]; }
+  if (tid < 10) B3[tid] = a.b3[tid];
+  __syncthreads();
+  for (int row0 = blockIdx.x * AD_S; row0 < a.M; row0 += gridDim.x * AD_S) {
+    const int ns = min(AD_S, a.M - row0);
+    // stage 1: one (sample, step) pair per thread, 30 channels each; the 52 inputs sit in registers
+    for (int idx = tid; idx < ns * 10; idx += 256) {
+      const int s = idx / 10, t = idx % 10;
+      const float4* xp = reinterpret_cast<const float4*>(a.X + (int64_t)(row0 + s) * a.ldx + 52 * t);
+      float x[52];
+#pragma unroll
+      for (int i = 0; i < 13; ++i) {
+        const float4 v = __ldg(xp + i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+      for (int c = 0; c < 30; ++c) {
+        float acc = B1[c];
+        const float* w = W1 + c * 53;
+#pragma unroll
+        for (int i = 0; i < 52; ++i) acc = fmaf(x[i], w[i], acc);
+        const float y = elu1(acc);
+        proj[s][t][c] = y;
+        if (a.proj) a.proj[(int64_t)(row0 + s) * 320 + 32 * t + c] = y;
+      }
+    }
+    __syncthreads();
+    // stage 2: Conv1d(30 -> 20, k = 4, stride 2): (sample, t', co)
+    for (int idx = tid; idx < ns * 80; idx += 256) {
+      const int s = idx / 80, r = idx % 80, tp = r / 20, co = r % 20;
+      float acc = B2[co];
+      const float* w = W2 + co * 121;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* p = &proj[s][2 * tp + k][0];
+#pragma unroll
+        for (int ci = 0; ci < 30; ++ci) acc = fmaf(p[ci], w[k * 30 + ci], acc);
+      }
+      const float y = elu1(acc);
+      c1[s][tp][co] = y;
+      if (a.c1) a.c1[(int64_t)(row0 + s) * 80 + 20 * tp + co] = y;
+    }
+    __syncthreads();
+    // stage 3: Conv1d(20 -> 10, k = 2): (sample, t'', co)
+    for (int idx = tid; idx < ns * 30; idx += 256) {
+      const int s = idx / 30, r = idx % 30, tp = r / 10, co = r % 10;
+      float acc = B3[co];
+      const float* w = W3 + co * 41;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float* p = &c1[s][tp + k][0];
+#pragma unroll
+        for (int ci = 0; ci < 20; ++ci) acc = fmaf(p[ci], w[k * 20 + ci], acc);
+      }
+      const float y = elu1(acc);
+      c2[s][tp][co] = y;
+      if (a.c2) a.c2[(int64_t)(row0 + s) * 36 + 12 * tp + co] = y;
+    }
+    __syncthreads();
+    // stage 4: Flatten + Linear(30 -> 20) + ELU: (sample, o)
+    for (int idx = tid; idx < ns * 20; idx += 256) {
+      const int s = idx / 20, o = idx % 20;
+      float acc = B4[o];
+      const float* w = W4 + o * 31;
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int c = 0; c < 10; ++c) acc = fmaf(c2[s][t][c], w[t * 10 + c], acc);
+      a.out[(int64_t)(row0 + s) * a.ldo + o] = elu1(acc);
+    }
+    __syncthreads();
+  }
+}
+
 // db[n] += sum_m dY[m,n]: lane = column, warps stride over a slab of rows, one atomic per column per CTA.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dY, int lddy, float* __restrict__ db, int M, int N, int rows_per_cta) {
@@ -366,7 +505,7 @@ int b200_ppo_loss(const PpoLossArgs* a, void* stream) {
   B200_CHECK_ARG(a->mu && a->std && a->actions && a->old_logp && a->adv && a->returns && a->target_values && a->value && a->latent_p &&
                      a->latent_a && a->dmu && a->dvalue && a->dlatent_p && a->dstd && a->sums,
                  "b200_ppo_loss: null pointer");
-  ppo_loss_kernel<<<(a->M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+  ppo_loss_kernel<<<(a->M + kLossThreads - 1) / kLossThreads, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
   B200_CHECK_LAUNCH("ppo_loss_kernel");
   return 0;
 }
@@ -406,6 +545,19 @@ int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
   B200_CHECK_LAUNCH("sumsq_kernel");
   clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, grad_scale, max_norm, beta1, beta2, eps);
   B200_CHECK_LAUNCH("clip_adam_kernel");
+  return 0;
+}
+
+int b200_adaptation_forward(const float* X, int ldx, const float* W1, const float* b1, const float* W2, const float* b2,
+                            const float* W3, const float* b3, const float* W4, const float* b4, float* out, int ldo, float* proj,
+                            float* c1, float* c2, int M, void* stream) {
+  B200_CHECK_ARG(X && W1 && b1 && W2 && b2 && W3 && b3 && W4 && b4 && out && M > 0, "b200_adaptation_forward: null argument");
+  B200_CHECK_ARG(ldx % 4 == 0 && ldx >= 520 && (((uintptr_t)X) & 15) == 0, "b200_adaptation_forward: X rows must be 16-byte aligned, >= 520 wide");
+  AdaptArgs a{X, ldx, W1, b1, W2, b2, W3, b3, W4, b4, out, ldo, proj, c1, c2, M};
+  int blocks = (M + AD_S - 1) / AD_S;
+  blocks = blocks > 148 * 4 ? 148 * 4 : blocks;
+  adapt_forward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  B200_CHECK_LAUNCH("adapt_forward_kernel");
   return 0;
 }
 

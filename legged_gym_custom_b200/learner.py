@@ -411,7 +411,7 @@ class PPO:
         priv, ldp = _p(self.p_priv) + 4 * r0 * self.p_priv.shape[1], self.p_priv.shape[1]
         lat_p, lat_a, dlat_a = ws.get("lat_p", M, L), ws.get("lat_a", M, L), ws.get("dlat_a", M, L)
         ac.fwd_priv(ws, priv, ldp, _p(lat_p), L, M)
-        ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M)
+        ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M, save=True)
         _lib.check(self.lib.b200_l2_rows_loss(_p(lat_a), L, _p(lat_p), L, _p(dlat_a), L, _p(self.loss_sums, 5), M, L, _lib.stream_ptr()))
         ac.bwd_adapt(ws, X, ld, _p(dlat_a), L, _p(lat_a), L, M)
         self._adam(ac.adapt)

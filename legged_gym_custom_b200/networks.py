@@ -234,6 +234,7 @@ class ActorCritic:
         a.finalize(self.device, learning_rate)
         self._ws = {}
         self._last = None
+        self.fused_adapt = True
         self.load_state_dict(self._random_state_dict(init_noise_std, seed))
 
     # ---- parameters ---------------------------------------------------------------------------------
@@ -348,8 +349,19 @@ class ActorCritic:
     def fwd_critic(self, ws, X, ldx, out, ldo, M):
         chain_forward(self.k, self.critic, ws, "c", X, ldx, out, ldo, M)
 
-    def fwd_adapt(self, ws, X, ldx, out, ldo, M):
-        """AdaptationEncoder.forward (support_networks.py:128-175) on obs rows (history = first 520 columns)."""
+    def fwd_adapt(self, ws, X, ldx, out, ldo, M, save=False):
+        """AdaptationEncoder.forward (support_networks.py:128-175) on obs rows (history = first 520 columns): one fused
+        fp32 kernel; `save` also stores the hidden activations for bwd_adapt (DAgger)."""
+        if self.fused_adapt:
+            a, f, c1_, c2_, o = self.adapt, self.ad_fc, self.ad_c1, self.ad_c2, self.ad_out
+            sv = (ws.ptr("ad_proj", M, 320), ws.ptr("ad_c1", M, 80), ws.ptr("ad_c2", M, 36)) if save else (None, None, None)
+            _lib.check(self.k.lib.b200_adaptation_forward(X, ldx, f.w(), f.b(), c1_.w(), c1_.b(), c2_.w(), c2_.b(), o.w(), o.b(), out, ldo,
+                                                          sv[0], sv[1], sv[2], M, _lib.stream_ptr()))
+            return
+        self._fwd_adapt_gemms(ws, X, ldx, out, ldo, M)
+
+    def _fwd_adapt_gemms(self, ws, X, ldx, out, ldo, M):
+        """the same network as 18 Linear-kernel launches (kept as the cross-check of the fused kernel)."""
         k, NP = self.k, self.num_proprio
         proj = ws.ptr("ad_proj", M, 320)
         for t in range(10):                                    # fc_encoder on each history step
