@@ -175,6 +175,22 @@ def run_b200(args):
     sampler.join(timeout=3)
     value = T_STEPS * N * world * K / elapsed
 
+    # ---- where the time goes: rollout (+GAE) vs update, CUDA events around the two halves of 2 more iterations
+    split = None
+    if world == 1:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tr = tu = 0.0
+        for it in range(W + K, W + K + 2):
+            ev[0].record()
+            runner.rollout(False)
+            ev[1].record()
+            runner.alg.update()
+            ev[2].record()
+            torch.cuda.synchronize()
+            tr += ev[0].elapsed_time(ev[1])
+            tu += ev[1].elapsed_time(ev[2])
+        split = {"rollout_gae_ms": tr / 2, "update_ms": tu / 2}
+
     # ---- per-kernel timing of ONE more iteration, launched eagerly (no graph replay) with CUDA events around every
     #      ABI call on the launching stream; also counts the kernels one iteration launches
     graphs = getattr(runner, "use_graphs", False)
@@ -239,7 +255,7 @@ def run_b200(args):
                            "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
                            "timed_iterations": f"it {W}..{W + K - 1} (PPO updates; the DAgger iteration it=0 is in the warm-up)",
                            "launch": "CUDA graphs (rollout+GAE: 1 graph; update: 1 graph per minibatch slot)" if not args.no_graphs else "eager"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "e2e": e2e, "split": split, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}
         print(json.dumps(line))
     if world > 1:

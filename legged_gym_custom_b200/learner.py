@@ -183,6 +183,7 @@ class PPO:
         self.act_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.use_device_counter = False
         self.use_graphs = False
+        self.use_streams = True
         self._graphs, self._graph_calls = {}, {}
 
     # ---- storage ------------------------------------------------------------------------------------
@@ -237,16 +238,23 @@ class PPO:
             (_p(true_estimated_obs), s.d_est, _p(s._est[t]), s._est.shape[2], s.d_est),
             (_p(scan_obs), s.d_scan, _p(s.scan_observations[t]), s.d_scan, s.d_scan),
         ], N)
-        # estimated obs -> actor input (the rollout acts on the ESTIMATE, ppo.py:134-137)
+        # estimated obs -> actor input (the rollout acts on the ESTIMATE, ppo.py:134-137); the estimator, the latent
+        # encoder, the scan encoder and the critic are independent until the actor's first layer
+        s_lat, s_scan, s_crit = self._fork(3)
         est.fwd(ws, _p(x), ld, _p(x, ac.col_est), ld, N)
-        if adaptation_mode:
-            ac.fwd_adapt(ws, _p(x), ld, _p(x, ac.col_latent), ld, N)
-        else:
-            ac.fwd_priv(ws, _p(s._priv[t]), s._priv.shape[2], _p(x, ac.col_latent), ld, N)
-        ac.fwd_scan(ws, _p(scan_obs), s.d_scan, _p(x, ac.col_scan), ld, N)
+        with self._on(s_lat):
+            if adaptation_mode:
+                ac.fwd_adapt(ws, _p(x), ld, _p(x, ac.col_latent), ld, N)
+            else:
+                ac.fwd_priv(ws, _p(s._priv[t]), s._priv.shape[2], _p(x, ac.col_latent), ld, N)
+        with self._on(s_scan):
+            ac.fwd_scan(ws, _p(scan_obs), s.d_scan, _p(x, ac.col_scan), ld, N)
+        with self._on(s_crit):
+            ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
+        self._join([s_lat, s_scan])
         mu = ws.get("mu", N, s.d_act)
         ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
-        ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
+        self._join([s_crit])
         if self.use_device_counter:
             _lib.check(self.lib.b200_sample_actions_dev(_p(mu), s.d_act, ac.main.ptr("std"), self.seed, C.c_void_p(self.act_counter_dev.data_ptr()),
                                                         _p(s.actions[t]), _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act,
@@ -315,24 +323,27 @@ class PPO:
         crit, scan = _p(self.p_crit) + 4 * r0 * s.d_crit, _p(self.p_scan) + 4 * r0 * s.d_scan
         tgt_est, ldte = _p(self.p_est) + 4 * r0 * self.p_est.shape[1], self.p_est.shape[1]
         L, A = ac.latent_dim, s.d_act
-        # forward
+        mu, val = ws.get("mu", M, A), ws.get("val", M, 4)
+        lat_a, pred, dpred = ws.get("lat_a", M, L), ws.get("pred", M, 4), ws.get("dpred", M, 4)
+        dmu, dval, dlat, dscan = ws.get("dmu", M, A), ws.get("dval", M, 4), ws.get("dlat", M, L), ws.get("dscan", M, ac.scan_latent_dim)
+        s_est, s_crit, s_ad = self._fork(3)
+        # estimator: forward, loss, backward, own optimiser (ppo.py:224-231) -- fully independent chain
+        with self._on(s_est):
+            est.fwd(ws, X, ld, _p(pred), 4, M)
+            _lib.check(self.lib.b200_mse_rows_loss(_p(pred), 4, tgt_est, ldte, _p(dpred), 4, _p(self.loss_sums, 4), M, est.output_dim,
+                                                   _lib.stream_ptr()))
+            chain_backward(est.k, est.layers, ws, "e", X + 4 * est.in_col, ld, _p(dpred), 4, M)
+            self._adam(est.group)
+        with self._on(s_crit):
+            ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
+        with self._on(s_ad):
+            ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M)                  # torch.inference_mode() in the reference (ppo.py:213-214)
+        # main stream: encoders -> actor
         ac.fwd_priv(ws, priv, ldp, X + 4 * ac.col_latent, ld, M)
         ac.fwd_scan(ws, scan, s.d_scan, X + 4 * ac.col_scan, ld, M)
-        mu, val = ws.get("mu", M, A), ws.get("val", M, 4)
         ac.fwd_actor(ws, X, ld, _p(mu), A, M)
-        ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
-        lat_a = ws.get("lat_a", M, L)
-        ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M)                     # torch.inference_mode() in the reference (ppo.py:213-214)
-        pred = ws.get("pred", M, 4)
-        est.fwd(ws, X, ld, _p(pred), 4, M)
-        # estimator: loss, backward, own optimiser (ppo.py:224-231)
-        dpred = ws.get("dpred", M, 4)
-        _lib.check(self.lib.b200_mse_rows_loss(_p(pred), 4, tgt_est, ldte, _p(dpred), 4, _p(self.loss_sums, 4), M, est.output_dim,
-                                               _lib.stream_ptr()))
-        chain_backward(est.k, est.layers, ws, "e", X + 4 * est.in_col, ld, _p(dpred), 4, M)
-        self._adam(est.group)
+        self._join([s_crit, s_ad])
         # PPO loss head (ppo.py:249-270)
-        dmu, dval, dlat, dscan = ws.get("dmu", M, A), ws.get("dval", M, 4), ws.get("dlat", M, L), ws.get("dscan", M, ac.scan_latent_dim)
         a = _lib.PpoLossArgs()
         a.mu, a.ldmu, a.std, a.actions = _p(mu), A, ac.main.ptr("std"), _p(self.p_act) + 4 * r0 * A
         a.old_logp, a.adv = _p(self.p_logp) + 4 * r0, _p(self.p_adv) + 4 * r0
@@ -345,36 +356,18 @@ class PPO:
         a.clip, a.value_coef, a.entropy_coef, a.reg_coef = self.clip_param, self.value_loss_coef, self.entropy_coef, 0.0
         a.use_clipped_value_loss, a.reg_coef_dev = int(self.use_clipped_value_loss), _p(self.reg_coef_dev)
         _lib.check(self.lib.b200_ppo_loss(C.byref(a), _lib.stream_ptr()))
-        # backward: actor (input gradient only for the latent / scan-latent columns), critic, encoders
+        # backward: critic on its own stream; actor (input gradient only for the latent / scan-latent columns) and encoders here
+        self._fork_onto([s_crit])
+        with self._on(s_crit):
+            chain_backward(k, ac.critic, ws, "c", crit, s.d_crit, _p(dval), 4, M)
         chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M)
         da0, lda0 = ws.ptr("da0", M, ceil4(ac.actor[0].N)), ceil4(ac.actor[0].N)
         k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dlat), L, M, accumulate=1, wcol=ac.col_latent, K=L)
         k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dscan), ac.scan_latent_dim, M, accumulate=0, wcol=ac.col_scan, K=ac.scan_latent_dim)
-        chain_backward(k, ac.critic, ws, "c", crit, s.d_crit, _p(dval), 4, M)
         chain_backward(k, ac.priv, ws, "p", priv, ldp, _p(dlat), L, M)
         chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dscan), ac.scan_latent_dim, M)
+        self._join([s_crit, s_est])
         self._adam(ac.main)
-
-    # ---- CUDA graphs: a minibatch is ~90 launches with fixed pointers -> capture once per minibatch slot, replay ----
-    def set_device_counter(self, enabled=True):
-        self.act_counter_dev.fill_(self.act_counter)
-        self.use_device_counter = bool(enabled)
-
-    def _run_captured(self, key, fn):
-        """1st call eager (allocates workspaces, sets kernel attributes), 2nd call captures + replays, then replays."""
-        if not self.use_graphs:
-            return fn()
-        n = self._graph_calls.get(key, 0)
-        self._graph_calls[key] = n + 1
-        if n == 0:
-            return fn()
-        if key not in self._graphs:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn()
-            self._graphs[key] = g
-        self._graphs[key].replay()
 
     def update(self):
         """ppo.py:182-293 -> (value_loss, surrogate_loss, reg_loss, reg_coef, estimator_loss)."""
