@@ -369,6 +369,59 @@ class PPO:
         self._join([s_crit, s_est])
         self._adam(ac.main)
 
+    # ---- side streams: estimator / critic / adaptation-encoder chains are independent of the actor chain until the loss
+    #      head (and, for the backward, until Adam); forking them lets the small and medium kernels overlap.  Under
+    #      CUDA-graph capture the event waits become the fork / join edges of the graph.
+    def _fork(self, n):
+        if not self.use_streams:
+            return [None] * n
+        if not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        self._fork_onto(self._side[:n])
+        return self._side[:n]
+
+    def _fork_onto(self, streams):
+        """make side streams wait for everything queued on the current stream so far"""
+        if not self.use_streams:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        for s in streams:
+            if s is not None:
+                s.wait_event(ev)
+
+    def _on(self, stream):
+        import contextlib
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def _join(self, streams):
+        for s in streams:
+            if s is not None:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                torch.cuda.current_stream().wait_event(ev)
+
+    # ---- CUDA graphs: a minibatch is ~90 launches with fixed pointers -> capture once per minibatch slot, replay ----
+    def set_device_counter(self, enabled=True):
+        self.act_counter_dev.fill_(self.act_counter)
+        self.use_device_counter = bool(enabled)
+
+    def _run_captured(self, key, fn):
+        """1st call eager (allocates workspaces, sets kernel attributes), 2nd call captures + replays, then replays."""
+        if not self.use_graphs:
+            return fn()
+        n = self._graph_calls.get(key, 0)
+        self._graph_calls[key] = n + 1
+        if n == 0:
+            return fn()
+        if key not in self._graphs:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+        self._graphs[key].replay()
+
     def update(self):
         """ppo.py:182-293 -> (value_loss, surrogate_loss, reg_loss, reg_coef, estimator_loss)."""
         indices = torch.randperm(self.num_mini_batches * self.mb, device=self.device, generator=self._perm_gen)
