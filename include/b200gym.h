@@ -158,6 +158,9 @@ typedef struct B200EnvParams {
   int32_t n_termination;
   int32_t termination[B200_NUM_BODIES];
   int32_t hip_joints[4], thigh_joints[4], calf_joints[4];
+  /* largest fp32 s with sqrt_rn(s) <= 1.0 / 0.1: "norm > t" is evaluated as "squared norm > s" (bit-identical masks,
+   * no square root) for the termination (legged_robot.py:146) and collision (:1088) contact tests */
+  float contact_thr2_term, contact_thr2_collision;
   int32_t _pad0;
   uint64_t seed;                       /* Philox key (oracle/philox.py, csrc/philox.cuh) */
 } B200EnvParams;

@@ -61,6 +61,12 @@ struct alignas(16) EnvScratch {
   int32_t last_contacts[4];
   int32_t outliers[32];
   int64_t ep_len, level, type;
+  // element stage (lane-parallel): per-body contact tests, per-dof products, per-leg gait terms, the four angles
+  int32_t body_hit[32];          // bit 0: |F| > 1 (termination test), bit 1: |F| > 0.1 (collision test)
+  float dofv[10][12];            // per-dof contributions of the dof-summed reward terms (rows: DV_*)
+  float leg_sin[4], leg_cos[4];  // sin / cos of 2 pi phase, contact order fl, fr, bl, br
+  int32_t leg_stance[4];
+  float ang[4];                  // roll, pitch, yaw, heading
   // results of the scalar stage
   float blv[4], bav[4], pg[4], rpy[4], phases[8];
   float cmd_out[4], lch_out[4], fat_out[4];
@@ -126,8 +132,12 @@ B200_HD YawQuat yaw_quat(const float* q) {
   r.w = q[3] / n;
   return r;
 }
-B200_HD void height_cell(const B200EnvParams& P, YawQuat yq, const float* root_pos, int j, int* px, int* py) {
-  const float vx = P.scan_x[j / P.scan_ny], vy = P.scan_y[j % P.scan_ny];
+// point j of the x-major scan grid: ix = j / ny without an integer division ((2j+1)/(2ny) is never within 1/(2ny) of an
+// integer, so the fp32 product truncates to the exact quotient for every j < 192, ny <= 24)
+B200_HD void height_cell(const B200EnvParams& P, const float* scan_x, const float* scan_y, YawQuat yq, const float* root_pos, int j,
+                         int* px, int* py) {
+  const int gx = (int)((float)(2 * j + 1) * (0.5f / (float)P.scan_ny));
+  const float vx = scan_x[gx], vy = scan_y[j - gx * P.scan_ny];
   // quat_apply((0,0,z,w), (vx,vy,0)): t = cross * 2; b + w*t + cross(xyz, t)
   const float t0 = -(yq.z * vy) * 2.0f, t1 = (yq.z * vx) * 2.0f;
   float rx = (vx + yq.w * t0) + (-(yq.z * t1));
@@ -241,6 +251,69 @@ B200_HD void publish_reset_state(EnvScratch& S, const ResetState& R, int root_di
   S.reset = reset;
 }
 
+// ---- the element stage: everything that is "the same formula on 19 bodies / 12 dofs / 4 legs / 3 angles" runs with
+// one lane per element instead of a serial loop in the scalar stage.  Contact tests compare the (FMA-accumulated, as
+// torch does) squared norm with the pre-rounded squared threshold: sqrt_rn(s) > t  <=>  s > contact_thr2 exactly.
+enum { DV_ACTION_RATE = 0, DV_DELTA_TORQUES, DV_DOF_ACC, DV_DQ2, DV_POS_LIMITS, DV_VEL2, DV_VEL_LIMITS, DV_ABS_DQ, DV_TORQUE_LIMITS, DV_TORQUES2 };
+
+B200_HD float gait_phase(const B200EnvParams& P, int64_t ep) { return fmodf((float)ep * P.dt, P.period) / P.period; }
+
+B200_HD void env_element_stage(const B200EnvParams& P, EnvScratch& S, int lane) {
+  if (lane < B200_NUM_BODIES) {
+    const float* c = S.contact + lane * 3;
+    const float n2 = B200_FMA(c[2], c[2], B200_FMA(c[1], c[1], c[0] * c[0]));
+    S.body_hit[lane] = (n2 > P.contact_thr2_term ? 1 : 0) | (n2 > P.contact_thr2_collision ? 2 : 0);
+  }
+  if (lane < B200_NUM_DOF) {
+    const int d = lane;
+    const float pos = S.dof[2 * d], vel = S.dof[2 * d + 1];
+    const float dq = pos - P.default_dof_pos[d];
+    S.dofv[DV_ACTION_RATE][d] = sq(S.last_act[d] - S.act[d]);
+    S.dofv[DV_DELTA_TORQUES][d] = sq(S.tq[d] - S.last_tq[d]);
+    S.dofv[DV_DOF_ACC][d] = sq((S.last_dv[d] - vel) / P.dt);
+    S.dofv[DV_DQ2][d] = sq(dq);
+    const float lo = pos - P.dof_pos_lo[d], hi = pos - P.dof_pos_hi[d];
+    S.dofv[DV_POS_LIMITS][d] = -(lo > 0.0f ? 0.0f : lo) + (hi < 0.0f ? 0.0f : hi);
+    S.dofv[DV_VEL2][d] = sq(vel);
+    S.dofv[DV_VEL_LIMITS][d] = clampf(fabsf(vel) - P.dof_vel_limits[d] * P.soft_dof_vel_limit, 0.0f, 1.0f);
+    S.dofv[DV_ABS_DQ][d] = fabsf(dq);
+    const float over = fabsf(S.tq[d]) - P.torque_limits[d] * P.soft_torque_limit;
+    S.dofv[DV_TORQUE_LIMITS][d] = over < 0.0f ? 0.0f : over;
+    S.dofv[DV_TORQUES2][d] = sq(S.tq[d]);
+  }
+  if (lane >= 12 && lane < 16) {                          // gait phase of one leg (go2.py:279-290), order fl, fr, bl, br
+    const int f = lane - 12;
+    const float ph = gait_phase(P, S.ep_len + 1);
+    const float off = f == 0 ? P.fl_offset : (f == 1 ? P.fr_offset : (f == 2 ? P.bl_offset : P.br_offset));
+    const float keep = norm3_fma(S.cmd[0], S.cmd[1], S.cmd[2]) < 0.2f ? 0.0f : 1.0f;
+    const float a = B200_TWO_PI_F * (fmodf(ph + off, 1.0f) * keep);
+    const float sn = sinf(a);
+    S.leg_sin[f] = sn;
+    S.leg_cos[f] = cosf(a);
+    S.leg_stance[f] = sn <= P.stance_threshold;
+  }
+  if (lane >= 16 && lane < 19) {                          // the three atan2 (roll, yaw, heading) share one code path
+    const float x = S.root[3], y = S.root[4], z = S.root[5], w = S.root[6];
+    float num, den;
+    if (lane == 16) {                                     // roll (go2.py:19-21)
+      num = 2.0f * (w * x + y * z);
+      den = 1.0f - 2.0f * (x * x + y * y);
+    } else if (lane == 17) {                              // yaw (go2.py:27-29)
+      num = 2.0f * (w * z + x * y);
+      den = 1.0f - 2.0f * (y * y + z * z);
+    } else {                                              // heading = atan2(fwd.y, fwd.x), fwd = quat_apply(q, (1,0,0))
+      const float t1 = z * 2.0f, t2 = -y * 2.0f;
+      den = 1.0f + (y * t2 - z * t1);
+      num = w * t1 + (-(x * t2));
+    }
+    S.ang[lane == 16 ? 0 : (lane == 17 ? 2 : 3)] = atan2f(num, den);
+  }
+  if (lane == 19) {                                       // pitch (go2.py:23-25)
+    const float x = S.root[3], y = S.root[4], z = S.root[5], w = S.root[6];
+    S.ang[1] = asinf(clampf(2.0f * (w * y - z * x), -1.0f, 1.0f));
+  }
+}
+
 // ---- the scalar stage: everything between "state loaded" and "observations assembled" ---
 // Pure function of the staged inputs: reads S.<in>, computes in registers, writes S.<out> once.
 // Every lane computes the same values (one warp's issue slots, no shuffles, lane-invariant stores).
@@ -264,12 +337,11 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   R.ep_len = ep;
 
   // update_feet_states (go2.py:266-328); leg order of contacts/feet: fl, fr, bl, br
-  const float ph = fmodf((float)ep * P.dt, P.period) / P.period;
+  const float ph = gait_phase(P, ep);
   const float keep = norm3_fma(R.cmd[0], R.cmd[1], R.cmd[2]) < 0.2f ? 0.0f : 1.0f;
   const float ph_fr = fmodf(ph + P.fr_offset, 1.0f) * keep, ph_fl = fmodf(ph + P.fl_offset, 1.0f) * keep;
   const float ph_bl = fmodf(ph + P.bl_offset, 1.0f) * keep, ph_br = fmodf(ph + P.br_offset, 1.0f) * keep;
   S.phases[0] = ph; S.phases[1] = ph_fr; S.phases[2] = ph_fl; S.phases[3] = ph_bl; S.phases[4] = ph_br;
-  const float leg_phase[4] = {ph_fl, ph_fr, ph_bl, ph_br};
   int filt[4];
   for (int f = 0; f < 4; ++f) {
     const int cur = S.contact[P.feet[f] * 3 + 2] > 1.0f;
@@ -280,20 +352,15 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
     R.fat[f] = S.fat[f];
   }
 
-  float roll, pitch;
-  {                                                     // quaternion_to_euler (go2.py:11-31)
-    const float x = q[0], y = q[1], z = q[2], w = q[3];
-    roll = atan2f(2.0f * (w * x + y * z), 1.0f - 2.0f * (x * x + y * y));
-    pitch = asinf(clampf(2.0f * (w * y - z * x), -1.0f, 1.0f));
-    S.rpy[0] = roll;
-    S.rpy[1] = pitch;
-    S.rpy[2] = atan2f(2.0f * (w * z + x * y), 1.0f - 2.0f * (y * y + z * z));
-  }
+  const float roll = S.ang[0], pitch = S.ang[1];        // quaternion_to_euler (go2.py:11-31), element stage
+  S.rpy[0] = roll;
+  S.rpy[1] = pitch;
+  S.rpy[2] = S.ang[2];
 
   // _post_physics_step_callback (go2.py:390-410)
   float* cmd = R.cmd;
   if (ep % P.resample_interval == 0) resample_commands(P, SITE_CMD_PERIODIC, step, e, q, cmd);
-  const float heading = heading_of(q);
+  const float heading = S.ang[3];
   if (P.heading_command) cmd[2] = clampf(wrap_to_pi(cmd[3] - heading) * P.heading_error_gain, -1.0f, 1.0f);
   int root_dirty = 0;
   if (P.push_robots && (step64 % P.push_interval) == 0) {   // legged_robot.py:535-540
@@ -306,10 +373,7 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
 
   // check_termination (go2.py:186-204)
   int reset = 0;
-  for (int i = 0; i < P.n_termination; ++i) {
-    const float* f = S.contact + P.termination[i] * 3;
-    reset |= norm3_fma(f[0], f[1], f[2]) > 1.0f;
-  }
+  for (int i = 0; i < P.n_termination; ++i) reset |= S.body_hit[P.termination[i]] & 1;
   const int time_out = ep > P.max_episode_length;
   reset |= time_out;
   reset |= pg.z > 0.0f;
@@ -322,9 +386,12 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   const float cmd_n3 = norm3_fma(cmd[0], cmd[1], cmd[2]);
   const float moving = cmd_n3 >= 0.2f ? 1.0f : 0.0f;
   const float jumping = S.jump_flag > 0.0f ? 1.0f : 0.0f;
-  int stance[4];
-  for (int f = 0; f < 4; ++f) stance[f] = sinf(B200_TWO_PI_F * leg_phase[f]) <= P.stance_threshold;
-#define B200_DQ(d) (S.dof[2 * (d)] - P.default_dof_pos[(d)])
+  const int stance[4] = {S.leg_stance[0], S.leg_stance[1], S.leg_stance[2], S.leg_stance[3]};
+#define B200_DOFSUM(ROW, OUT)                                   \
+  {                                                             \
+    OUT = 0.0f;                                                 \
+    for (int d_ = 0; d_ < 12; ++d_) OUT += S.dofv[ROW][d_];      \
+  }
 #define B200_TERM(NAME, EXPR)                         \
   {                                                   \
     float r_ = 0.0f;                                  \
@@ -336,8 +403,7 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   }
   {
     float a = 0.0f;
-    if (sc[B200_REW_action_rate] != 0.0f)
-      for (int d = 0; d < 12; ++d) a += sq(S.last_act[d] - S.act[d]);
+    if (sc[B200_REW_action_rate] != 0.0f) B200_DOFSUM(DV_ACTION_RATE, a)
     B200_TERM(action_rate, a)
   }
   B200_TERM(ang_vel_xy, sq(bav.x) + sq(bav.y))
@@ -352,16 +418,13 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   {
     float a = 0.0f;
     if (sc[B200_REW_calf_collision] != 0.0f)
-      for (int f = 0; f < 4; ++f) {
-        const float* c = S.contact + P.calves[f] * 3;
-        a += norm3_fma(c[0], c[1], c[2]) > 0.1f ? 1.0f : 0.0f;
-      }
+      for (int f = 0; f < 4; ++f) a += (S.body_hit[P.calves[f]] & 2) ? 1.0f : 0.0f;
     B200_TERM(calf_collision, a)
   }
   {
     float a = 0.0f;
     if (sc[B200_REW_calf_pos] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += sq(B200_DQ(P.calf_joints[f]));
+      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.calf_joints[f]];
     B200_TERM(calf_pos, a)
   }
   B200_TERM(calf_symmetry, fabsf(S.dof[2 * P.calf_joints[0]] - S.dof[2 * P.calf_joints[1]]) +
@@ -369,46 +432,35 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   {
     float a = 0.0f;
     if (sc[B200_REW_collision] != 0.0f)
-      for (int i = 0; i < P.n_penalised; ++i) {
-        const float* c = S.contact + P.penalised[i] * 3;
-        a += norm3_fma(c[0], c[1], c[2]) > 0.1f ? 1.0f : 0.0f;
-      }
+      for (int i = 0; i < P.n_penalised; ++i) a += (S.body_hit[P.penalised[i]] & 2) ? 1.0f : 0.0f;
     B200_TERM(collision, a)
   }
   {
     float a = 0.0f;
-    if (sc[B200_REW_delta_torques] != 0.0f)
-      for (int d = 0; d < 12; ++d) a += sq(S.tq[d] - S.last_tq[d]);
+    if (sc[B200_REW_delta_torques] != 0.0f) B200_DOFSUM(DV_DELTA_TORQUES, a)
     B200_TERM(delta_torques, a)
   }
   {
     float a = 0.0f;
-    if (sc[B200_REW_dof_acc] != 0.0f)
-      for (int d = 0; d < 12; ++d) a += sq((S.last_dv[d] - S.dof[2 * d + 1]) / P.dt);
+    if (sc[B200_REW_dof_acc] != 0.0f) B200_DOFSUM(DV_DOF_ACC, a)
     B200_TERM(dof_acc, a)
   }
-  float dof_err = 0.0f;
-  for (int d = 0; d < 12; ++d) dof_err += sq(B200_DQ(d));
+  float dof_err;
+  B200_DOFSUM(DV_DQ2, dof_err)
   B200_TERM(dof_error, dof_err)
   {
     float a = 0.0f;
-    if (sc[B200_REW_dof_pos_limits] != 0.0f)
-      for (int d = 0; d < 12; ++d) {
-        const float lo = S.dof[2 * d] - P.dof_pos_lo[d], hi = S.dof[2 * d] - P.dof_pos_hi[d];
-        a += -(lo > 0.0f ? 0.0f : lo) + (hi < 0.0f ? 0.0f : hi);
-      }
+    if (sc[B200_REW_dof_pos_limits] != 0.0f) B200_DOFSUM(DV_POS_LIMITS, a)
     B200_TERM(dof_pos_limits, a)
   }
   {
     float a = 0.0f;
-    if (sc[B200_REW_dof_vel] != 0.0f)
-      for (int d = 0; d < 12; ++d) a += sq(S.dof[2 * d + 1]);
+    if (sc[B200_REW_dof_vel] != 0.0f) B200_DOFSUM(DV_VEL2, a)
     B200_TERM(dof_vel, a)
   }
   {
     float a = 0.0f;
-    if (sc[B200_REW_dof_vel_limits] != 0.0f)
-      for (int d = 0; d < 12; ++d) a += clampf(fabsf(S.dof[2 * d + 1]) - P.dof_vel_limits[d] * P.soft_dof_vel_limit, 0.0f, 1.0f);
+    if (sc[B200_REW_dof_vel_limits] != 0.0f) B200_DOFSUM(DV_VEL_LIMITS, a)
     B200_TERM(dof_vel_limits, a)
   }
   {                                                     // go2.py:819-831 (stateful)
@@ -449,7 +501,7 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   {
     float a = 0.0f;
     if (sc[B200_REW_hip_pos] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += sq(B200_DQ(P.hip_joints[f]));
+      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.hip_joints[f]];
     B200_TERM(hip_pos, a)
   }
   B200_TERM(jump_zone_forward_vel, (root[7] < 0.0f ? 0.0f : root[7]) * jumping * moving)
@@ -474,7 +526,7 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   {
     float a = 0.0f;
     if (sc[B200_REW_stand_still] != 0.0f) {
-      for (int d = 0; d < 12; ++d) a += fabsf(B200_DQ(d));
+      B200_DOFSUM(DV_ABS_DQ, a)
       a *= norm2_fma(cmd[0], cmd[1]) < 0.1f ? 1.0f : 0.0f;
     }
     B200_TERM(stand_still, a)
@@ -500,24 +552,19 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   {
     float a = 0.0f;
     if (sc[B200_REW_thigh_pos] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += sq(B200_DQ(P.thigh_joints[f]));
+      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.thigh_joints[f]];
     B200_TERM(thigh_pos, a)
   }
   B200_TERM(thigh_symmetry, fabsf(S.dof[2 * P.thigh_joints[0]] - S.dof[2 * P.thigh_joints[1]]) +
                                 fabsf(S.dof[2 * P.thigh_joints[2]] - S.dof[2 * P.thigh_joints[3]]))
   {
     float a = 0.0f;
-    if (sc[B200_REW_torque_limits] != 0.0f)
-      for (int d = 0; d < 12; ++d) {
-        const float over = fabsf(S.tq[d]) - P.torque_limits[d] * P.soft_torque_limit;
-        a += over < 0.0f ? 0.0f : over;
-      }
+    if (sc[B200_REW_torque_limits] != 0.0f) B200_DOFSUM(DV_TORQUE_LIMITS, a)
     B200_TERM(torque_limits, a)
   }
   {
     float a = 0.0f;
-    if (sc[B200_REW_torques] != 0.0f)
-      for (int d = 0; d < 12; ++d) a += sq(S.tq[d]);
+    if (sc[B200_REW_torques] != 0.0f) B200_DOFSUM(DV_TORQUES2, a)
     B200_TERM(torques, a)
   }
   B200_TERM(tracking_ang_vel, expf(-sq(cmd[2] - bav.z) / P.tracking_sigma))
@@ -535,7 +582,7 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
     S.term[B200_REW_termination] = r_;
   }
 #undef B200_TERM
-#undef B200_DQ
+#undef B200_DOFSUM
   S.rew = rew;
 
   // reset_idx on this env if flagged (go2.py:375-376)
@@ -558,7 +605,7 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
 }
 
 // ---- one element of cur_obs (go2.py:506-519) ----------------------------------------------
-B200_HD float cur_obs_element(const B200EnvParams& P, const EnvScratch& S, uint32_t step, uint32_t e, int i) {
+B200_HD float cur_obs_element(const B200EnvParams& P, const EnvScratch& S, float u, int i) {
   float v;
   if (i < 3) v = S.bav[i] * P.obs_ang_vel;
   else if (i < 5) v = S.rpy[i - 3];
@@ -566,14 +613,12 @@ B200_HD float cur_obs_element(const B200EnvParams& P, const EnvScratch& S, uint3
   else if (i < 20) v = (S.dof_out[2 * (i - 8)] - P.default_dof_pos[i - 8]) * P.obs_dof_pos;
   else if (i < 32) v = S.dof_out[2 * (i - 20) + 1] * P.obs_dof_vel;
   else if (i < 44) v = S.act[i - 32];
-  else {                                                // sin/cos of fr, fl, bl, br (go2.py:476-481)
-    const float a = B200_TWO_PI_F * S.phases[1 + ((i - 44) >> 1)];
-    v = ((i - 44) & 1) ? cosf(a) : sinf(a);
+  else {                                                // sin/cos of fr, fl, bl, br (go2.py:476-481); scratch order fl, fr, bl, br
+    const int leg = (i - 44) >> 1;
+    const int f = leg == 0 ? 1 : (leg == 1 ? 0 : leg);
+    v = ((i - 44) & 1) ? S.leg_cos[f] : S.leg_sin[f];
   }
-  if (P.add_noise) {
-    const float u = keyed_uniform(P.seed, SITE_OBS_NOISE, step, e, (uint32_t)i);
-    v += (2.0f * u - 1.0f) * P.noise_vec[i];
-  }
+  if (P.add_noise) v += (2.0f * u - 1.0f) * P.noise_vec[i];
   return v;
 }
 
@@ -588,8 +633,9 @@ B200_HD f4_ clamp4(f4_ v, float c) {
 // ---- the whole env step for env `e`, lanes [lane_lo, lane_hi) -------------------------------
 // Row sizes are multiples of 4 floats for the go2 layout (52, 520, 572, 736, 132, critic tail 164),
 // so the bulk rows move as 16-byte vectors; `vec_ok` (warp-uniform) falls back to scalars otherwise.
-B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, int e, int64_t step64,
-                           int lane_lo, int lane_hi) {
+// scan_x / scan_y: the scan-point tables (shared-memory copies on the GPU, P.scan_x / P.scan_y on the host)
+B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* scan_x, const float* scan_y,
+                           int e, int64_t step64, int lane_lo, int lane_hi) {
   const int NP = B200_PROPRIO, H = P.history_len, NS = P.num_scan;
   const int HN = H * NP, OBS = HN + NP;
   const int TAIL = P.num_priv + P.num_est + NS;
@@ -642,7 +688,7 @@ B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvS
       const YawQuat yq = yaw_quat(S.root + 3);
       for (int j = lane; j < NS; j += 32) {
         int px, py;
-        height_cell(P, yq, S.root, j, &px, &py);
+        height_cell(P, scan_x, scan_y, yq, S.root, j, &px, &py);
         const float h = height_at(P, B.height_samples, px, py);
         S.heights[j] = h;
         n_out += fabsf(h) > 0.1f;
@@ -656,6 +702,10 @@ B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvS
     }
     S.outliers[lane] = n_out;
   }
+  B200_WARP_SYNC();
+
+  // ---- stage 2a: element stage (one lane per body / dof / leg / angle)
+  B200_FOR_LANES(lane) { env_element_stage(P, S, lane); }
   B200_WARP_SYNC();
 
   // ---- stage 2: scalar logic (lane-invariant)
@@ -672,7 +722,20 @@ B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvS
     if (S.reset) {                                        // obs_history_buf[env_ids] = 0 (go2.py:238)
       for (int i = lane; i < HN; i += 32) S.histcur[i] = 0.0f;
     }
-    for (int i = lane; i < NP; i += 32) S.histcur[HN + i] = cur_obs_element(P, S, (uint32_t)step64, (uint32_t)e, i);
+    {
+      // observation noise (go2.py:519): elements lane and lane + 32 take words (lane >> 4) and (lane >> 4) + 2 of ONE
+      // Philox block (block = lane & 15) -- the keyed lane numbering of oracle/philox.py::noise_lane
+      Philox4 r;
+      if (P.add_noise) r = keyed_block(P.seed, SITE_OBS_NOISE, (uint32_t)step64, (uint32_t)e, (uint32_t)(lane & 15));
+      for (int i = lane; i < NP; i += 32) {
+        float u = 0.0f;
+        if (P.add_noise) {
+          const uint32_t w = (uint32_t)(i >> 4);
+          u = u32_to_uniform(w == 0 ? r.v[0] : (w == 1 ? r.v[1] : (w == 2 ? r.v[2] : r.v[3])));
+        }
+        S.histcur[HN + i] = cur_obs_element(P, S, u, i);
+      }
+    }
     for (int i = lane; i < P.num_priv; i += 32) {         // go2.py:528-532
       float v;
       if (i < 4) v = B200_LDG(B.priv_mass_params + (int64_t)e * 4 + i);

@@ -26,15 +26,21 @@ void b200_set_error(const char* fmt, ...) {
 constexpr int kWarpsPerCta = 4;
 
 // `step_dev` != nullptr: the step counter lives in device memory (CUDA-graph replay); else `step` is used.
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6)
 post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
                     const int64_t* __restrict__ step_dev) {
   __shared__ EnvScratch scratch[kWarpsPerCta];
+  __shared__ float scan_x[B200_MAX_SCAN_AXIS], scan_y[B200_MAX_SCAN_AXIS];
+  if (threadIdx.x < B200_MAX_SCAN_AXIS) {
+    scan_x[threadIdx.x] = P.scan_x[threadIdx.x];
+    scan_y[threadIdx.x] = P.scan_y[threadIdx.x];
+  }
+  __syncthreads();
   if (step_dev) step = *step_dev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * kWarpsPerCta + warp;
   if (e >= P.num_envs) return;
-  env_warp_step(P, B, scratch[warp], e, step, lane, lane + 1);
+  env_warp_step(P, B, scratch[warp], scan_x, scan_y, e, step, lane, lane + 1);
 }
 
 __global__ void __launch_bounds__(256)
@@ -62,7 +68,7 @@ heights_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ 
   if (P.has_height_samples) {
     float root[7];
     for (int i = 0; i < 7; ++i) root[i] = B.root_states[(int64_t)e * 13 + i];
-    height_cell(P, yaw_quat(root + 3), root, j, &px, &py);
+    height_cell(P, P.scan_x, P.scan_y, yaw_quat(root + 3), root, j, &px, &py);
     h = height_at(P, B.height_samples, px, py);
   }
   B.measured_heights[idx] = h;

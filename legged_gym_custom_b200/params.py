@@ -69,7 +69,8 @@ class EnvParams(C.Structure):
         ("pitch_deg_target", f32), ("roll_deg_target", f32),
         ("feet", i32 * NUM_FEET), ("calves", i32 * NUM_FEET), ("n_penalised", i32), ("penalised", i32 * NUM_BODIES),
         ("n_termination", i32), ("termination", i32 * NUM_BODIES),
-        ("hip_joints", i32 * 4), ("thigh_joints", i32 * 4), ("calf_joints", i32 * 4), ("_pad0", i32),
+        ("hip_joints", i32 * 4), ("thigh_joints", i32 * 4), ("calf_joints", i32 * 4),
+        ("contact_thr2_term", f32), ("contact_thr2_collision", f32), ("_pad0", i32),
         ("seed", C.c_uint64),
     ]
 
@@ -93,6 +94,17 @@ BUFFER_FIELDS = [
 
 class EnvBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BUFFER_FIELDS]
+
+
+def sqrt_threshold_squared(t):
+    """largest float32 s with sqrt_rn(s) <= t, so that  sqrt(s) > t  <=>  s > result  (exactly, for every float32 s)"""
+    t = np.float32(t)
+    s = np.float32(t * t)
+    while np.sqrt(s, dtype=np.float32) <= t:
+        s = np.nextafter(s, np.float32(np.inf), dtype=np.float32)
+    while np.sqrt(s, dtype=np.float32) > t:
+        s = np.nextafter(s, np.float32(-np.inf), dtype=np.float32)
+    return float(s)
 
 
 def _get(ns, name, default=None):
@@ -230,5 +242,7 @@ def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shap
         p.hip_joints[i] = DOF_NAMES.index(f"{leg}_hip_joint")
         p.thigh_joints[i] = DOF_NAMES.index(f"{leg}_thigh_joint")
         p.calf_joints[i] = DOF_NAMES.index(f"{leg}_calf_joint")
+    p.contact_thr2_term = sqrt_threshold_squared(1.0)
+    p.contact_thr2_collision = sqrt_threshold_squared(0.1)
     p.seed = int(seed)
     return p

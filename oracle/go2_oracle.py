@@ -495,7 +495,7 @@ class Go2Oracle:
                          st["actions"],
                          torch.stack(feat, dim=1)), dim=-1)
         if p.add_noise:
-            u = self._u(philox.SITE_OBS_NOISE, torch.arange(N), list(range(p.num_proprio)))
+            u = self._u(philox.SITE_OBS_NOISE, torch.arange(N), philox.noise_lane(np.arange(p.num_proprio)))
             cur += (2 * u - 1) * self.noise_vec
         o["obs_buf"] = torch.cat([st["obs_history_buf"].view(N, -1), cur], dim=-1)
         o["privileged_obs_buf"] = torch.cat((self.mass, self.fric, self.kp_kd[0] - 1, self.kp_kd[1] - 1), dim=-1)

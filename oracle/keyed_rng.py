@@ -71,6 +71,8 @@ def _lanes(shape):
         assert shape[0] == n and len(shape) == 2, (shape, n)
         width = shape[1]
     lanes = np.arange(c["lane"], c["lane"] + width)
+    if c["site"] == philox.SITE_OBS_NOISE:
+        lanes = philox.noise_lane(lanes)
     c["lane"] += width
     return lanes, shape
 

@@ -32,6 +32,13 @@ SITE_OBS_NOISE = 6      # go2.py:519 rand_like; lanes 0..num_proprio-1
 SITE_ACTION_NOISE = 7   # actor_critic.py:204 Normal.sample; lanes 2a, 2a+1 (Box-Muller pair of action a)
 
 
+def noise_lane(i):
+    """Observation-noise element i -> keyed lane.  Elements i and i+32 (the two a GPU lane owns) share one Philox
+    block: block = i & 15, word = i >> 4  (csrc/env_core.cuh stage 3)."""
+    i = np.asarray(i)
+    return ((i & 15) << 2) | (i >> 4)
+
+
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
     """Vectorised Philox4x32-10 (Salmon et al., SC'11). All args broadcastable uint32 arrays."""
     c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint64) & MASK for c in np.broadcast_arrays(c0, c1, c2, c3)]
