@@ -116,7 +116,17 @@ B200_HD float wrap_to_pi(float a) {
   return r - (r > B200_PI_F ? B200_TWO_PI_F : 0.0f);
 }
 
-B200_HD float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }   // NaN passes through like torch.clip
+// torch.clip semantics (NaN passes through).  Device: max.NaN / min.NaN, two instructions.
+B200_HD float clampf(float v, float lo, float hi) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(hi));
+  return r;
+#else
+  return v < lo ? lo : (v > hi ? hi : v);
+#endif
+}
 B200_HD float sq(float v) { return v * v; }
 
 // ---- height scan: one point (legged_robot.py:1018-1025, math.py:38-42) ------------------
@@ -152,16 +162,20 @@ B200_HD void height_cell(const B200EnvParams& P, const float* scan_x, const floa
     rx = rx * inv;
     ry = ry * inv;
   }
-  int64_t ix = (int64_t)rx, iy = (int64_t)ry;          // .long(): truncation toward zero
+  // .long() truncates toward zero; clamp first so the 32-bit conversion cannot overflow (the clip to [0, n-2] that
+  // follows makes the result identical to the int64 path for every finite input)
+  const float hx = (float)(P.hs_rows - 1), hy = (float)(P.hs_cols - 1);
+  int ix = (int)(rx < -1.0f ? -1.0f : (rx > hx ? hx : rx)), iy = (int)(ry < -1.0f ? -1.0f : (ry > hy ? hy : ry));
   ix = ix < 0 ? 0 : (ix > P.hs_rows - 2 ? P.hs_rows - 2 : ix);
   iy = iy < 0 ? 0 : (iy > P.hs_cols - 2 ? P.hs_cols - 2 : iy);
-  *px = (int)ix;
-  *py = (int)iy;
+  *px = ix;
+  *py = iy;
 }
 B200_HD float height_at(const B200EnvParams& P, const int16_t* hs, int px, int py) {
-  const int16_t a = B200_LDG(hs + (int64_t)px * P.hs_cols + py);
-  const int16_t b = B200_LDG(hs + (int64_t)(px + 1) * P.hs_cols + py);
-  const int16_t c = B200_LDG(hs + (int64_t)px * P.hs_cols + py + 1);
+  const int16_t* p = hs + (px * P.hs_cols + py);        // rows * cols < 2^31 (checked at env creation)
+  const int16_t a = B200_LDG(p);
+  const int16_t b = B200_LDG(p + P.hs_cols);
+  const int16_t c = B200_LDG(p + 1);
   int16_t m = a < b ? a : b;
   m = m < c ? m : c;
   return (float)m * P.vertical_scale;
@@ -286,7 +300,10 @@ B200_HD void env_element_stage(const B200EnvParams& P, EnvScratch& S, int lane) 
     const float ph = gait_phase(P, S.ep_len + 1);
     const float off = f == 0 ? P.fl_offset : (f == 1 ? P.fr_offset : (f == 2 ? P.bl_offset : P.br_offset));
     const float keep = norm3_fma(S.cmd[0], S.cmd[1], S.cmd[2]) < 0.2f ? 0.0f : 1.0f;
-    const float a = B200_TWO_PI_F * (fmodf(ph + off, 1.0f) * keep);
+    const float phf = fmodf(ph + off, 1.0f) * keep;
+    S.phases[f == 0 ? 2 : (f == 1 ? 1 : (f + 1))] = phf;      // API order: phase, fr, fl, bl, br
+    if (f == 0) S.phases[0] = ph;
+    const float a = B200_TWO_PI_F * phf;
     const float sn = sinf(a);
     S.leg_sin[f] = sn;
     S.leg_cos[f] = cosf(a);
@@ -337,11 +354,6 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   R.ep_len = ep;
 
   // update_feet_states (go2.py:266-328); leg order of contacts/feet: fl, fr, bl, br
-  const float ph = gait_phase(P, ep);
-  const float keep = norm3_fma(R.cmd[0], R.cmd[1], R.cmd[2]) < 0.2f ? 0.0f : 1.0f;
-  const float ph_fr = fmodf(ph + P.fr_offset, 1.0f) * keep, ph_fl = fmodf(ph + P.fl_offset, 1.0f) * keep;
-  const float ph_bl = fmodf(ph + P.bl_offset, 1.0f) * keep, ph_br = fmodf(ph + P.br_offset, 1.0f) * keep;
-  S.phases[0] = ph; S.phases[1] = ph_fr; S.phases[2] = ph_fl; S.phases[3] = ph_bl; S.phases[4] = ph_br;
   int filt[4];
   for (int f = 0; f < 4; ++f) {
     const int cur = S.contact[P.feet[f] * 3 + 2] > 1.0f;
@@ -359,11 +371,11 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
 
   // _post_physics_step_callback (go2.py:390-410)
   float* cmd = R.cmd;
-  if (ep % P.resample_interval == 0) resample_commands(P, SITE_CMD_PERIODIC, step, e, q, cmd);
+  if ((uint32_t)ep % (uint32_t)P.resample_interval == 0u) resample_commands(P, SITE_CMD_PERIODIC, step, e, q, cmd);
   const float heading = S.ang[3];
   if (P.heading_command) cmd[2] = clampf(wrap_to_pi(cmd[3] - heading) * P.heading_error_gain, -1.0f, 1.0f);
   int root_dirty = 0;
-  if (P.push_robots && (step64 % P.push_interval) == 0) {   // legged_robot.py:535-540
+  if (P.push_robots && ((uint32_t)step64 % (uint32_t)P.push_interval) == 0u) {   // legged_robot.py:535-540
     const float span = P.max_push_vel - -P.max_push_vel;
     R.root[7] = span * keyed_uniform(P.seed, SITE_PUSH, step, e, 0) + -P.max_push_vel;
     R.root[8] = span * keyed_uniform(P.seed, SITE_PUSH, step, e, 1) + -P.max_push_vel;
@@ -766,8 +778,11 @@ B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvS
         obs4[i] = v;
         crit4[i] = v;
       }
-      for (int i = lane; i < HN / 4; i += 32)             // history <- shift left one slot, or cur x H
-        hist4[i] = refill ? hc[HN / 4 + i % (NP / 4)] : hc[i + NP / 4];
+      if (!refill) {                                      // history <- shift left one slot ...
+        for (int i = lane; i < HN / 4; i += 32) hist4[i] = hc[i + NP / 4];
+      } else {                                            // ... or cur x H right after a reset (go2.py:570-574)
+        for (int i = lane; i < HN / 4; i += 32) hist4[i] = hc[HN / 4 + i % (NP / 4)];
+      }
       const f4_* t4 = reinterpret_cast<const f4_*>(S.tail);
       for (int i = lane; i < TAIL / 4; i += 32) crit4[OBS / 4 + i] = t4[i];
       const f4_* s4 = reinterpret_cast<const f4_*>(S.tail + P.num_priv + P.num_est);

@@ -148,7 +148,8 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   B200_CHECK_ARG(p->num_scan == p->scan_nx * p->scan_ny && p->num_scan <= B200_MAX_SCAN, "b200_env_create: bad scan grid");
   B200_CHECK_ARG(p->num_priv == 29 && p->num_est == 3, "b200_env_create: privileged/estimated layout must be 29/3");
   B200_CHECK_ARG(p->n_penalised <= B200_NUM_BODIES && p->n_termination <= B200_NUM_BODIES, "b200_env_create: body tables");
-  B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2), "b200_env_create: height_samples shape");
+  B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2 && (int64_t)p->hs_rows * p->hs_cols < (1ll << 31)),
+                 "b200_env_create: height_samples shape");
   B200_CHECK_ARG(p->resample_interval > 0 && p->push_interval > 0, "b200_env_create: intervals must be > 0");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
