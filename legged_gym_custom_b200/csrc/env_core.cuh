@@ -645,16 +645,24 @@ B200_HD f4_ clamp4(f4_ v, float c) {
 // ---- the whole env step for env `e`, lanes [lane_lo, lane_hi) -------------------------------
 // Row sizes are multiples of 4 floats for the go2 layout (52, 520, 572, 736, 132, critic tail 164),
 // so the bulk rows move as 16-byte vectors; `vec_ok` (warp-uniform) falls back to scalars otherwise.
+// The env step of env `e` is three calls:
+//   env_warp_pre    one warp, lanes [lane_lo, lane_hi): stage 0 (load), 1 (height scan), 2a (element stage)
+//   env_scalar_stage one THREAD per env (the CUDA kernel runs it on warp 0 of the CTA, lane = env slot)
+//   env_warp_post   one warp: stage 3 (observation assembly), 4 (write-back)
 // scan_x / scan_y: the scan-point tables (shared-memory copies on the GPU, P.scan_x / P.scan_y on the host)
-B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* scan_x, const float* scan_y,
-                           int e, int64_t step64, int lane_lo, int lane_hi) {
-  const int NP = B200_PROPRIO, H = P.history_len, NS = P.num_scan;
-  const int HN = H * NP, OBS = HN + NP;
-  const int TAIL = P.num_priv + P.num_est + NS;
-  const int CRIT = OBS + TAIL;
-  const int64_t N = P.num_envs;
-  const bool vec_ok = (HN % 4 == 0) && (TAIL % 4 == 0) && (NS % 4 == 0) && ((P.num_priv + P.num_est) % 4 == 0);
-  float* hist = B.obs_history_buf + (int64_t)e * HN;
+#define B200_ENV_DIMS                                                      \
+  const int NP = B200_PROPRIO, H = P.history_len, NS = P.num_scan;         \
+  const int HN = H * NP, OBS = HN + NP;                                    \
+  const int TAIL = P.num_priv + P.num_est + NS;                            \
+  const int CRIT = OBS + TAIL;                                             \
+  const int64_t N = P.num_envs;                                            \
+  const bool vec_ok = (HN % 4 == 0) && (TAIL % 4 == 0) && (NS % 4 == 0) && ((P.num_priv + P.num_est) % 4 == 0); \
+  float* hist = B.obs_history_buf + (int64_t)e * HN;                       \
+  (void)OBS; (void)CRIT; (void)N; (void)TAIL
+
+B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* scan_x, const float* scan_y,
+                          int e, int lane_lo, int lane_hi) {
+  B200_ENV_DIMS;
 
   // ---- stage 0: stage the env's rows into scratch (coalesced: consecutive lanes, consecutive floats)
   B200_FOR_LANES(lane) {
@@ -720,13 +728,10 @@ B200_HD void env_warp_step(const B200EnvParams& P, const B200EnvBuffers& B, EnvS
   B200_FOR_LANES(lane) { env_element_stage(P, S, lane); }
   B200_WARP_SYNC();
 
-  // ---- stage 2: scalar logic (lane-invariant)
-#if defined(__CUDA_ARCH__)
-  env_scalar_stage(P, B, S, (uint32_t)e, step64);
-#else
-  if (lane_lo == 0) env_scalar_stage(P, B, S, (uint32_t)e, step64);
-#endif
-  B200_WARP_SYNC();
+}
+
+B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, int e, int64_t step64, int lane_lo, int lane_hi) {
+  B200_ENV_DIMS;
 
   // ---- stage 3: current observation + critic tail, elements strided over lanes
   B200_FOR_LANES(lane) {

@@ -1,7 +1,7 @@
 // Env-side kernels of libb200gym.so (compiled with -fmad=false, see env_core.cuh).
 //
 //   K1 pd_torques_kernel        one thread per (env, dof)            legged_robot.py:74-75, :440-478
-//   K2 post_physics_kernel      one warp per env, 4 warps per CTA    go2.py:345-387 and callees
+//   K2 post_physics_kernel      one warp per env (8 per CTA) + 1 thread per env for the scalar stage   go2.py:345-387 and callees
 //   K3 extras_kernel            one CTA per reward term (+1)         go2.py:246-263 (episode means, time_outs)
 //      reset_all_kernel         one thread per env                   base_task.py:131-133
 //      heights_kernel           one thread per scan point            legged_robot.py:997-1032
@@ -23,13 +23,14 @@ void b200_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kEnvsPerCta = 8;      // one warp per env for the lane-parallel stages; warp 0 runs the scalar stage, one THREAD per env
 
 // `step_dev` != nullptr: the step counter lives in device memory (CUDA-graph replay); else `step` is used.
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 6)
+__global__ void __launch_bounds__(kEnvsPerCta * 32, 4)
 post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
                     const int64_t* __restrict__ step_dev) {
-  __shared__ EnvScratch scratch[kWarpsPerCta];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  EnvScratch* scratch = reinterpret_cast<EnvScratch*>(smem_raw);
   __shared__ float scan_x[B200_MAX_SCAN_AXIS], scan_y[B200_MAX_SCAN_AXIS];
   if (threadIdx.x < B200_MAX_SCAN_AXIS) {
     scan_x[threadIdx.x] = P.scan_x[threadIdx.x];
@@ -38,9 +39,14 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
   __syncthreads();
   if (step_dev) step = *step_dev;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * kWarpsPerCta + warp;
-  if (e >= P.num_envs) return;
-  env_warp_step(P, B, scratch[warp], scan_x, scan_y, e, step, lane, lane + 1);
+  const int e0 = blockIdx.x * kEnvsPerCta;
+  const int e = e0 + warp;
+  const bool live = e < P.num_envs;
+  if (live) env_warp_pre(P, B, scratch[warp], scan_x, scan_y, e, lane, lane + 1);
+  __syncthreads();
+  if (warp == 0 && lane < kEnvsPerCta && e0 + lane < P.num_envs) env_scalar_stage(P, B, scratch[lane], (uint32_t)(e0 + lane), step);
+  __syncthreads();
+  if (live) env_warp_post(P, B, scratch[warp], e, step, lane, lane + 1);
 }
 
 __global__ void __launch_bounds__(256)
@@ -170,6 +176,19 @@ int b200_env_destroy(B200Env* env) {
   return 0;
 }
 
+static int post_physics_attr() {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEnvsPerCta * sizeof(EnvScratch)));
+    if (e != cudaSuccess) {
+      b200_set_error("post_physics_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    done = true;
+  }
+  return 0;
+}
+
 static int check_bufs(const B200Env* env, const B200EnvBuffers* b, const char* who) {
   B200_CHECK_ARG(env && b, "%s: null argument", who);
   const void* const* ptrs = reinterpret_cast<const void* const*>(b);
@@ -199,8 +218,9 @@ int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actio
 
 int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, void* stream) {
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step")) return rc;
-  const int ctas = (env->p.num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
-  post_physics_kernel<<<ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter, nullptr);
+  if (int rc = post_physics_attr()) return rc;
+  const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
+  post_physics_kernel<<<ctas, kEnvsPerCta * 32, kEnvsPerCta * sizeof(EnvScratch), (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter, nullptr);
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");
@@ -222,8 +242,9 @@ int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step_dev")) return rc;
   B200_CHECK_ARG(step_counter_dev, "b200_post_physics_step_dev: null counter");
   counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev, 1);       // go2.py:355
-  const int ctas = (env->p.num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
-  post_physics_kernel<<<ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(env->p, *bufs, 0, step_counter_dev);
+  if (int rc = post_physics_attr()) return rc;
+  const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
+  post_physics_kernel<<<ctas, kEnvsPerCta * 32, kEnvsPerCta * sizeof(EnvScratch), (cudaStream_t)stream>>>(env->p, *bufs, 0, step_counter_dev);
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");

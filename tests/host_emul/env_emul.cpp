@@ -44,7 +44,9 @@ int emul_post_physics_step(const B200EnvParams* p, const B200EnvBuffers* b, int6
   static EnvScratch S;
   for (int e = 0; e < p->num_envs; ++e) {
     memset(&S, 0xCD, sizeof(S));   // poison: a stage that reads what no stage wrote shows up as garbage
-    env_warp_step(*p, *b, S, p->scan_x, p->scan_y, e, step, 0, 32);
+    env_warp_pre(*p, *b, S, p->scan_x, p->scan_y, e, 0, 32);
+    env_scalar_stage(*p, *b, S, (uint32_t)e, step);
+    env_warp_post(*p, *b, S, e, step, 0, 32);
   }
   extras(*p, *b);
   return 0;
