@@ -305,8 +305,8 @@ class PPO:
         return self.start_val + stage * (self.end_val - self.start_val)
 
     def _allreduce(self, group):
-        if self.process_group is not None:
-            torch.distributed.all_reduce(group.grads, group=self.process_group)
+        from .dist import allreduce_flat_grads
+        allreduce_flat_grads([group], self.process_group)
 
     def _adam(self, group):
         self._allreduce(group)

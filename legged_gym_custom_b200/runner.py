@@ -42,6 +42,9 @@ class OnPolicyRunner:
                        estimator_learning_rate=ac_["estimator_learning_rate"], max_grad_norm=ac_["max_grad_norm"],
                        use_clipped_value_loss=ac_["use_clipped_value_loss"], schedule=ac_["schedule"], desired_kl=ac_["desired_kl"],
                        resume=self.cfg["resume"], device=self.device, seed=seed, process_group=process_group)
+        if process_group is not None:      # replicas start from rank 0's weights; afterwards identical reduced gradients keep them in sync
+            from .dist import broadcast_parameters
+            broadcast_parameters([actor_critic.main, actor_critic.adapt, estimator.group], process_group)
         self.dagger_update_freq = ac_["dagger_update_freq"]
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
         self.alg.init_storage(num_envs=env.num_envs, num_transitions_per_env=self.num_steps_per_env, total_obs_shape=[env.num_obs],
