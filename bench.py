@@ -257,9 +257,14 @@ def run_b200(args):
                            "launch": "CUDA graphs (rollout+GAE: 1 graph; update: 1 graph per minibatch slot)" if not args.no_graphs else "eager"},
                 "e2e": e2e, "split": split, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # every collective of this run has completed on every rank (timed_iterations ends with an all-reduce + item()).
+        # Tearing the NCCL communicator down while captured graphs still hold its kernels can hang, so leave hard.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ---- CPU arm: the reference's CPU path restated (oracle/), timed on the host cores ---------------------------------
