@@ -155,3 +155,50 @@ def test_go2env_api_smoke():
     assert torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
     assert torch.equal(out[2][:, :572], out[0])
     assert len(env.step5(torch.zeros(256, 12, device=DEV))) == 5
+
+
+def test_go2_rough_terrain_matches_oracle():
+    """BASELINE config 2: the `go2` task on a rough trimesh terrain with terrain curriculum and height measurements
+    (Go2Cfg + terrain.mesh_type='trimesh', curriculum=True; 10 x 20 tiles of 8 m -> height_samples [1300, 2100]).
+    The rough height field is synthetic (terrain generation beyond the parkour layouts is out of scope); base_height,
+    scan observations, curriculum levels and the bit-exact height indices are all exercised."""
+    class RoughCfg(configs.Go2Cfg):
+        class terrain(configs.Go2Cfg.terrain):
+            mesh_type, curriculum, measure_heights = "trimesh", True, True
+            num_rows, num_cols, terrain_length, terrain_width = 10, 20, 8., 8.
+            max_init_terrain_level = 5
+
+        class rewards(configs.Go2Cfg.rewards):
+            class scales(configs.Go2Cfg.rewards.scales):
+                base_height = -20.0
+                stumble_feet = -1.0
+                feet_air_time = 1.0
+    rng = np.random.default_rng(11)
+    rows, cols = 10 * 80 + 500, 20 * 80 + 500
+    hs = np.zeros((rows, cols), dtype=np.int16)
+    hs[250:-250, 250:-250] = (rng.integers(-12, 13, (rows - 500, cols - 500))).astype(np.int16)     # +-6 cm roughness
+    hs[400:420, :] = 60                                                                              # a 30 cm step across
+    origins = np.zeros((10, 20, 3), dtype=np.float32)
+    origins[..., 0] = (np.arange(10)[:, None] + 0.5) * 8.0
+    origins[..., 1] = (np.arange(20)[None, :] + 0.5) * 8.0
+    N = 2048
+    p = env_params_from_cfg(RoughCfg, num_envs=N, seed=21, hs_shape=hs.shape)
+    assert p.has_height_samples and p.curriculum and not p.parkour and p.reward_scales[gu.REWARD_INDEX["base_height"]] != 0
+    statics = su.random_statics(p, rng, hs, origins)
+    st = su.random_state(p, rng, origins)
+    orc = Go2Oracle(p, statics, st)
+    env = CudaEnv(p)
+    env.bufs.load_statics(statics)
+    st2 = dict(st)
+    step = int(st2.pop("common_step_counter"))
+    env.bufs.load_state(st2)
+    origins0 = st["env_origins"].numpy()
+    for t_ in range(3):
+        frames = synth.make_frames(N, origins0, rng, hole_prob=0.0, flip_prob=0.01)
+        frames["root"][:, 0] = origins0[:, 0] + rng.uniform(-3.5, 6.0, N).astype(np.float32)   # around the tile centre: promote + demote
+        actions = rng.normal(0, 1.5, (N, NUM_DOF)).astype(np.float32)
+        out = orc.step(torch.from_numpy(actions), frames)
+        step += 1
+        env.step(actions, frames, step)
+        gu.check_step(env.bufs, gu.oracle_expected(orc, out), t_)
+    env.close()
