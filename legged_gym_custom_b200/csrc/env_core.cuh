@@ -478,11 +478,14 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   {                                                     // go2.py:819-831 (stateful)
     float a = 0.0f;
     if (sc[B200_REW_feet_air_time] != 0.0f) {
+      // update_feet_states has already overwritten last_contacts with the CURRENT contacts (go2.py:307-310), so the
+      // "filtered" contact of this reward (go2.py:824-825) is just the current one
       for (int f = 0; f < 4; ++f) {
-        const float first = (S.fat[f] > 0.0f && filt[f]) ? 1.0f : 0.0f;
+        const int now = R.contact_cur[f];
+        const float first = (S.fat[f] > 0.0f && now) ? 1.0f : 0.0f;
         const float t = S.fat[f] + P.dt;
         a += (t - 0.5f) * first;
-        R.fat[f] = t * (filt[f] ? 0.0f : 1.0f);
+        R.fat[f] = t * (now ? 0.0f : 1.0f);
       }
       a *= norm2_fma(cmd[0], cmd[1]) > 0.1f ? 1.0f : 0.0f;
     }

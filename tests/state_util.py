@@ -41,8 +41,9 @@ def random_state(p, rng, terrain_origins=None, step0=395):
     st["last_contact_heights"] = torch.from_numpy(rng.uniform(0.0, 0.1, (N, 4)).astype(np.float32))
     st["feet_air_time"] = torch.from_numpy(rng.uniform(0.0, 0.4, (N, 4)).astype(np.float32))
     st["jump_flags"] = torch.from_numpy((rng.random((N, 1)) < 0.3).astype(np.float32))
-    active = torch.tensor([p.reward_scales[i] != 0.0 for i in range(len(REWARD_TERMS))])
-    st["episode_sums"] = f(len(REWARD_TERMS), N, scale=0.3) * active[:, None]   # inactive terms have no episode sum
+    # inactive terms have no episode sum; an active term's sum carries the sign of its scale (no artificial cancellation)
+    sign = torch.tensor([float(np.sign(p.reward_scales[i])) for i in range(len(REWARD_TERMS))])
+    st["episode_sums"] = f(len(REWARD_TERMS), N, scale=0.3).abs() * sign[:, None]
     st["reset_buf"] = torch.zeros(N, dtype=torch.bool)
     st["common_step_counter"] = torch.tensor(step0, dtype=torch.int64)
     return st

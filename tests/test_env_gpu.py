@@ -202,3 +202,37 @@ def test_go2_rough_terrain_matches_oracle():
         env.step(actions, frames, step)
         gu.check_step(env.bufs, gu.oracle_expected(orc, out), t_)
     env.close()
+
+
+def test_every_reward_term_active_matches_oracle():
+    """all 38 `_reward_*` terms on at once (stateful feet_air_time and the post-clip termination reward included)."""
+    from legged_gym_custom_b200.params import REWARD_TERMS
+
+    class AllCfg(configs.Go2ParkourCfg):
+        class rewards(configs.Go2ParkourCfg.rewards):
+            only_positive_rewards = False
+            soft_dof_vel_limit, soft_torque_limit = 0.05, 0.3
+
+            class scales:
+                pass
+    for i, name in enumerate(REWARD_TERMS):
+        setattr(AllCfg.rewards.scales, name, (-1.0) ** i * (0.3 + 0.1 * i))
+    hs, origins = gu.terrain_for("go2_parkour")
+    N = 3000
+    p = env_params_from_cfg(AllCfg, num_envs=N, seed=5, hs_shape=hs.shape)
+    rng = np.random.default_rng(3)
+    statics, st = su.random_statics(p, rng, hs, origins), su.random_state(p, rng, origins)
+    orc = Go2Oracle(p, statics, st)
+    env = CudaEnv(p)
+    env.bufs.load_statics(statics)
+    st2 = dict(st)
+    step = int(st2.pop("common_step_counter"))
+    env.bufs.load_state(st2)
+    for t_ in range(3):
+        frames = synth.make_frames(N, st["env_origins"].numpy(), rng, hole_prob=0.02, flip_prob=0.02, body_hit_prob=0.05)
+        actions = rng.normal(0, 1.5, (N, NUM_DOF)).astype(np.float32)
+        out = orc.step(torch.from_numpy(actions), frames)
+        step += 1
+        env.step(actions, frames, step)
+        gu.check_step(env.bufs, gu.oracle_expected(orc, out), t_)
+    env.close()

@@ -44,6 +44,49 @@ def test_kernel_source_matches_reference(lib, task):
     print(task, "worst relative errors:", {k: f"{v:.1e}" for k, v in sorted(report.items(), key=lambda kv: -kv[1])[:6]})
 
 
+def test_kernel_source_every_reward_term_active(lib):
+    """all 38 reward terms switched on at once (including the stateful feet_air_time and the termination reward), on a
+    rough height field with curriculum: the oracle and the kernel source must still agree."""
+    import state_util as su
+    from legged_gym_custom_b200 import configs, synth
+    from legged_gym_custom_b200.params import NUM_DOF, REWARD_TERMS, env_params_from_cfg
+    from oracle.go2_oracle import Go2Oracle
+
+    class AllCfg(configs.Go2ParkourCfg):
+        class rewards(configs.Go2ParkourCfg.rewards):
+            only_positive_rewards = False
+            soft_dof_vel_limit, soft_torque_limit = 0.05, 0.3
+
+            class scales:
+                pass
+    for i, name in enumerate(REWARD_TERMS):
+        setattr(AllCfg.rewards.scales, name, (-1.0) ** i * (0.3 + 0.1 * i))
+    hs, origins = gu.terrain_for("go2_parkour")
+    N = 400
+    p = env_params_from_cfg(AllCfg, num_envs=N, seed=5, hs_shape=hs.shape)
+    assert len(p.reward_names()) == len(REWARD_TERMS) - 1 and p.reward_scales[len(REWARD_TERMS) - 1] != 0
+    rng = np.random.default_rng(3)
+    statics, st = su.random_statics(p, rng, hs, origins), su.random_state(p, rng, origins)
+    orc = Go2Oracle(p, statics, st)
+    bufs = BufferSet(p, "cpu", record_height_index=True)
+    bufs.load_statics(statics)
+    st2 = dict(st)
+    step = int(st2.pop("common_step_counter"))
+    bufs.load_state(st2)
+    for t in range(3):
+        frames = synth.make_frames(N, st["env_origins"].numpy(), rng, hole_prob=0.02, flip_prob=0.02, body_hit_prob=0.05)
+        actions = torch.from_numpy(rng.normal(0, 1.5, (N, NUM_DOF)).astype(np.float32))
+        out = orc.step(actions, frames)
+        for k in range(p.decimation):
+            lib.emul_pd_torques(C.byref(p), C.byref(bufs.struct), C.c_void_p(actions.data_ptr()), int(k == 0))
+            bufs["dof_state"].copy_(torch.from_numpy(frames["dof"][k]))
+        for name, key in (("root_states", "root"), ("contact_forces", "contact"), ("rigid_body_states", "rigid")):
+            bufs[name].copy_(torch.from_numpy(frames[key]))
+        step += 1
+        lib.emul_post_physics_step(C.byref(p), C.byref(bufs.struct), step)
+        gu.check_step(bufs, gu.oracle_expected(orc, out), t)
+
+
 @pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 1500, 3), ("go2", 333, 2)])
 def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
     """same harness as tests/test_env_gpu.py::test_cuda_env_matches_oracle_at_scale, on the host emulator."""
