@@ -236,6 +236,13 @@ int b200_env_buffers_size(void);
 /* Handle lifetime. Copies `params`; `device` is the CUDA ordinal. */
 int b200_env_create(const B200EnvParams* params, int device, B200Env** out);
 int b200_env_destroy(B200Env* env);
+/* The go2 layout (history 10, scan 12 x 11: every registered go2 task) runs a kernel variant with the layout
+ * baked in; `on` != 0 forces the layout-generic variant instead (tests run both against the oracle). */
+int b200_env_force_generic_layout(B200Env* env, int on);
+/* Profiling aid: when `trace` (device, uint64 [ceil(num_envs / 8)][8]) is non-NULL, thread 0 of every CTA of the
+ * post-physics kernel records %globaltimer (ns) at its phase boundaries: [0] start, [1] rows loaded + height scan,
+ * [2] items, [3] reward terms + history loads, [4] reward sum / reset, [5] end (observations written). */
+int b200_env_set_phase_trace(B200Env* env, unsigned long long* trace);
 
 /* Replaces LeggedRobot.step's action clip (legged_robot.py:74-75) + _compute_torques
  * (legged_robot.py:440-478).  `actions_in` [N,12] raw policy actions; when `clip_and_store`

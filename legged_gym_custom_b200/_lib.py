@@ -15,6 +15,8 @@ SYMBOLS = {
     "b200_env_buffers_size": (C.c_int, []),
     "b200_env_create": (C.c_int, [C.POINTER(EnvParams), C.c_int, C.POINTER(C.c_void_p)]),
     "b200_env_destroy": (C.c_int, [C.c_void_p]),
+    "b200_env_force_generic_layout": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_env_set_phase_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_pd_torques": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_int, C.c_void_p]),
     "b200_post_physics_step": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_void_p]),
     "b200_post_physics_step_dev": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_void_p]),

@@ -27,4 +27,6 @@ void b200_set_error(const char* fmt, ...);
 struct B200Env {
   B200EnvParams p;
   int device;
+  unsigned long long* phase_trace;   // device [ceil(num_envs / 8)][8] or NULL (b200_env_set_phase_trace)
+  int force_generic_layout;   // tests: run the layout-generic kernel variant even for the go2 layout
 };

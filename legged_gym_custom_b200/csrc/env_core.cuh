@@ -19,6 +19,7 @@
 //  * division and sqrt are IEEE (nvcc defaults -prec-div/-prec-sqrt = true).
 #pragma once
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/b200gym.h"
@@ -35,6 +36,11 @@
 #endif
 #define B200_FOR_LANES(lane) for (int lane = lane_lo; lane < lane_hi; ++lane)
 
+// the go2 layout (every registered go2 task): kernels instantiated with FIXED = true bake it in
+#define B200_GO2_HISTORY 10
+#define B200_GO2_SCAN_NX 12
+#define B200_GO2_SCAN_NY 11
+
 #define B200_TWO_PI_F 6.283185307179586f   /* fp32(2*np.pi) */
 #define B200_PI_F 3.141592653589793f
 
@@ -44,8 +50,8 @@ struct float3_ {
 
 // ---- per-warp scratch -------------------------------------------------------------------
 struct alignas(16) EnvScratch {
-  // [history | cur] contiguous: obs_buf is a clipped copy of it, the new history is it shifted by one slot
-  float histcur[B200_MAX_HIST + B200_MAX_PROPRIO];
+  // the new proprioceptive row (unclipped); the history rows never pass through shared memory (env_hist_*)
+  float cur[B200_MAX_PROPRIO];
   float tail[32 + 4 + B200_MAX_SCAN];   // priv | est | scan  = critic tail (16 B aligned pieces for 29+3+132)
   float heights[B200_MAX_SCAN];
   // staged inputs
@@ -67,6 +73,10 @@ struct alignas(16) EnvScratch {
   float leg_sin[4], leg_cos[4];  // sin / cos of 2 pi phase, contact order fl, fr, bl, br
   int32_t leg_stance[4];
   float ang[4];                  // roll, pitch, yaw, heading
+  // termination known before the scalar stage (element stage, lane 20): lets the history rows move while it runs
+  int32_t early_reset, early_time_out, early_refill;
+  uint32_t reset_draws[4 * 7];   // env_reset_draw (only when early_reset)
+  uint32_t pad_[4];              // keeps sizeof / 16 odd (see the static_assert below)
   // results of the scalar stage
   float blv[4], bav[4], pg[4], rpy[4], phases[8];
   float cmd_out[4], lch_out[4], fat_out[4];
@@ -77,6 +87,21 @@ struct alignas(16) EnvScratch {
   int32_t contact_filt[4], contact_cur[4];
   int32_t reset, time_out, root_dirty, dof_dirty;
   int64_t ep_len_out, level_out;
+};
+
+// lanes of a warp address consecutive EnvScratch objects (lane = env slot): an odd number of 16-byte units per object
+// puts 8 consecutive slots on 8 different bank groups
+static_assert((sizeof(EnvScratch) / 16) % 2 == 1, "EnvScratch stride would bank-conflict the per-env lanes");
+
+// Per-dof / per-observation constants that are indexed by LANE: out of the constant bank (a lane-varying index
+// serialises there) into a small table -- shared memory on the GPU, filled once per CTA by env_tables_fill.
+struct EnvTables {
+  float default_dof_pos[B200_NUM_DOF], dof_pos_lo[B200_NUM_DOF], dof_pos_hi[B200_NUM_DOF];
+  float dof_vel_soft[B200_NUM_DOF];      // dof_vel_limits * soft_dof_vel_limit
+  float torque_soft[B200_NUM_DOF];       // torque_limits * soft_torque_limit
+  // cur_obs[i] = (scratch_as_floats[cur_idx[i]] - cur_off[i]) * cur_scl[i] + (2u - 1) * noise[i]   (go2.py:506-519)
+  int32_t cur_idx[B200_MAX_PROPRIO];
+  float cur_off[B200_MAX_PROPRIO], cur_scl[B200_MAX_PROPRIO], noise[B200_MAX_PROPRIO];
 };
 
 struct alignas(16) f4_ {
@@ -144,10 +169,10 @@ B200_HD YawQuat yaw_quat(const float* q) {
 }
 // point j of the x-major scan grid: ix = j / ny without an integer division ((2j+1)/(2ny) is never within 1/(2ny) of an
 // integer, so the fp32 product truncates to the exact quotient for every j < 192, ny <= 24)
-B200_HD void height_cell(const B200EnvParams& P, const float* scan_x, const float* scan_y, YawQuat yq, const float* root_pos, int j,
+B200_HD void height_cell(const B200EnvParams& P, int ny, const float* scan_x, const float* scan_y, YawQuat yq, const float* root_pos, int j,
                          int* px, int* py) {
-  const int gx = (int)((float)(2 * j + 1) * (0.5f / (float)P.scan_ny));
-  const float vx = scan_x[gx], vy = scan_y[j - gx * P.scan_ny];
+  const int gx = (int)((float)(2 * j + 1) * (0.5f / (float)ny));
+  const float vx = scan_x[gx], vy = scan_y[j - gx * ny];
   // quat_apply((0,0,z,w), (vx,vy,0)): t = cross * 2; b + w*t + cross(xyz, t)
   const float t0 = -(yq.z * vy) * 2.0f, t1 = (yq.z * vx) * 2.0f;
   float rx = (vx + yq.w * t0) + (-(yq.z * t1));
@@ -182,8 +207,13 @@ B200_HD float height_at(const B200EnvParams& P, const int16_t* hs, int px, int p
 }
 
 // ---- command resampling for one env (go2.py:413-464) -------------------------------------
+B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v, const float* quat, float* cmd);
 B200_HD void resample_commands(const B200EnvParams& P, uint32_t site, uint32_t step, uint32_t e, const float* quat, float* cmd) {
   const Philox4 r = keyed_block(P.seed, site, step, e, 0);
+  resample_commands_from(P, r.v, quat, cmd);
+}
+B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v, const float* quat, float* cmd) {
+  struct { uint32_t v[4]; } r = {{r_v[0], r_v[1], r_v[2], r_v[3]}};
   cmd[0] = P.cmd_span[0] * u32_to_uniform(r.v[0]) + P.cmd_lo[0];
   cmd[1] = P.cmd_span[1] * u32_to_uniform(r.v[1]) + P.cmd_lo[1];
   if (P.heading_command)
@@ -208,7 +238,17 @@ struct ResetState {
   int32_t contact_cur[4];
   int64_t level, ep_len;
 };
-B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetState& R, int64_t type, uint32_t step, uint32_t e,
+// The reset draws of one env are 7 Philox blocks (block id -> site, block): 0-2 RESET_DOFS 0-2 (lanes 0..11), 3-4 RESET_ROOT
+// 0-1 (lanes 0..7), 5 CURRICULUM 0, 6 CMD_RESET 0.  They are independent of everything else, so the CUDA kernel draws them
+// with 7 lanes in parallel (env_reset_draw -> EnvScratch::reset_draws) and reset_env consumes the 28 words.
+#define B200_RESET_BLOCKS 7
+B200_HD void env_reset_draw(const B200EnvParams& P, uint32_t* draws /* [28] */, uint32_t e, uint32_t step, int block) {
+  const uint32_t site = block < 3 ? SITE_RESET_DOFS : (block < 5 ? SITE_RESET_ROOT : (block == 5 ? SITE_CURRICULUM : SITE_CMD_RESET));
+  const uint32_t blk = block < 3 ? block : (block < 5 ? block - 3 : 0);
+  const Philox4 r = keyed_block(P.seed, site, step, e, blk);
+  for (int i = 0; i < 4; ++i) draws[block * 4 + i] = r.v[i];
+}
+B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetState& R, int64_t type, const uint32_t* draws,
                        int do_curriculum) {
   if (P.curriculum && do_curriculum) {                  // legged_robot.py:543-574
     const float dist = norm2_fma(R.root[0] - R.origin[0], R.root[1] - R.origin[1]);
@@ -217,7 +257,7 @@ B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetSta
     const int down = dist < expected * P.demote_threshold;
     int64_t lv = R.level + up - down;
     if (lv >= P.max_terrain_level)
-      lv = (int64_t)(keyed_u32(P.seed, SITE_CURRICULUM, step, e, 0) % (uint32_t)P.max_terrain_level);
+      lv = (int64_t)(draws[20] % (uint32_t)P.max_terrain_level);
     else
       lv = lv < 0 ? 0 : lv;
     R.level = lv;
@@ -227,7 +267,7 @@ B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetSta
     R.origin[2] = B200_LDG(o + 2);
   }
   for (int d = 0; d < B200_NUM_DOF; ++d) {              // _reset_dofs
-    const float u = keyed_uniform(P.seed, SITE_RESET_DOFS, step, e, d);
+    const float u = u32_to_uniform(draws[d]);
     R.dof[2 * d] = P.default_dof_pos[d] + (P.dof_reset_span * u + P.dof_reset_lo);
     R.dof[2 * d + 1] = 0.0f;
   }
@@ -235,11 +275,11 @@ B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetSta
   for (int i = 0; i < 3; ++i) R.root[i] += R.origin[i];
   int lane0 = 0;
   if (P.custom_origins) {
-    for (int i = 0; i < 2; ++i) R.root[i] += 2.0f * keyed_uniform(P.seed, SITE_RESET_ROOT, step, e, i) + -1.0f;
+    for (int i = 0; i < 2; ++i) R.root[i] += 2.0f * u32_to_uniform(draws[12 + i]) + -1.0f;
     lane0 = 2;
   }
-  for (int i = 0; i < 6; ++i) R.root[7 + i] = 1.0f * keyed_uniform(P.seed, SITE_RESET_ROOT, step, e, lane0 + i) + -0.5f;
-  resample_commands(P, SITE_CMD_RESET, step, e, R.root + 3, R.cmd);
+  for (int i = 0; i < 6; ++i) R.root[7 + i] = 1.0f * u32_to_uniform(draws[12 + lane0 + i]) + -0.5f;
+  resample_commands_from(P, draws + 24, R.root + 3, R.cmd);
   for (int f = 0; f < 4; ++f) {
     R.lch[f] = 0.0f;
     R.fat[f] = 0.0f;
@@ -248,368 +288,137 @@ B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetSta
   R.ep_len = 0;
 }
 
-B200_HD void publish_reset_state(EnvScratch& S, const ResetState& R, int root_dirty, int dof_dirty, int reset) {
-  for (int i = 0; i < 13; ++i) S.root_out[i] = R.root[i];
-  for (int i = 0; i < 24; ++i) S.dof_out[i] = R.dof[i];
-  for (int i = 0; i < 4; ++i) {
-    S.cmd_out[i] = R.cmd[i];
-    S.lch_out[i] = R.lch[i];
-    S.fat_out[i] = R.fat[i];
-    S.contact_cur[i] = R.contact_cur[i];
-  }
-  for (int i = 0; i < 3; ++i) S.origin_out[i] = R.origin[i];
-  S.level_out = R.level;
-  S.ep_len_out = R.ep_len;
-  S.root_dirty = root_dirty;
-  S.dof_dirty = dof_dirty;
-  S.reset = reset;
-}
-
-// ---- the element stage: everything that is "the same formula on 19 bodies / 12 dofs / 4 legs / 3 angles" runs with
-// one lane per element instead of a serial loop in the scalar stage.  Contact tests compare the (FMA-accumulated, as
-// torch does) squared norm with the pre-rounded squared threshold: sqrt_rn(s) > t  <=>  s > contact_thr2 exactly.
+// ---- the item stage: everything between "state loaded" and "observations assembled" that is the same formula on
+// 19 bodies / 12 dofs / 4 legs / 4 angles, plus the per-env pieces the reward terms share (base-frame velocities,
+// foot contacts, command update, push, termination flags).  One ITEM = one thread; the CUDA kernel packs the items of
+// the CTA's 8 envs type by type into full warps (env_kernels.cu), the host emulation runs them one after the other.
+// Items only read staged inputs (stage 0 / 1) and write disjoint scratch fields, so their order does not matter.
+// Contact tests compare the (FMA-accumulated, as torch does) squared norm with the pre-rounded squared threshold:
+// sqrt_rn(s) > t  <=>  s > contact_thr2 exactly.
 enum { DV_ACTION_RATE = 0, DV_DELTA_TORQUES, DV_DOF_ACC, DV_DQ2, DV_POS_LIMITS, DV_VEL2, DV_VEL_LIMITS, DV_ABS_DQ, DV_TORQUE_LIMITS, DV_TORQUES2 };
 
 B200_HD float gait_phase(const B200EnvParams& P, int64_t ep) { return fmodf((float)ep * P.dt, P.period) / P.period; }
 
-B200_HD void env_element_stage(const B200EnvParams& P, EnvScratch& S, int lane) {
-  if (lane < B200_NUM_BODIES) {
-    const float* c = S.contact + lane * 3;
-    const float n2 = B200_FMA(c[2], c[2], B200_FMA(c[1], c[1], c[0] * c[0]));
-    S.body_hit[lane] = (n2 > P.contact_thr2_term ? 1 : 0) | (n2 > P.contact_thr2_collision ? 2 : 0);
+B200_HD void env_item_body(const B200EnvParams& P, EnvScratch& S, int b) {
+  const float* c = S.contact + b * 3;
+  const float n2 = B200_FMA(c[2], c[2], B200_FMA(c[1], c[1], c[0] * c[0]));
+  S.body_hit[b] = (n2 > P.contact_thr2_term ? 1 : 0) | (n2 > P.contact_thr2_collision ? 2 : 0);
+}
+
+B200_HD void env_item_dof(const B200EnvParams& P, const EnvTables& T, EnvScratch& S, int d) {
+  const float pos = S.dof[2 * d], vel = S.dof[2 * d + 1];
+  const float dq = pos - T.default_dof_pos[d];
+  S.dofv[DV_ACTION_RATE][d] = sq(S.last_act[d] - S.act[d]);
+  S.dofv[DV_DELTA_TORQUES][d] = sq(S.tq[d] - S.last_tq[d]);
+  S.dofv[DV_DOF_ACC][d] = sq((S.last_dv[d] - vel) / P.dt);
+  S.dofv[DV_DQ2][d] = sq(dq);
+  const float lo = pos - T.dof_pos_lo[d], hi = pos - T.dof_pos_hi[d];
+  S.dofv[DV_POS_LIMITS][d] = -(lo > 0.0f ? 0.0f : lo) + (hi < 0.0f ? 0.0f : hi);
+  S.dofv[DV_VEL2][d] = sq(vel);
+  S.dofv[DV_VEL_LIMITS][d] = clampf(fabsf(vel) - T.dof_vel_soft[d], 0.0f, 1.0f);
+  S.dofv[DV_ABS_DQ][d] = fabsf(dq);
+  const float over = fabsf(S.tq[d]) - T.torque_soft[d];
+  S.dofv[DV_TORQUE_LIMITS][d] = over < 0.0f ? 0.0f : over;
+  S.dofv[DV_TORQUES2][d] = sq(S.tq[d]);
+}
+
+// gait phase of one leg (go2.py:279-290), order fl, fr, bl, br
+B200_HD void env_item_leg(const B200EnvParams& P, EnvScratch& S, int f) {
+  const float ph = gait_phase(P, S.ep_len + 1);
+  const float off = f == 0 ? P.fl_offset : (f == 1 ? P.fr_offset : (f == 2 ? P.bl_offset : P.br_offset));
+  const float keep = norm3_fma(S.cmd[0], S.cmd[1], S.cmd[2]) < 0.2f ? 0.0f : 1.0f;
+  const float phf = fmodf(ph + off, 1.0f) * keep;
+  S.phases[f == 0 ? 2 : (f == 1 ? 1 : (f + 1))] = phf;      // API order: phase, fr, fl, bl, br
+  if (f == 0) S.phases[0] = ph;
+  const float a = B200_TWO_PI_F * phf;
+  const float sn = sinf(a);
+  S.leg_sin[f] = sn;
+  S.leg_cos[f] = cosf(a);
+  S.leg_stance[f] = sn <= P.stance_threshold;
+}
+
+// a = 0 roll, 1 pitch, 2 yaw (quaternion_to_euler, go2.py:11-31), 3 heading.  The heading item goes on with the command
+// update of _post_physics_step_callback (go2.py:390-410), which is the only consumer of the heading.
+B200_HD void env_item_angle(const B200EnvParams& P, EnvScratch& S, int a, uint32_t e, uint32_t step) {
+  const float x = S.root[3], y = S.root[4], z = S.root[5], w = S.root[6];
+  if (a == 1) {                                           // pitch (go2.py:23-25)
+    const float pitch = asinf(clampf(2.0f * (w * y - z * x), -1.0f, 1.0f));
+    S.ang[1] = pitch;
+    S.rpy[1] = pitch;
+    return;
   }
-  if (lane < B200_NUM_DOF) {
-    const int d = lane;
-    const float pos = S.dof[2 * d], vel = S.dof[2 * d + 1];
-    const float dq = pos - P.default_dof_pos[d];
-    S.dofv[DV_ACTION_RATE][d] = sq(S.last_act[d] - S.act[d]);
-    S.dofv[DV_DELTA_TORQUES][d] = sq(S.tq[d] - S.last_tq[d]);
-    S.dofv[DV_DOF_ACC][d] = sq((S.last_dv[d] - vel) / P.dt);
-    S.dofv[DV_DQ2][d] = sq(dq);
-    const float lo = pos - P.dof_pos_lo[d], hi = pos - P.dof_pos_hi[d];
-    S.dofv[DV_POS_LIMITS][d] = -(lo > 0.0f ? 0.0f : lo) + (hi < 0.0f ? 0.0f : hi);
-    S.dofv[DV_VEL2][d] = sq(vel);
-    S.dofv[DV_VEL_LIMITS][d] = clampf(fabsf(vel) - P.dof_vel_limits[d] * P.soft_dof_vel_limit, 0.0f, 1.0f);
-    S.dofv[DV_ABS_DQ][d] = fabsf(dq);
-    const float over = fabsf(S.tq[d]) - P.torque_limits[d] * P.soft_torque_limit;
-    S.dofv[DV_TORQUE_LIMITS][d] = over < 0.0f ? 0.0f : over;
-    S.dofv[DV_TORQUES2][d] = sq(S.tq[d]);
+  float num, den;                                         // the three atan2 share one code path
+  if (a == 0) {                                           // roll (go2.py:19-21)
+    num = 2.0f * (w * x + y * z);
+    den = 1.0f - 2.0f * (x * x + y * y);
+  } else if (a == 2) {                                    // yaw (go2.py:27-29)
+    num = 2.0f * (w * z + x * y);
+    den = 1.0f - 2.0f * (y * y + z * z);
+  } else {                                                // heading = atan2(fwd.y, fwd.x), fwd = quat_apply(q, (1,0,0))
+    const float t1 = z * 2.0f, t2 = -y * 2.0f;
+    den = 1.0f + (y * t2 - z * t1);
+    num = w * t1 + (-(x * t2));
   }
-  if (lane >= 12 && lane < 16) {                          // gait phase of one leg (go2.py:279-290), order fl, fr, bl, br
-    const int f = lane - 12;
-    const float ph = gait_phase(P, S.ep_len + 1);
-    const float off = f == 0 ? P.fl_offset : (f == 1 ? P.fr_offset : (f == 2 ? P.bl_offset : P.br_offset));
-    const float keep = norm3_fma(S.cmd[0], S.cmd[1], S.cmd[2]) < 0.2f ? 0.0f : 1.0f;
-    const float phf = fmodf(ph + off, 1.0f) * keep;
-    S.phases[f == 0 ? 2 : (f == 1 ? 1 : (f + 1))] = phf;      // API order: phase, fr, fl, bl, br
-    if (f == 0) S.phases[0] = ph;
-    const float a = B200_TWO_PI_F * phf;
-    const float sn = sinf(a);
-    S.leg_sin[f] = sn;
-    S.leg_cos[f] = cosf(a);
-    S.leg_stance[f] = sn <= P.stance_threshold;
-  }
-  if (lane >= 16 && lane < 19) {                          // the three atan2 (roll, yaw, heading) share one code path
-    const float x = S.root[3], y = S.root[4], z = S.root[5], w = S.root[6];
-    float num, den;
-    if (lane == 16) {                                     // roll (go2.py:19-21)
-      num = 2.0f * (w * x + y * z);
-      den = 1.0f - 2.0f * (x * x + y * y);
-    } else if (lane == 17) {                              // yaw (go2.py:27-29)
-      num = 2.0f * (w * z + x * y);
-      den = 1.0f - 2.0f * (y * y + z * z);
-    } else {                                              // heading = atan2(fwd.y, fwd.x), fwd = quat_apply(q, (1,0,0))
-      const float t1 = z * 2.0f, t2 = -y * 2.0f;
-      den = 1.0f + (y * t2 - z * t1);
-      num = w * t1 + (-(x * t2));
-    }
-    S.ang[lane == 16 ? 0 : (lane == 17 ? 2 : 3)] = atan2f(num, den);
-  }
-  if (lane == 19) {                                       // pitch (go2.py:23-25)
-    const float x = S.root[3], y = S.root[4], z = S.root[5], w = S.root[6];
-    S.ang[1] = asinf(clampf(2.0f * (w * y - z * x), -1.0f, 1.0f));
+  const float v = atan2f(num, den);
+  S.ang[a] = v;
+  if (a == 0) S.rpy[0] = v;
+  if (a == 2) S.rpy[2] = v;
+  if (a == 3) {
+    float cmd[4] = {S.cmd[0], S.cmd[1], S.cmd[2], S.cmd[3]};
+    const int64_t ep = S.ep_len + 1;                      // go2.py:354
+    if ((uint32_t)ep % (uint32_t)P.resample_interval == 0u) resample_commands(P, SITE_CMD_PERIODIC, step, e, S.root + 3, cmd);
+    if (P.heading_command) cmd[2] = clampf(wrap_to_pi(cmd[3] - v) * P.heading_error_gain, -1.0f, 1.0f);
+    for (int i = 0; i < 4; ++i) S.cmd_out[i] = cmd[i];
   }
 }
 
-// ---- the scalar stage: everything between "state loaded" and "observations assembled" ---
-// Pure function of the staged inputs: reads S.<in>, computes in registers, writes S.<out> once.
-// Every lane computes the same values (one warp's issue slots, no shuffles, lane-invariant stores).
-B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, uint32_t e, int64_t step64) {
-  const uint32_t step = (uint32_t)step64;
+// base-frame velocities and gravity (go2.py:357-360)
+B200_HD void env_item_velocities(EnvScratch& S) {
   const float* q = S.root + 3;
-  const int64_t ep = S.ep_len + 1;                      // go2.py:354
   const float3_ blv = quat_rotate_inverse(q, S.root[7], S.root[8], S.root[9]);
   const float3_ bav = quat_rotate_inverse(q, S.root[10], S.root[11], S.root[12]);
   const float3_ pg = quat_rotate_inverse(q, 0.0f, 0.0f, -1.0f);
   S.blv[0] = blv.x; S.blv[1] = blv.y; S.blv[2] = blv.z;
   S.bav[0] = bav.x; S.bav[1] = bav.y; S.bav[2] = bav.z;
   S.pg[0] = pg.x; S.pg[1] = pg.y; S.pg[2] = pg.z;
+}
 
-  ResetState R;
-  for (int i = 0; i < 13; ++i) R.root[i] = S.root[i];
-  for (int i = 0; i < 24; ++i) R.dof[i] = S.dof[i];
-  for (int i = 0; i < 4; ++i) R.cmd[i] = S.cmd[i];
-  for (int i = 0; i < 3; ++i) R.origin[i] = S.origin[i];
-  R.level = S.level;
-  R.ep_len = ep;
-
-  // update_feet_states (go2.py:266-328); leg order of contacts/feet: fl, fr, bl, br
-  int filt[4];
+// update_feet_states (go2.py:266-328; leg order of contacts / feet: fl, fr, bl, br) and _push_robots
+// (legged_robot.py:535-540).  Stage 0 has already copied root -> root_out, so the push lands on the copy.
+B200_HD void env_item_feet_push(const B200EnvParams& P, EnvScratch& S, uint32_t e, int64_t step64) {
   for (int f = 0; f < 4; ++f) {
     const int cur = S.contact[P.feet[f] * 3 + 2] > 1.0f;
-    filt[f] = cur | (S.last_contacts[f] != 0);
-    R.contact_cur[f] = cur;
-    S.contact_filt[f] = filt[f];
-    R.lch[f] = filt[f] ? S.feet_z[f] : S.lch[f];
-    R.fat[f] = S.fat[f];
+    const int filt = cur | (S.last_contacts[f] != 0);
+    S.contact_cur[f] = cur;
+    S.contact_filt[f] = filt;
+    S.lch_out[f] = filt ? S.feet_z[f] : S.lch[f];
   }
-
-  const float roll = S.ang[0], pitch = S.ang[1];        // quaternion_to_euler (go2.py:11-31), element stage
-  S.rpy[0] = roll;
-  S.rpy[1] = pitch;
-  S.rpy[2] = S.ang[2];
-
-  // _post_physics_step_callback (go2.py:390-410)
-  float* cmd = R.cmd;
-  if ((uint32_t)ep % (uint32_t)P.resample_interval == 0u) resample_commands(P, SITE_CMD_PERIODIC, step, e, q, cmd);
-  const float heading = S.ang[3];
-  if (P.heading_command) cmd[2] = clampf(wrap_to_pi(cmd[3] - heading) * P.heading_error_gain, -1.0f, 1.0f);
   int root_dirty = 0;
-  if (P.push_robots && ((uint32_t)step64 % (uint32_t)P.push_interval) == 0u) {   // legged_robot.py:535-540
+  if (P.push_robots && ((uint32_t)step64 % (uint32_t)P.push_interval) == 0u) {
     const float span = P.max_push_vel - -P.max_push_vel;
-    R.root[7] = span * keyed_uniform(P.seed, SITE_PUSH, step, e, 0) + -P.max_push_vel;
-    R.root[8] = span * keyed_uniform(P.seed, SITE_PUSH, step, e, 1) + -P.max_push_vel;
+    S.root_out[7] = span * keyed_uniform(P.seed, SITE_PUSH, (uint32_t)step64, e, 0) + -P.max_push_vel;
+    S.root_out[8] = span * keyed_uniform(P.seed, SITE_PUSH, (uint32_t)step64, e, 1) + -P.max_push_vel;
     root_dirty = 1;
   }
-  const float* root = R.root;                           // world-frame rewards see the push (Appendix C.7)
+  S.root_dirty = root_dirty;
+}
 
-  // check_termination (go2.py:186-204)
+// check_termination (go2.py:186-204) and the jump flags of the NEXT step (go2.py:487-494, from this step's heights):
+// known before any reward is, which lets the history rows move while the rewards are computed
+B200_HD void env_item_flags(const B200EnvParams& P, EnvScratch& S) {
   int reset = 0;
-  for (int i = 0; i < P.n_termination; ++i) reset |= S.body_hit[P.termination[i]] & 1;
+  for (int i = 0; i < P.n_termination; ++i) {
+    const float* c = S.contact + P.termination[i] * 3;
+    reset |= B200_FMA(c[2], c[2], B200_FMA(c[1], c[1], c[0] * c[0])) > P.contact_thr2_term;
+  }
+  const int64_t ep = S.ep_len + 1;                      // go2.py:354
   const int time_out = ep > P.max_episode_length;
   reset |= time_out;
-  reset |= pg.z > 0.0f;
-  if (P.parkour) reset |= root[2] < -1.0f;
-  S.time_out = time_out;
-
-  // compute_reward (legged_robot.py:216-237): alphabetical accumulation, term * (scale*dt)
-  const float* sc = P.reward_scales;
-  float rew = 0.0f;
-  const float cmd_n3 = norm3_fma(cmd[0], cmd[1], cmd[2]);
-  const float moving = cmd_n3 >= 0.2f ? 1.0f : 0.0f;
-  const float jumping = S.jump_flag > 0.0f ? 1.0f : 0.0f;
-  const int stance[4] = {S.leg_stance[0], S.leg_stance[1], S.leg_stance[2], S.leg_stance[3]};
-#define B200_DOFSUM(ROW, OUT)                                   \
-  {                                                             \
-    OUT = 0.0f;                                                 \
-    for (int d_ = 0; d_ < 12; ++d_) OUT += S.dofv[ROW][d_];      \
-  }
-#define B200_TERM(NAME, EXPR)                         \
-  {                                                   \
-    float r_ = 0.0f;                                  \
-    if (sc[B200_REW_##NAME] != 0.0f) {                \
-      r_ = (EXPR) * sc[B200_REW_##NAME];              \
-      rew += r_;                                      \
-    }                                                 \
-    S.term[B200_REW_##NAME] = r_;                     \
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_action_rate] != 0.0f) B200_DOFSUM(DV_ACTION_RATE, a)
-    B200_TERM(action_rate, a)
-  }
-  B200_TERM(ang_vel_xy, sq(bav.x) + sq(bav.y))
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_base_height] != 0.0f) {
-      for (int j = 0; j < P.num_scan; ++j) a += root[2] - S.heights[j];
-      a = sq(a / (float)P.num_scan - P.base_height_target);
-    }
-    B200_TERM(base_height, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_calf_collision] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += (S.body_hit[P.calves[f]] & 2) ? 1.0f : 0.0f;
-    B200_TERM(calf_collision, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_calf_pos] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.calf_joints[f]];
-    B200_TERM(calf_pos, a)
-  }
-  B200_TERM(calf_symmetry, fabsf(S.dof[2 * P.calf_joints[0]] - S.dof[2 * P.calf_joints[1]]) +
-                               fabsf(S.dof[2 * P.calf_joints[2]] - S.dof[2 * P.calf_joints[3]]))
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_collision] != 0.0f)
-      for (int i = 0; i < P.n_penalised; ++i) a += (S.body_hit[P.penalised[i]] & 2) ? 1.0f : 0.0f;
-    B200_TERM(collision, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_delta_torques] != 0.0f) B200_DOFSUM(DV_DELTA_TORQUES, a)
-    B200_TERM(delta_torques, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_dof_acc] != 0.0f) B200_DOFSUM(DV_DOF_ACC, a)
-    B200_TERM(dof_acc, a)
-  }
-  float dof_err;
-  B200_DOFSUM(DV_DQ2, dof_err)
-  B200_TERM(dof_error, dof_err)
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_dof_pos_limits] != 0.0f) B200_DOFSUM(DV_POS_LIMITS, a)
-    B200_TERM(dof_pos_limits, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_dof_vel] != 0.0f) B200_DOFSUM(DV_VEL2, a)
-    B200_TERM(dof_vel, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_dof_vel_limits] != 0.0f) B200_DOFSUM(DV_VEL_LIMITS, a)
-    B200_TERM(dof_vel_limits, a)
-  }
-  {                                                     // go2.py:819-831 (stateful)
-    float a = 0.0f;
-    if (sc[B200_REW_feet_air_time] != 0.0f) {
-      // update_feet_states has already overwritten last_contacts with the CURRENT contacts (go2.py:307-310), so the
-      // "filtered" contact of this reward (go2.py:824-825) is just the current one
-      for (int f = 0; f < 4; ++f) {
-        const int now = R.contact_cur[f];
-        const float first = (S.fat[f] > 0.0f && now) ? 1.0f : 0.0f;
-        const float t = S.fat[f] + P.dt;
-        a += (t - 0.5f) * first;
-        R.fat[f] = t * (now ? 0.0f : 1.0f);
-      }
-      a *= norm2_fma(cmd[0], cmd[1]) > 0.1f ? 1.0f : 0.0f;
-    }
-    B200_TERM(feet_air_time, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_feet_contact_forces] != 0.0f)
-      for (int f = 0; f < 4; ++f) {
-        const float* c = S.contact + P.feet[f] * 3;
-        const float over = norm3_fma(c[0], c[1], c[2]) - P.max_contact_force;
-        a += over < 0.0f ? 0.0f : over;
-      }
-    B200_TERM(feet_contact_forces, a)
-  }
-  {                                                     // go2.py:734-756; wrap_to_pi mutates commands[:,3]
-    float a = 0.0f;
-    if (sc[B200_REW_heading_alignment] != 0.0f) {
-      float desired = 0.0f;
-      if (P.heading_command) {
-        cmd[3] = wrap_to_pi(cmd[3]);
-        desired = cmd[3];
-      }
-      a = sq(wrap_to_pi(desired - heading)) * moving;
-    }
-    B200_TERM(heading_alignment, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_hip_pos] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.hip_joints[f]];
-    B200_TERM(hip_pos, a)
-  }
-  B200_TERM(jump_zone_forward_vel, (root[7] < 0.0f ? 0.0f : root[7]) * jumping * moving)
-  B200_TERM(jump_zone_upward_vel, (root[9] < 0.0f ? 0.0f : root[9]) * jumping * moving)
-  B200_TERM(lin_vel_z, sq(blv.z))
-  B200_TERM(min_height, clampf(P.base_height_target - root[2], 0.0f, P.base_height_target) * jumping)
-  B200_TERM(orientation, sq(pg.x) + sq(pg.y))
-  {                                                     // go2.py:621-644
-    float a = 0.0f;
-    for (int f = 0; f < 4; ++f) a += (filt[f] == stance[f]) ? 0.25f : -0.25f;
-    B200_TERM(phase_contact_match, a)
-  }
-  {                                                     // go2.py:647-678
-    float a = 0.0f;
-    for (int f = 0; f < 4; ++f) {
-      const float h = clampf(S.feet_z[f] - R.lch[f], 0.0f, P.max_foot_height) / P.max_foot_height;
-      a += stance[f] ? -h : h;
-    }
-    B200_TERM(phase_foot_lifting, a / 2.0f)
-  }
-  B200_TERM(reverse_penalty, -(root[7] > 0.0f ? 0.0f : root[7]))
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_stand_still] != 0.0f) {
-      B200_DOFSUM(DV_ABS_DQ, a)
-      a *= norm2_fma(cmd[0], cmd[1]) < 0.1f ? 1.0f : 0.0f;
-    }
-    B200_TERM(stand_still, a)
-  }
-  {
-    int any = 0;
-    if (sc[B200_REW_stumble_calves] != 0.0f)
-      for (int f = 0; f < 4; ++f) {
-        const float* c = S.contact + P.calves[f] * 3;
-        any |= norm2_fma(c[0], c[1]) > 5.0f * fabsf(c[2]);
-      }
-    B200_TERM(stumble_calves, any ? 1.0f : 0.0f)
-  }
-  {
-    int any = 0;
-    if (sc[B200_REW_stumble_feet] != 0.0f)
-      for (int f = 0; f < 4; ++f) {
-        const float* c = S.contact + P.feet[f] * 3;
-        any |= norm2_fma(c[0], c[1]) > 5.0f * fabsf(c[2]);
-      }
-    B200_TERM(stumble_feet, any ? 1.0f : 0.0f)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_thigh_pos] != 0.0f)
-      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.thigh_joints[f]];
-    B200_TERM(thigh_pos, a)
-  }
-  B200_TERM(thigh_symmetry, fabsf(S.dof[2 * P.thigh_joints[0]] - S.dof[2 * P.thigh_joints[1]]) +
-                                fabsf(S.dof[2 * P.thigh_joints[2]] - S.dof[2 * P.thigh_joints[3]]))
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_torque_limits] != 0.0f) B200_DOFSUM(DV_TORQUE_LIMITS, a)
-    B200_TERM(torque_limits, a)
-  }
-  {
-    float a = 0.0f;
-    if (sc[B200_REW_torques] != 0.0f) B200_DOFSUM(DV_TORQUES2, a)
-    B200_TERM(torques, a)
-  }
-  B200_TERM(tracking_ang_vel, expf(-sq(cmd[2] - bav.z) / P.tracking_sigma))
-  B200_TERM(tracking_lin_vel, expf(-(sq(cmd[0] - blv.x) + sq(cmd[1] - blv.y)) / P.tracking_sigma))
-  B200_TERM(tracking_pitch, expf(-sq(pitch * 57.29577951308232f - P.pitch_deg_target) / P.tracking_sigma))
-  B200_TERM(tracking_roll, expf(-sq(roll * 57.29577951308232f - P.roll_deg_target) / P.tracking_sigma))
-  B200_TERM(zero_cmd_dof_error, dof_err * (cmd_n3 < 0.2f ? 1.0f : 0.0f))
-  if (P.only_positive_rewards) rew = rew < 0.0f ? 0.0f : rew;
-  {                                                     // legged_robot.py:234-237
-    float r_ = 0.0f;
-    if (sc[B200_REW_termination] != 0.0f) {
-      r_ = ((reset && !time_out) ? 1.0f : 0.0f) * sc[B200_REW_termination];
-      rew += r_;
-    }
-    S.term[B200_REW_termination] = r_;
-  }
-#undef B200_TERM
-#undef B200_DOFSUM
-  S.rew = rew;
-
-  // reset_idx on this env if flagged (go2.py:375-376)
-  int dof_dirty = 0;
-  if (reset) {
-    reset_env(P, B, R, S.type, step, e, 1);
-    root_dirty = 1;
-    dof_dirty = 1;
-  }
-  publish_reset_state(S, R, root_dirty, dof_dirty, reset);
-
-  // jump flags for the NEXT step's rewards (go2.py:487-494), from this step's heights
+  reset |= quat_rotate_inverse(S.root + 3, 0.0f, 0.0f, -1.0f).z > 0.0f;
+  if (P.parkour) reset |= S.root[2] < -1.0f;            // a push only touches root[7:9]
+  S.early_reset = reset;
+  S.early_time_out = time_out;
+  S.early_refill = reset || ep <= 1;                    // go2.py:570-574: episode_length_buf <= 1 after the reset
   float jf = S.jump_flag;
   if (P.parkour) {
     int n = 0;
@@ -619,21 +428,292 @@ B200_HD void env_scalar_stage(const B200EnvParams& P, const B200EnvBuffers& B, E
   S.jump_flag_out = jf;
 }
 
-// ---- one element of cur_obs (go2.py:506-519) ----------------------------------------------
-B200_HD float cur_obs_element(const B200EnvParams& P, const EnvScratch& S, float u, int i) {
-  float v;
-  if (i < 3) v = S.bav[i] * P.obs_ang_vel;
-  else if (i < 5) v = S.rpy[i - 3];
-  else if (i < 8) v = S.cmd_out[i - 5] * (i < 7 ? P.obs_lin_vel : P.obs_ang_vel);
-  else if (i < 20) v = (S.dof_out[2 * (i - 8)] - P.default_dof_pos[i - 8]) * P.obs_dof_pos;
-  else if (i < 32) v = S.dof_out[2 * (i - 20) + 1] * P.obs_dof_vel;
-  else if (i < 44) v = S.act[i - 32];
-  else {                                                // sin/cos of fr, fl, bl, br (go2.py:476-481); scratch order fl, fr, bl, br
+// item ids of one env: bodies | dofs | legs | angles | velocities | feet + push | flags
+enum { ITEM_BODY0 = 0, ITEM_DOF0 = ITEM_BODY0 + B200_NUM_BODIES, ITEM_LEG0 = ITEM_DOF0 + B200_NUM_DOF, ITEM_ANGLE0 = ITEM_LEG0 + 4,
+       ITEM_VEL = ITEM_ANGLE0 + 4, ITEM_FEET, ITEM_FLAGS, ITEM_COUNT };
+B200_HD void env_item(const B200EnvParams& P, const EnvTables& T, EnvScratch& S, int item, uint32_t e, int64_t step64) {
+  if (item < ITEM_DOF0) env_item_body(P, S, item - ITEM_BODY0);
+  else if (item < ITEM_LEG0) env_item_dof(P, T, S, item - ITEM_DOF0);
+  else if (item < ITEM_ANGLE0) env_item_leg(P, S, item - ITEM_LEG0);
+  else if (item < ITEM_VEL) env_item_angle(P, S, item - ITEM_ANGLE0, e, (uint32_t)step64);
+  else if (item == ITEM_VEL) env_item_velocities(S);
+  else if (item == ITEM_FEET) env_item_feet_push(P, S, e, step64);
+  else env_item_flags(P, S);
+}
+
+// ---- the reward terms (legged_robot.py:216-237 and every _reward_*): term k is evaluated by part k % B200_TERM_PARTS --
+// the CUDA kernel runs the parts on different warps (lane = env slot), the emulation one after the other.  A term reads
+// the staged inputs and the item-stage results and writes term[k] = value * (scale * dt), 0 for a disabled term; the two
+// stateful terms also publish their state (feet_air_time -> fat_out, heading_alignment -> cmd_out[3]).
+#define B200_TERM_PARTS 8
+template <bool FIXED>
+B200_HD void env_terms_part(const B200EnvParams& P, EnvScratch& S, int part) {
+  const int num_scan = FIXED ? B200_GO2_SCAN_NX * B200_GO2_SCAN_NY : P.num_scan;
+  const float* sc = P.reward_scales;
+  const float* cmd = S.cmd_out;                         // after resampling / heading update, before a reset
+  const float* root = S.root_out;                       // world-frame rewards see the push (Appendix C.7)
+  const float* blv = S.blv;
+  const float* bav = S.bav;
+  const float* pg = S.pg;
+#define B200_MINE(NAME) ((B200_REW_##NAME % B200_TERM_PARTS) == part)
+#define B200_ON(NAME) (sc[B200_REW_##NAME] != 0.0f)
+#define B200_PUT(NAME, VALUE) S.term[B200_REW_##NAME] = B200_ON(NAME) ? (VALUE) * sc[B200_REW_##NAME] : 0.0f
+#define B200_DOFSUM(ROW, OUT)                                   \
+  {                                                             \
+    OUT = 0.0f;                                                 \
+    for (int d_ = 0; d_ < 12; ++d_) OUT += S.dofv[ROW][d_];      \
+  }
+#define B200_DOFSUM_TERM(NAME, ROW)            \
+  if (B200_MINE(NAME)) {                       \
+    float a = 0.0f;                            \
+    if (B200_ON(NAME)) B200_DOFSUM(ROW, a)     \
+    B200_PUT(NAME, a);                         \
+  }
+  B200_DOFSUM_TERM(action_rate, DV_ACTION_RATE)
+  if (B200_MINE(ang_vel_xy)) B200_PUT(ang_vel_xy, sq(bav[0]) + sq(bav[1]));
+  if (B200_MINE(base_height)) {
+    float a = 0.0f;
+    if (B200_ON(base_height)) {
+      for (int j = 0; j < num_scan; ++j) a += root[2] - S.heights[j];
+      a = sq(a / (float)num_scan - P.base_height_target);
+    }
+    B200_PUT(base_height, a);
+  }
+  if (B200_MINE(calf_collision)) {
+    float a = 0.0f;
+    if (B200_ON(calf_collision))
+      for (int f = 0; f < 4; ++f) a += (S.body_hit[P.calves[f]] & 2) ? 1.0f : 0.0f;
+    B200_PUT(calf_collision, a);
+  }
+  if (B200_MINE(calf_pos)) {
+    float a = 0.0f;
+    if (B200_ON(calf_pos))
+      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.calf_joints[f]];
+    B200_PUT(calf_pos, a);
+  }
+  if (B200_MINE(calf_symmetry))
+    B200_PUT(calf_symmetry, fabsf(S.dof[2 * P.calf_joints[0]] - S.dof[2 * P.calf_joints[1]]) +
+                                fabsf(S.dof[2 * P.calf_joints[2]] - S.dof[2 * P.calf_joints[3]]));
+  if (B200_MINE(collision)) {
+    float a = 0.0f;
+    if (B200_ON(collision))
+      for (int i = 0; i < P.n_penalised; ++i) a += (S.body_hit[P.penalised[i]] & 2) ? 1.0f : 0.0f;
+    B200_PUT(collision, a);
+  }
+  B200_DOFSUM_TERM(delta_torques, DV_DELTA_TORQUES)
+  B200_DOFSUM_TERM(dof_acc, DV_DOF_ACC)
+  B200_DOFSUM_TERM(dof_error, DV_DQ2)
+  B200_DOFSUM_TERM(dof_pos_limits, DV_POS_LIMITS)
+  B200_DOFSUM_TERM(dof_vel, DV_VEL2)
+  B200_DOFSUM_TERM(dof_vel_limits, DV_VEL_LIMITS)
+  if (B200_MINE(feet_air_time)) {                       // go2.py:819-831 (stateful)
+    float a = 0.0f;
+    if (B200_ON(feet_air_time)) {
+      // update_feet_states has already overwritten last_contacts with the CURRENT contacts (go2.py:307-310), so the
+      // "filtered" contact of this reward (go2.py:824-825) is just the current one
+      for (int f = 0; f < 4; ++f) {
+        const int now = S.contact_cur[f];
+        const float first = (S.fat[f] > 0.0f && now) ? 1.0f : 0.0f;
+        const float t = S.fat[f] + P.dt;
+        a += (t - 0.5f) * first;
+        S.fat_out[f] = t * (now ? 0.0f : 1.0f);
+      }
+      a *= norm2_fma(cmd[0], cmd[1]) > 0.1f ? 1.0f : 0.0f;
+    }
+    B200_PUT(feet_air_time, a);
+  }
+  if (B200_MINE(feet_contact_forces)) {
+    float a = 0.0f;
+    if (B200_ON(feet_contact_forces))
+      for (int f = 0; f < 4; ++f) {
+        const float* c = S.contact + P.feet[f] * 3;
+        const float over = norm3_fma(c[0], c[1], c[2]) - P.max_contact_force;
+        a += over < 0.0f ? 0.0f : over;
+      }
+    B200_PUT(feet_contact_forces, a);
+  }
+  if (B200_MINE(heading_alignment)) {                   // go2.py:734-756; wrap_to_pi mutates commands[:,3]
+    float a = 0.0f;
+    if (B200_ON(heading_alignment)) {
+      float desired = 0.0f;
+      if (P.heading_command) {
+        desired = wrap_to_pi(cmd[3]);
+        S.cmd_out[3] = desired;
+      }
+      const float moving = norm3_fma(cmd[0], cmd[1], cmd[2]) >= 0.2f ? 1.0f : 0.0f;
+      a = sq(wrap_to_pi(desired - S.ang[3])) * moving;
+    }
+    B200_PUT(heading_alignment, a);
+  }
+  if (B200_MINE(hip_pos)) {
+    float a = 0.0f;
+    if (B200_ON(hip_pos))
+      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.hip_joints[f]];
+    B200_PUT(hip_pos, a);
+  }
+  if (B200_MINE(jump_zone_forward_vel) || B200_MINE(jump_zone_upward_vel) || B200_MINE(min_height)) {
+    const float moving = norm3_fma(cmd[0], cmd[1], cmd[2]) >= 0.2f ? 1.0f : 0.0f;
+    const float jumping = S.jump_flag > 0.0f ? 1.0f : 0.0f;
+    if (B200_MINE(jump_zone_forward_vel)) B200_PUT(jump_zone_forward_vel, (root[7] < 0.0f ? 0.0f : root[7]) * jumping * moving);
+    if (B200_MINE(jump_zone_upward_vel)) B200_PUT(jump_zone_upward_vel, (root[9] < 0.0f ? 0.0f : root[9]) * jumping * moving);
+    if (B200_MINE(min_height)) B200_PUT(min_height, clampf(P.base_height_target - root[2], 0.0f, P.base_height_target) * jumping);
+  }
+  if (B200_MINE(lin_vel_z)) B200_PUT(lin_vel_z, sq(blv[2]));
+  if (B200_MINE(orientation)) B200_PUT(orientation, sq(pg[0]) + sq(pg[1]));
+  if (B200_MINE(phase_contact_match)) {                 // go2.py:621-644
+    float a = 0.0f;
+    for (int f = 0; f < 4; ++f) a += (S.contact_filt[f] == S.leg_stance[f]) ? 0.25f : -0.25f;
+    B200_PUT(phase_contact_match, a);
+  }
+  if (B200_MINE(phase_foot_lifting)) {                  // go2.py:647-678
+    float a = 0.0f;
+    for (int f = 0; f < 4; ++f) {
+      const float h = clampf(S.feet_z[f] - S.lch_out[f], 0.0f, P.max_foot_height) / P.max_foot_height;
+      a += S.leg_stance[f] ? -h : h;
+    }
+    B200_PUT(phase_foot_lifting, a / 2.0f);
+  }
+  if (B200_MINE(reverse_penalty)) B200_PUT(reverse_penalty, -(root[7] > 0.0f ? 0.0f : root[7]));
+  if (B200_MINE(stand_still)) {
+    float a = 0.0f;
+    if (B200_ON(stand_still)) {
+      B200_DOFSUM(DV_ABS_DQ, a)
+      a *= norm2_fma(cmd[0], cmd[1]) < 0.1f ? 1.0f : 0.0f;
+    }
+    B200_PUT(stand_still, a);
+  }
+  if (B200_MINE(stumble_calves)) {
+    int any = 0;
+    if (B200_ON(stumble_calves))
+      for (int f = 0; f < 4; ++f) {
+        const float* c = S.contact + P.calves[f] * 3;
+        any |= norm2_fma(c[0], c[1]) > 5.0f * fabsf(c[2]);
+      }
+    B200_PUT(stumble_calves, any ? 1.0f : 0.0f);
+  }
+  if (B200_MINE(stumble_feet)) {
+    int any = 0;
+    if (B200_ON(stumble_feet))
+      for (int f = 0; f < 4; ++f) {
+        const float* c = S.contact + P.feet[f] * 3;
+        any |= norm2_fma(c[0], c[1]) > 5.0f * fabsf(c[2]);
+      }
+    B200_PUT(stumble_feet, any ? 1.0f : 0.0f);
+  }
+  if (B200_MINE(thigh_pos)) {
+    float a = 0.0f;
+    if (B200_ON(thigh_pos))
+      for (int f = 0; f < 4; ++f) a += S.dofv[DV_DQ2][P.thigh_joints[f]];
+    B200_PUT(thigh_pos, a);
+  }
+  if (B200_MINE(thigh_symmetry))
+    B200_PUT(thigh_symmetry, fabsf(S.dof[2 * P.thigh_joints[0]] - S.dof[2 * P.thigh_joints[1]]) +
+                                 fabsf(S.dof[2 * P.thigh_joints[2]] - S.dof[2 * P.thigh_joints[3]]));
+  B200_DOFSUM_TERM(torque_limits, DV_TORQUE_LIMITS)
+  B200_DOFSUM_TERM(torques, DV_TORQUES2)
+  if (B200_MINE(tracking_ang_vel)) B200_PUT(tracking_ang_vel, expf(-sq(cmd[2] - bav[2]) / P.tracking_sigma));
+  if (B200_MINE(tracking_lin_vel)) B200_PUT(tracking_lin_vel, expf(-(sq(cmd[0] - blv[0]) + sq(cmd[1] - blv[1])) / P.tracking_sigma));
+  if (B200_MINE(tracking_pitch)) B200_PUT(tracking_pitch, expf(-sq(S.ang[1] * 57.29577951308232f - P.pitch_deg_target) / P.tracking_sigma));
+  if (B200_MINE(tracking_roll)) B200_PUT(tracking_roll, expf(-sq(S.ang[0] * 57.29577951308232f - P.roll_deg_target) / P.tracking_sigma));
+  if (B200_MINE(zero_cmd_dof_error)) {
+    float a = 0.0f;
+    if (B200_ON(zero_cmd_dof_error)) {
+      B200_DOFSUM(DV_DQ2, a)
+      a = a * (norm3_fma(cmd[0], cmd[1], cmd[2]) < 0.2f ? 1.0f : 0.0f);
+    }
+    B200_PUT(zero_cmd_dof_error, a);
+  }
+#undef B200_DOFSUM_TERM
+#undef B200_DOFSUM
+#undef B200_PUT
+#undef B200_MINE
+}
+
+// ---- compute_reward's sum (alphabetical, legged_robot.py:216-237), the termination reward, and reset_idx on this env if
+// flagged (go2.py:375-376).  One thread per env, after every part of env_terms_part.
+// (needs EnvScratch::reset_draws when the env resets: env_reset_draw, blocks 0..6)
+B200_HD void env_finalize(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S) {
+  const float* sc = P.reward_scales;
+  const int reset = S.early_reset, time_out = S.early_time_out;
+  float rew = 0.0f;
+  for (int k = 0; k < B200_REW_termination; ++k)
+    if (sc[k] != 0.0f) rew += S.term[k];
+  if (P.only_positive_rewards) rew = rew < 0.0f ? 0.0f : rew;
+  {                                                     // legged_robot.py:234-237
+    float r_ = 0.0f;
+    if (B200_ON(termination)) {
+      r_ = ((reset && !time_out) ? 1.0f : 0.0f) * sc[B200_REW_termination];
+      rew += r_;
+    }
+    S.term[B200_REW_termination] = r_;
+  }
+#undef B200_ON
+  S.rew = rew;
+  S.reset = reset;
+  S.time_out = time_out;
+  S.dof_dirty = reset;
+  S.level_out = S.level;
+  S.ep_len_out = S.ep_len + 1;
+  if (reset) {                                          // rare: everything the reset touches goes through registers
+    ResetState R;
+    for (int i = 0; i < 13; ++i) R.root[i] = S.root_out[i];
+    for (int i = 0; i < 24; ++i) R.dof[i] = S.dof_out[i];
+    for (int i = 0; i < 4; ++i) R.cmd[i] = S.cmd_out[i];
+    for (int i = 0; i < 3; ++i) R.origin[i] = S.origin_out[i];
+    R.level = S.level;
+    R.ep_len = S.ep_len + 1;
+    reset_env(P, B, R, S.type, S.reset_draws, 1);
+    for (int i = 0; i < 13; ++i) S.root_out[i] = R.root[i];
+    for (int i = 0; i < 24; ++i) S.dof_out[i] = R.dof[i];
+    for (int i = 0; i < 4; ++i) {
+      S.cmd_out[i] = R.cmd[i];
+      S.lch_out[i] = R.lch[i];
+      S.fat_out[i] = R.fat[i];
+      S.contact_cur[i] = R.contact_cur[i];
+    }
+    for (int i = 0; i < 3; ++i) S.origin_out[i] = R.origin[i];
+    S.level_out = R.level;
+    S.ep_len_out = R.ep_len;
+    S.root_dirty = 1;
+  }
+}
+
+
+// ---- cur_obs (go2.py:506-519) as a table: element i = (one float of the scratch - offset) * scale ----------------
+//   [0:3) base_ang_vel * 0.25 | [3:5) roll, pitch | [5:8) commands * (2, 2, 0.25) | [8:20) (dof_pos - default) * 1
+//   [20:32) dof_vel * 0.05 | [32:44) actions | [44:52) sin, cos of the fr, fl, bl, br phases (go2.py:476-481)
+// (x - 0) * 1 is x bit for bit, so one formula serves every segment.  Entry i of every table: env_tables_fill(P, T, i).
+#define B200_SOFF(field) ((int)(offsetof(EnvScratch, field) / sizeof(float)))
+B200_HD void env_tables_fill(const B200EnvParams& P, EnvTables& T, int i) {
+  if (i < B200_NUM_DOF) {
+    T.default_dof_pos[i] = P.default_dof_pos[i];
+    T.dof_pos_lo[i] = P.dof_pos_lo[i];
+    T.dof_pos_hi[i] = P.dof_pos_hi[i];
+    T.dof_vel_soft[i] = P.dof_vel_limits[i] * P.soft_dof_vel_limit;
+    T.torque_soft[i] = P.torque_limits[i] * P.soft_torque_limit;
+  }
+  if (i >= B200_MAX_PROPRIO) return;
+  int idx = 0;
+  float off = 0.0f, scl = 1.0f;
+  if (i < 3) { idx = B200_SOFF(bav) + i; scl = P.obs_ang_vel; }
+  else if (i < 5) { idx = B200_SOFF(rpy) + (i - 3); }
+  else if (i < 8) { idx = B200_SOFF(cmd_out) + (i - 5); scl = i < 7 ? P.obs_lin_vel : P.obs_ang_vel; }
+  else if (i < 20) { idx = B200_SOFF(dof_out) + 2 * (i - 8); off = P.default_dof_pos[i - 8]; scl = P.obs_dof_pos; }
+  else if (i < 32) { idx = B200_SOFF(dof_out) + 2 * (i - 20) + 1; scl = P.obs_dof_vel; }
+  else if (i < 44) { idx = B200_SOFF(act) + (i - 32); }
+  else if (i < B200_PROPRIO) {                          // scratch order of the legs is fl, fr, bl, br
     const int leg = (i - 44) >> 1;
     const int f = leg == 0 ? 1 : (leg == 1 ? 0 : leg);
-    v = ((i - 44) & 1) ? S.leg_cos[f] : S.leg_sin[f];
+    idx = (((i - 44) & 1) ? B200_SOFF(leg_cos) : B200_SOFF(leg_sin)) + f;
   }
-  if (P.add_noise) v += (2.0f * u - 1.0f) * P.noise_vec[i];
+  T.cur_idx[i] = idx;
+  T.cur_off[i] = off;
+  T.cur_scl[i] = scl;
+  T.noise[i] = i < B200_PROPRIO ? P.noise_vec[i] : 0.0f;
+}
+B200_HD float cur_obs_element(const B200EnvParams& P, const EnvTables& T, const EnvScratch& S, float u, int i) {
+  float v = (reinterpret_cast<const float*>(&S)[T.cur_idx[i]] - T.cur_off[i]) * T.cur_scl[i];
+  if (P.add_noise) v += (2.0f * u - 1.0f) * T.noise[i];
   return v;
 }
 
@@ -645,79 +725,148 @@ B200_HD f4_ clamp4(f4_ v, float c) {
   return v;
 }
 
-// ---- the whole env step for env `e`, lanes [lane_lo, lane_hi) -------------------------------
-// Row sizes are multiples of 4 floats for the go2 layout (52, 520, 572, 736, 132, critic tail 164),
-// so the bulk rows move as 16-byte vectors; `vec_ok` (warp-uniform) falls back to scalars otherwise.
-// The env step of env `e` is three calls:
-//   env_warp_pre    one warp, lanes [lane_lo, lane_hi): stage 0 (load), 1 (height scan), 2a (element stage)
-//   env_scalar_stage one THREAD per env (the CUDA kernel runs it on warp 0 of the CTA, lane = env slot)
-//   env_warp_post   one warp: stage 3 (observation assembly), 4 (write-back)
+// ---- the whole env step for env `e` --------------------------------------------------------------
+// All bulk rows are multiples of 4 floats (52, 520, 572, 736, 132, critic tail 164; b200_env_create
+// rejects a scan size that is not) and move as 16-byte vectors.  The env step of env `e` is, in dependency order:
+//   env_warp_pre      one warp, lanes [lane_lo, lane_hi): stage 0 (load the small rows), 1 (height scan)
+//   env_item          ITEM_COUNT independent items (bodies, dofs, legs, angles + command update, velocities, feet + push,
+//                     termination flags), one thread each
+//   env_hist_load / env_hist_store   the history rows, one 16-byte vector per call: history -> clip -> obs / critic
+//                     and history shifted by one slot, straight from global to global; need only the flags item
+//   env_terms_part    the reward terms, B200_TERM_PARTS independent parts, one thread per (env, part)
+//   env_finalize      reward sum, termination reward, reset_idx; one thread per env
+//   env_warp_post     one warp: stage 3 (current observation, critic tail), 4 (write-back)
+// The CUDA kernel (env_kernels.cu) maps these onto a CTA of 8 envs so that every phase fills its warps.
+// FIXED = true bakes the go2 layout (history 10, scan 12 x 11) into the code: trip counts and row offsets
+// become literals, loops unroll, loads batch.  FIXED = false reads them from P (any other layout).
 // scan_x / scan_y: the scan-point tables (shared-memory copies on the GPU, P.scan_x / P.scan_y on the host)
-#define B200_ENV_DIMS                                                      \
-  const int NP = B200_PROPRIO, H = P.history_len, NS = P.num_scan;         \
-  const int HN = H * NP, OBS = HN + NP;                                    \
-  const int TAIL = P.num_priv + P.num_est + NS;                            \
-  const int CRIT = OBS + TAIL;                                             \
-  const int64_t N = P.num_envs;                                            \
-  const bool vec_ok = (HN % 4 == 0) && (TAIL % 4 == 0) && (NS % 4 == 0) && ((P.num_priv + P.num_est) % 4 == 0); \
-  float* hist = B.obs_history_buf + (int64_t)e * HN;                       \
-  (void)OBS; (void)CRIT; (void)N; (void)TAIL
+#define B200_ENV_DIMS                                                                 \
+  constexpr int NP = B200_PROPRIO, NP4 = NP / 4;                                      \
+  const int H = FIXED ? B200_GO2_HISTORY : P.history_len;                             \
+  const int NS = FIXED ? B200_GO2_SCAN_NX * B200_GO2_SCAN_NY : P.num_scan;            \
+  const int NY = FIXED ? B200_GO2_SCAN_NY : P.scan_ny;                                \
+  constexpr int NPRIV = 29, NEST = 3, PE = NPRIV + NEST;                              \
+  const int HN = H * NP, HN4 = HN / 4, OBS = HN + NP, OBS4 = OBS / 4;                 \
+  const int TAIL = PE + NS, TAIL4 = TAIL / 4, NS4 = NS / 4;                           \
+  const int CRIT = OBS + TAIL;                                                        \
+  const int64_t N = P.num_envs;                                                       \
+  (void)H; (void)NS; (void)NY; (void)HN; (void)HN4; (void)OBS; (void)OBS4; (void)TAIL; \
+  (void)TAIL4; (void)NS4; (void)CRIT; (void)N; (void)NP4; (void)PE
 
+B200_HD bool env_layout_is_go2(const B200EnvParams& P) {
+  return P.history_len == B200_GO2_HISTORY && P.scan_nx == B200_GO2_SCAN_NX && P.scan_ny == B200_GO2_SCAN_NY &&
+         P.num_scan == B200_GO2_SCAN_NX * B200_GO2_SCAN_NY;
+}
+
+template <bool FIXED>
 B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* scan_x, const float* scan_y,
                           int e, int lane_lo, int lane_hi) {
   B200_ENV_DIMS;
 
-  // ---- stage 0: stage the env's rows into scratch (coalesced: consecutive lanes, consecutive floats)
+  // ---- stage 0: stage the env's small rows into scratch (coalesced: consecutive lanes, consecutive floats).
+  // Every load is unconditional on a clamped index and issued before the first store, so the ~25 rows cost ONE
+  // memory round trip instead of one per predicated block.  The privileged statics of stage 3 are fetched here too.
   B200_FOR_LANES(lane) {
-    if (vec_ok) {
-      const f4_* src = reinterpret_cast<const f4_*>(hist);
-      f4_* dst = reinterpret_cast<f4_*>(S.histcur);
-      for (int i = lane; i < HN / 4; i += 32) dst[i] = src[i];
-    } else {
-      for (int i = lane; i < HN; i += 32) S.histcur[i] = hist[i];
+    const int64_t E = e;
+    const int l4 = lane & 3, l12 = lane < 12 ? lane : 11, l13 = lane < 13 ? lane : 12, l24 = lane < 24 ? lane : 23;
+    const int lc = lane + 32 < B200_NUM_BODIES * 3 ? lane + 32 : B200_NUM_BODIES * 3 - 1;
+    const int ls = lane + 32 < B200_NUM_REWARD_TERMS ? lane + 32 : B200_NUM_REWARD_TERMS - 1;
+    const float r_root = B.root_states[E * 13 + l13];
+    const float r_dof = B.dof_state[E * 24 + l24];
+    const float r_c0 = B200_LDG(B.contact_forces + E * B200_NUM_BODIES * 3 + lane);
+    const float r_c1 = B200_LDG(B.contact_forces + E * B200_NUM_BODIES * 3 + lc);
+    const float r_fz = B200_LDG(B.rigid_body_states + (E * B200_NUM_BODIES + P.feet[l4]) * 13 + 2);
+    const float r_cmd = B.commands[E * 4 + l4];
+    const float r_lch = B.last_contact_heights[E * 4 + l4];
+    const float r_fat = B.feet_air_time[E * 4 + l4];
+    const uint8_t r_lc = B.last_contacts[E * 4 + l4];
+    const float r_act = B.actions[E * 12 + l12];
+    const float r_tq = B.torques[E * 12 + l12];
+    const float r_la = B.last_actions[E * 12 + l12];
+    const float r_ldv = B.last_dof_vel[E * 12 + l12];
+    const float r_ltq = B.last_torques[E * 12 + l12];
+    const float r_s0 = B.episode_sums[E * B200_NUM_REWARD_TERMS + lane];
+    const float r_s1 = B.episode_sums[E * B200_NUM_REWARD_TERMS + ls];
+    const float r_org = B.env_origins[E * 3 + (lane < 3 ? lane : 2)];
+    const int64_t r_ep = B.episode_length_buf[e];
+    const float r_jf = B.jump_flags[e];
+    const int64_t r_lv = B.terrain_levels[e];
+    const int64_t r_ty = B200_LDG(B.terrain_types + e);
+    // privileged statics (go2.py:528-532): mass/com 4 | friction 1 | kp - 1 (12) | kd - 1 (12); lanes 29-31 unused
+    float r_priv;
+    {
+      const int i = lane < NPRIV ? lane : NPRIV - 1;
+      const float* src = i < 4 ? B.priv_mass_params + E * 4 + i
+                               : (i < 5 ? B.priv_friction + E : (i < 17 ? B.kp_kd_multipliers + E * 12 + (i - 5) : B.kp_kd_multipliers + (N + E) * 12 + (i - 17)));
+      r_priv = B200_LDG(src);
+      if (i >= 5) r_priv = r_priv - 1.0f;
     }
-    if (lane < 13) S.root[lane] = B.root_states[(int64_t)e * 13 + lane];
-    if (lane < 24) S.dof[lane] = B.dof_state[(int64_t)e * 24 + lane];
-    for (int i = lane; i < B200_NUM_BODIES * 3; i += 32) S.contact[i] = B200_LDG(B.contact_forces + (int64_t)e * B200_NUM_BODIES * 3 + i);
+    if (lane < 13) S.root[lane] = S.root_out[lane] = r_root;      // *_out: what the step leaves behind unless a push /
+    if (lane < 24) S.dof[lane] = S.dof_out[lane] = r_dof;         // reset / reward term overwrites it
+    S.contact[lane] = r_c0;
+    if (lane + 32 < B200_NUM_BODIES * 3) S.contact[lane + 32] = r_c1;
     if (lane < 4) {
-      S.feet_z[lane] = B200_LDG(B.rigid_body_states + ((int64_t)e * B200_NUM_BODIES + P.feet[lane]) * 13 + 2);
-      S.cmd[lane] = B.commands[(int64_t)e * 4 + lane];
-      S.lch[lane] = B.last_contact_heights[(int64_t)e * 4 + lane];
-      S.fat[lane] = B.feet_air_time[(int64_t)e * 4 + lane];
-      S.last_contacts[lane] = B.last_contacts[(int64_t)e * 4 + lane];
+      S.feet_z[lane] = r_fz;
+      S.cmd[lane] = r_cmd;
+      S.lch[lane] = r_lch;
+      S.fat[lane] = S.fat_out[lane] = r_fat;
+      S.last_contacts[lane] = r_lc;
     }
     if (lane < 12) {
-      S.act[lane] = B.actions[(int64_t)e * 12 + lane];
-      S.tq[lane] = B.torques[(int64_t)e * 12 + lane];
-      S.last_act[lane] = B.last_actions[(int64_t)e * 12 + lane];
-      S.last_dv[lane] = B.last_dof_vel[(int64_t)e * 12 + lane];
-      S.last_tq[lane] = B.last_torques[(int64_t)e * 12 + lane];
+      S.act[lane] = r_act;
+      S.tq[lane] = r_tq;
+      S.last_act[lane] = r_la;
+      S.last_dv[lane] = r_ldv;
+      S.last_tq[lane] = r_ltq;
     }
-    for (int k = lane; k < B200_NUM_REWARD_TERMS; k += 32) S.sums[k] = B.episode_sums[(int64_t)e * B200_NUM_REWARD_TERMS + k];
-    if (lane < 3) S.origin[lane] = B.env_origins[(int64_t)e * 3 + lane];
+    S.sums[lane] = r_s0;
+    if (lane + 32 < B200_NUM_REWARD_TERMS) S.sums[lane + 32] = r_s1;
+    if (lane < 3) S.origin[lane] = S.origin_out[lane] = r_org;
+    if (lane < NPRIV) S.tail[lane] = clampf(r_priv, -P.clip_obs, P.clip_obs);
     if (lane == 0) {
-      S.ep_len = B.episode_length_buf[e];
-      S.jump_flag = B.jump_flags[e];
-      S.level = B.terrain_levels[e];
-      S.type = B200_LDG(B.terrain_types + e);
+      S.ep_len = r_ep;
+      S.jump_flag = r_jf;
+      S.level = r_lv;
+      S.type = r_ty;
     }
   }
   B200_WARP_SYNC();
 
-  // ---- stage 1: height scan, points strided over lanes (legged_robot.py:997-1032)
+  // ---- stage 1: height scan, points strided over lanes (legged_robot.py:997-1032): all cells of the lane first, then
+  // all gathers (3 per point, independent), then the minima -- one round trip to the height field per lane
   B200_FOR_LANES(lane) {
     int n_out = 0;
     if (P.has_height_samples) {
       const YawQuat yq = yaw_quat(S.root + 3);
-      for (int j = lane; j < NS; j += 32) {
-        int px, py;
-        height_cell(P, scan_x, scan_y, yq, S.root, j, &px, &py);
-        const float h = height_at(P, B.height_samples, px, py);
-        S.heights[j] = h;
-        n_out += fabsf(h) > 0.1f;
-        if (B.height_index) {
-          B.height_index[((int64_t)e * NS + j) * 2] = px;
-          B.height_index[((int64_t)e * NS + j) * 2 + 1] = py;
+      constexpr int kMaxPerLane = (B200_MAX_SCAN + 31) / 32;
+      const int per_lane = FIXED ? (B200_GO2_SCAN_NX * B200_GO2_SCAN_NY + 31) / 32 : kMaxPerLane;
+      int px[kMaxPerLane], py[kMaxPerLane];
+      int16_t ha[kMaxPerLane], hb[kMaxPerLane], hc[kMaxPerLane];
+#pragma unroll
+      for (int k = 0; k < per_lane; ++k) {
+        const int j = lane + 32 * k;
+        height_cell(P, NY, scan_x, scan_y, yq, S.root, j < NS ? j : NS - 1, &px[k], &py[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < per_lane; ++k) {
+        const int16_t* p = B.height_samples + (px[k] * P.hs_cols + py[k]);   // rows * cols < 2^31 (checked at env creation)
+        ha[k] = B200_LDG(p);
+        hb[k] = B200_LDG(p + P.hs_cols);
+        hc[k] = B200_LDG(p + 1);
+      }
+#pragma unroll
+      for (int k = 0; k < per_lane; ++k) {
+        const int j = lane + 32 * k;
+        if (j < NS) {
+          int16_t m = ha[k] < hb[k] ? ha[k] : hb[k];
+          m = m < hc[k] ? m : hc[k];
+          const float h = (float)m * P.vertical_scale;
+          S.heights[j] = h;
+          n_out += fabsf(h) > 0.1f;
+          if (B.height_index) {
+            B.height_index[((int64_t)e * NS + j) * 2] = px[k];
+            B.height_index[((int64_t)e * NS + j) * 2 + 1] = py[k];
+          }
         }
       }
     } else {
@@ -726,22 +875,36 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
     S.outliers[lane] = n_out;
   }
   B200_WARP_SYNC();
-
-  // ---- stage 2a: element stage (one lane per body / dof / leg / angle)
-  B200_FOR_LANES(lane) { env_element_stage(P, S, lane); }
-  B200_WARP_SYNC();
-
 }
 
-B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, int e, int64_t step64, int lane_lo, int lane_hi) {
+// ---- the history rows (go2.py:566-576): vector i of env e's [H x 52] history.
+//   obs[e, 0:HN] = critic[e, 0:HN] = clip(history)   (zeros when the env reset: obs_history_buf[env_ids] = 0, go2.py:238)
+//   history      = history shifted left by one slot   (unless it is refilled with the new row: env_warp_post)
+// A caller that moves a row with several lanes must finish ALL its loads of the row before the first store (the shift
+// is in place): the CUDA kernel puts a barrier between the two, the host emulation loads the whole row first.
+template <bool FIXED>
+B200_HD f4_ env_hist_load(const B200EnvParams& P, const B200EnvBuffers& B, int e, int i) {
+  B200_ENV_DIMS;
+  return reinterpret_cast<const f4_*>(B.obs_history_buf + (int64_t)e * HN)[i];
+}
+template <bool FIXED>
+B200_HD void env_hist_store(const B200EnvParams& P, const B200EnvBuffers& B, int e, int i, f4_ v, int reset, int refill) {
+  B200_ENV_DIMS;
+  f4_ o = clamp4(v, P.clip_obs);
+  if (reset) o.x = o.y = o.z = o.w = 0.0f;
+  reinterpret_cast<f4_*>(B.obs_buf + (int64_t)e * OBS)[i] = o;
+  reinterpret_cast<f4_*>(B.critic_obs_buf + (int64_t)e * CRIT)[i] = o;
+  if (!refill && i >= NP4) reinterpret_cast<f4_*>(B.obs_history_buf + (int64_t)e * HN)[i - NP4] = v;
+}
+
+template <bool FIXED>
+B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, const EnvTables& T, EnvScratch& S, int e, int64_t step64, int lane_lo,
+                           int lane_hi) {
   B200_ENV_DIMS;
 
   // ---- stage 3: current observation + critic tail, elements strided over lanes
   B200_FOR_LANES(lane) {
     const float c = P.clip_obs;
-    if (S.reset) {                                        // obs_history_buf[env_ids] = 0 (go2.py:238)
-      for (int i = lane; i < HN; i += 32) S.histcur[i] = 0.0f;
-    }
     {
       // observation noise (go2.py:519): elements lane and lane + 32 take words (lane >> 4) and (lane >> 4) + 2 of ONE
       // Philox block (block = lane & 15) -- the keyed lane numbering of oracle/philox.py::noise_lane
@@ -753,67 +916,43 @@ B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, EnvS
           const uint32_t w = (uint32_t)(i >> 4);
           u = u32_to_uniform(w == 0 ? r.v[0] : (w == 1 ? r.v[1] : (w == 2 ? r.v[2] : r.v[3])));
         }
-        S.histcur[HN + i] = cur_obs_element(P, S, u, i);
+        S.cur[i] = cur_obs_element(P, T, S, u, i);
       }
     }
-    for (int i = lane; i < P.num_priv; i += 32) {         // go2.py:528-532
-      float v;
-      if (i < 4) v = B200_LDG(B.priv_mass_params + (int64_t)e * 4 + i);
-      else if (i < 5) v = B200_LDG(B.priv_friction + e);
-      else if (i < 17) v = B200_LDG(B.kp_kd_multipliers + (int64_t)e * 12 + (i - 5)) - 1.0f;
-      else v = B200_LDG(B.kp_kd_multipliers + (N + e) * 12 + (i - 17)) - 1.0f;
-      S.tail[i] = clampf(v, -c, c);
-    }
-    for (int i = lane; i < P.num_est; i += 32) S.tail[P.num_priv + i] = clampf(S.blv[i] * P.obs_lin_vel, -c, c);
+    if (lane >= NPRIV) S.tail[lane] = clampf(S.blv[lane - NPRIV] * P.obs_lin_vel, -c, c);   // priv part: stage 0
     for (int j = lane; j < NS; j += 32)                    // go2.py:538, root z AFTER a possible reset
-      S.tail[P.num_priv + P.num_est + j] = clampf((S.root_out[2] - 0.3f) - S.heights[j], -1.0f, 1.0f);
+      S.tail[PE + j] = clampf((S.root_out[2] - 0.3f) - S.heights[j], -1.0f, 1.0f);
   }
   B200_WARP_SYNC();
 
   // ---- stage 4: write everything back (row-contiguous, lanes over consecutive 16-byte vectors)
   B200_FOR_LANES(lane) {
     const float c = P.clip_obs;
-    const bool refill = S.ep_len_out <= 1;               // go2.py:570-574
-    float* obs = B.obs_buf + (int64_t)e * OBS;
-    float* crit = B.critic_obs_buf + (int64_t)e * CRIT;
-    if (vec_ok) {
-      const f4_* hc = reinterpret_cast<const f4_*>(S.histcur);
-      f4_* obs4 = reinterpret_cast<f4_*>(obs);
-      f4_* crit4 = reinterpret_cast<f4_*>(crit);
-      f4_* hist4 = reinterpret_cast<f4_*>(hist);
-      for (int i = lane; i < OBS / 4; i += 32) {          // obs = clip([history | cur]); critic starts with it
-        const f4_ v = clamp4(hc[i], c);
-        obs4[i] = v;
-        crit4[i] = v;
-      }
-      if (!refill) {                                      // history <- shift left one slot ...
-        for (int i = lane; i < HN / 4; i += 32) hist4[i] = hc[i + NP / 4];
-      } else {                                            // ... or cur x H right after a reset (go2.py:570-574)
-        for (int i = lane; i < HN / 4; i += 32) hist4[i] = hc[HN / 4 + i % (NP / 4)];
-      }
-      const f4_* t4 = reinterpret_cast<const f4_*>(S.tail);
-      for (int i = lane; i < TAIL / 4; i += 32) crit4[OBS / 4 + i] = t4[i];
-      const f4_* s4 = reinterpret_cast<const f4_*>(S.tail + P.num_priv + P.num_est);
-      const f4_* h4 = reinterpret_cast<const f4_*>(S.heights);
-      for (int i = lane; i < NS / 4; i += 32) {
-        reinterpret_cast<f4_*>(B.scan_obs_buf + (int64_t)e * NS)[i] = s4[i];
-        reinterpret_cast<f4_*>(B.measured_heights + (int64_t)e * NS)[i] = h4[i];
-      }
-    } else {
-      for (int i = lane; i < OBS; i += 32) {
-        const float v = clampf(S.histcur[i], -c, c);
-        obs[i] = v;
-        crit[i] = v;
-      }
-      for (int i = lane; i < HN; i += 32) hist[i] = refill ? S.histcur[HN + i % NP] : S.histcur[i + NP];
-      for (int i = lane; i < TAIL; i += 32) crit[OBS + i] = S.tail[i];
-      for (int j = lane; j < NS; j += 32) {
-        B.scan_obs_buf[(int64_t)e * NS + j] = S.tail[P.num_priv + P.num_est + j];
-        B.measured_heights[(int64_t)e * NS + j] = S.heights[j];
-      }
+    const bool refill = S.ep_len_out <= 1;               // go2.py:570-574 (== S.early_refill)
+    f4_* obs4 = reinterpret_cast<f4_*>(B.obs_buf + (int64_t)e * OBS);
+    f4_* crit4 = reinterpret_cast<f4_*>(B.critic_obs_buf + (int64_t)e * CRIT);
+    f4_* hist4 = reinterpret_cast<f4_*>(B.obs_history_buf + (int64_t)e * HN);
+    const f4_* cur4 = reinterpret_cast<const f4_*>(S.cur);
+    if (lane < NP4) {                                     // obs / critic end with clip(cur); history's newest slot is cur
+      const f4_ v = cur4[lane];
+      const f4_ o = clamp4(v, c);
+      obs4[HN4 + lane] = o;
+      crit4[HN4 + lane] = o;
+      if (!refill) hist4[HN4 - NP4 + lane] = v;
     }
-    for (int i = lane; i < P.num_priv; i += 32) B.privileged_obs_buf[(int64_t)e * P.num_priv + i] = S.tail[i];
-    for (int i = lane; i < P.num_est; i += 32) B.estimated_obs_buf[(int64_t)e * P.num_est + i] = S.tail[P.num_priv + i];
+    if (refill) {                                         // cur x H right after a reset (go2.py:570-574)
+      for (int i = lane; i < HN4; i += 32) hist4[i] = cur4[i % NP4];
+    }
+    const f4_* t4 = reinterpret_cast<const f4_*>(S.tail);
+    for (int i = lane; i < TAIL4; i += 32) crit4[OBS4 + i] = t4[i];
+    const f4_* s4 = reinterpret_cast<const f4_*>(S.tail + PE);
+    const f4_* h4 = reinterpret_cast<const f4_*>(S.heights);
+    for (int i = lane; i < NS4; i += 32) {
+      reinterpret_cast<f4_*>(B.scan_obs_buf + (int64_t)e * NS)[i] = s4[i];
+      reinterpret_cast<f4_*>(B.measured_heights + (int64_t)e * NS)[i] = h4[i];
+    }
+    if (lane < NPRIV) B.privileged_obs_buf[(int64_t)e * NPRIV + lane] = S.tail[lane];
+    else B.estimated_obs_buf[(int64_t)e * NEST + (lane - NPRIV)] = S.tail[lane];
     // persistent state (go2.py:380-384 and the in-place updates of reset_idx)
     if (lane < 12) {
       B.last_actions[(int64_t)e * 12 + lane] = S.act[lane];
@@ -864,7 +1003,9 @@ B200_HD void env_reset_only(const B200EnvParams& P, const B200EnvBuffers& B, int
   for (int i = 0; i < 3; ++i) R.origin[i] = B.env_origins[(int64_t)e * 3 + i];
   R.level = B.terrain_levels[e];
   R.ep_len = 0;
-  reset_env(P, B, R, B.terrain_types[e], (uint32_t)step64, (uint32_t)e, init_done);
+  uint32_t draws[4 * B200_RESET_BLOCKS];
+  for (int b = 0; b < B200_RESET_BLOCKS; ++b) env_reset_draw(P, draws, (uint32_t)e, (uint32_t)step64, b);
+  reset_env(P, B, R, B.terrain_types[e], draws, init_done);
   for (int i = 0; i < 13; ++i) B.root_states[(int64_t)e * 13 + i] = R.root[i];
   for (int i = 0; i < 24; ++i) B.dof_state[(int64_t)e * 24 + i] = R.dof[i];
   for (int i = 0; i < 4; ++i) {

@@ -23,30 +23,121 @@ void b200_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int kEnvsPerCta = 8;      // one warp per env for the lane-parallel stages; warp 0 runs the scalar stage, one THREAD per env
+constexpr int kEnvsPerCta = 8;      // one warp per env for the row-parallel stages
+constexpr int kHistThreads = (kEnvsPerCta - 1) * 32;   // warps 1..7 move the history rows
+constexpr int kHistPerThread = 5;   // 8 envs x 130 vectors = 1040 <= 5 x 224
+static_assert(B200_TERM_PARTS == kEnvsPerCta, "one reward-term part per warp");
+static_assert(kEnvsPerCta * (B200_NUM_BODIES + B200_NUM_DOF + 1) <= kEnvsPerCta * 32, "item pass 1 must fit the CTA");
 
 // `step_dev` != nullptr: the step counter lives in device memory (CUDA-graph replay); else `step` is used.
+//
+// Phases of a CTA (8 envs, 8 warps; every phase ends with __syncthreads):
+//   A   warp w: load env w's small rows, height scan (stage 0 / 1 of env_core.cuh)
+//   E   the items of all 8 envs packed type by type: pass 1 = 152 bodies | 96 dofs | 8 flags over the 256 threads;
+//       pass 2 = warp 0: 32 legs, warp 1: 32 angles (+ command update), warp 2: velocities, warp 3: feet + push (8 lanes)
+//   B1  warp p, lane s < 8: part p of the reward terms of env slot s; warp w, 7 lanes: the Philox blocks of env w's reset
+//       (if it resets); warps 1-7 then LOAD the 8 history rows
+//   B2  warp 0, lane s < 8: reward sum, termination reward, reset of env slot s;
+//       warps 1-7 meanwhile STORE the history rows (history -> clip -> obs / critic, history shifted in place)
+//   C   warp w: current observation + critic tail of env w, write-back
+template <bool FIXED>
 __global__ void __launch_bounds__(kEnvsPerCta * 32, 4)
 post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
-                    const int64_t* __restrict__ step_dev) {
+                    const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EnvScratch* scratch = reinterpret_cast<EnvScratch*>(smem_raw);
   __shared__ float scan_x[B200_MAX_SCAN_AXIS], scan_y[B200_MAX_SCAN_AXIS];
+  __shared__ EnvTables T;
   if (threadIdx.x < B200_MAX_SCAN_AXIS) {
     scan_x[threadIdx.x] = P.scan_x[threadIdx.x];
     scan_y[threadIdx.x] = P.scan_y[threadIdx.x];
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + B200_MAX_PROPRIO) env_tables_fill(P, T, threadIdx.x - 64);
   __syncthreads();
   if (step_dev) step = *step_dev;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  // optional phase trace (b200_env_set_phase_trace): %globaltimer of warp 0 at the phase boundaries, [cta][8]
+#define B200_TRACE(slot)                                                                          \
+  if (trace && t == 0) {                                                                          \
+    unsigned long long t_;                                                                        \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+    trace[(size_t)blockIdx.x * 8 + (slot)] = t_;                                                  \
+  }
+  B200_TRACE(0)
   const int e0 = blockIdx.x * kEnvsPerCta;
   const int e = e0 + warp;
   const bool live = e < P.num_envs;
-  if (live) env_warp_pre(P, B, scratch[warp], scan_x, scan_y, e, lane, lane + 1);
+  const int n_live = min(kEnvsPerCta, P.num_envs - e0);
+
+  // ---- A
+  if (live) env_warp_pre<FIXED>(P, B, scratch[warp], scan_x, scan_y, e, lane, lane + 1);
+  B200_TRACE(1)
   __syncthreads();
-  if (warp == 0 && lane < kEnvsPerCta && e0 + lane < P.num_envs) env_scalar_stage(P, B, scratch[lane], (uint32_t)(e0 + lane), step);
+
+  // ---- E
+  {
+    constexpr int kBodies = kEnvsPerCta * B200_NUM_BODIES, kDofs = kEnvsPerCta * B200_NUM_DOF;
+    if (t < kBodies) {
+      const int slot = t / B200_NUM_BODIES;
+      if (slot < n_live) env_item_body(P, scratch[slot], t - slot * B200_NUM_BODIES);
+    } else if (t < kBodies + kDofs) {
+      const int slot = (t - kBodies) / B200_NUM_DOF;
+      if (slot < n_live) env_item_dof(P, T, scratch[slot], (t - kBodies) - slot * B200_NUM_DOF);
+    } else if (t - (kBodies + kDofs) < n_live) {
+      env_item_flags(P, scratch[t - (kBodies + kDofs)]);
+    }
+    const int slot4 = lane >> 2;
+    if (warp == 0) {
+      if (slot4 < n_live) env_item_leg(P, scratch[slot4], lane & 3);
+    } else if (warp == 1) {
+      if (slot4 < n_live) env_item_angle(P, scratch[slot4], lane & 3, (uint32_t)(e0 + slot4), (uint32_t)step);
+    } else if (warp == 2) {
+      if (lane < n_live) env_item_velocities(scratch[lane]);
+    } else if (warp == 3) {
+      if (lane < n_live) env_item_feet_push(P, scratch[lane], (uint32_t)(e0 + lane), step);
+    }
+  }
+  B200_TRACE(2)
   __syncthreads();
-  if (live) env_warp_post(P, B, scratch[warp], e, step, lane, lane + 1);
+
+  // ---- B1 / B2
+  const int hn4 = (FIXED ? B200_GO2_HISTORY : P.history_len) * (B200_PROPRIO / 4);
+  const int total = kEnvsPerCta * hn4;
+  const int ht = t - 32;
+  if (lane < n_live) env_terms_part<FIXED>(P, scratch[lane], warp);
+  if (live && scratch[warp].early_reset && lane < B200_RESET_BLOCKS)       // rare: the 7 Philox blocks of a reset, in parallel
+    env_reset_draw(P, scratch[warp].reset_draws, (uint32_t)e, (uint32_t)step, lane);
+  for (int base = 0; base < total; base += kHistThreads * kHistPerThread) {      // one trip for the go2 layout
+    f4_ v[kHistPerThread];
+    if (warp > 0) {
+#pragma unroll
+      for (int j = 0; j < kHistPerThread; ++j) {
+        const int k = base + ht + j * kHistThreads;
+        const int slot = k / hn4, i = k - slot * hn4;
+        if (k < total && slot < n_live) v[j] = env_hist_load<FIXED>(P, B, e0 + slot, i);
+      }
+    }
+    if (base == 0) { B200_TRACE(3) }
+    __syncthreads();                                   // terms complete; every load of the rows before any store
+    if (warp == 0) {
+      if (base == 0 && lane < n_live) env_finalize(P, B, scratch[lane]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kHistPerThread; ++j) {
+        const int k = base + ht + j * kHistThreads;
+        const int slot = k / hn4, i = k - slot * hn4;
+        if (k < total && slot < n_live)
+          env_hist_store<FIXED>(P, B, e0 + slot, i, v[j], scratch[slot].early_reset, scratch[slot].early_refill);
+      }
+    }
+  }
+  B200_TRACE(4)
+  __syncthreads();
+
+  // ---- C
+  if (live) env_warp_post<FIXED>(P, B, T, scratch[warp], e, step, lane, lane + 1);
+  B200_TRACE(5)
+#undef B200_TRACE
 }
 
 __global__ void __launch_bounds__(256)
@@ -74,7 +165,7 @@ heights_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ 
   if (P.has_height_samples) {
     float root[7];
     for (int i = 0; i < 7; ++i) root[i] = B.root_states[(int64_t)e * 13 + i];
-    height_cell(P, P.scan_x, P.scan_y, yaw_quat(root + 3), root, j, &px, &py);
+    height_cell(P, P.scan_ny, P.scan_x, P.scan_y, yaw_quat(root + 3), root, j, &px, &py);
     h = height_at(P, B.height_samples, px, py);
   }
   B.measured_heights[idx] = h;
@@ -152,6 +243,7 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   B200_CHECK_ARG(p->num_proprio == B200_PROPRIO, "b200_env_create: num_proprio %d unsupported (go2 layout is %d)", p->num_proprio, B200_PROPRIO);
   B200_CHECK_ARG(p->history_len > 0 && p->history_len * p->num_proprio <= B200_MAX_HIST, "b200_env_create: history too long");
   B200_CHECK_ARG(p->num_scan == p->scan_nx * p->scan_ny && p->num_scan <= B200_MAX_SCAN, "b200_env_create: bad scan grid");
+  B200_CHECK_ARG(p->num_scan % 4 == 0, "b200_env_create: num_scan must be a multiple of 4 (rows move as 16-byte vectors)");
   B200_CHECK_ARG(p->num_priv == 29 && p->num_est == 3, "b200_env_create: privileged/estimated layout must be 29/3");
   B200_CHECK_ARG(p->n_penalised <= B200_NUM_BODIES && p->n_termination <= B200_NUM_BODIES, "b200_env_create: body tables");
   B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2 && (int64_t)p->hs_rows * p->hs_cols < (1ll << 31)),
@@ -167,6 +259,8 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   B200Env* env = new B200Env;
   env->p = *p;
   env->device = device;
+  env->force_generic_layout = 0;
+  env->phase_trace = nullptr;
   *out = env;
   return 0;
 }
@@ -176,17 +270,42 @@ int b200_env_destroy(B200Env* env) {
   return 0;
 }
 
+int b200_env_set_phase_trace(B200Env* env, unsigned long long* trace) {
+  B200_CHECK_ARG(env, "b200_env_set_phase_trace: null handle");
+  env->phase_trace = trace;
+  return 0;
+}
+
+int b200_env_force_generic_layout(B200Env* env, int on) {
+  B200_CHECK_ARG(env, "b200_env_force_generic_layout: null handle");
+  env->force_generic_layout = on ? 1 : 0;
+  return 0;
+}
+
 static int post_physics_attr() {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEnvsPerCta * sizeof(EnvScratch)));
-    if (e != cudaSuccess) {
-      b200_set_error("post_physics_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
+    for (int fixed = 0; fixed < 2; ++fixed) {
+      cudaError_t e = cudaFuncSetAttribute(fixed ? post_physics_kernel<true> : post_physics_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEnvsPerCta * sizeof(EnvScratch)));
+      if (e != cudaSuccess) {
+        b200_set_error("post_physics_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
     }
     done = true;
   }
   return 0;
+}
+
+// the go2 layout (history 10, scan 12 x 11) runs the variant with the layout baked in
+static void launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st) {
+  const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
+  const size_t smem = kEnvsPerCta * sizeof(EnvScratch);
+  if (env_layout_is_go2(env->p) && !env->force_generic_layout)
+    post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace);
+  else
+    post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace);
 }
 
 static int check_bufs(const B200Env* env, const B200EnvBuffers* b, const char* who) {
@@ -219,8 +338,7 @@ int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actio
 int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, void* stream) {
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step")) return rc;
   if (int rc = post_physics_attr()) return rc;
-  const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
-  post_physics_kernel<<<ctas, kEnvsPerCta * 32, kEnvsPerCta * sizeof(EnvScratch), (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter, nullptr);
+  launch_post_physics(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream);
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");
@@ -243,8 +361,7 @@ int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t
   B200_CHECK_ARG(step_counter_dev, "b200_post_physics_step_dev: null counter");
   counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev, 1);       // go2.py:355
   if (int rc = post_physics_attr()) return rc;
-  const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
-  post_physics_kernel<<<ctas, kEnvsPerCta * 32, kEnvsPerCta * sizeof(EnvScratch), (cudaStream_t)stream>>>(env->p, *bufs, 0, step_counter_dev);
+  launch_post_physics(env, bufs, 0, step_counter_dev, (cudaStream_t)stream);
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");

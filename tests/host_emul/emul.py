@@ -26,5 +26,6 @@ def load():
     assert lib.emul_buffers_size() == C.sizeof(EnvBuffers), (lib.emul_buffers_size(), C.sizeof(EnvBuffers))
     lib.emul_pd_torques.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_void_p, C.c_int]
     lib.emul_post_physics_step.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64]
+    lib.emul_post_physics_step_variant.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64, C.c_int]
     lib.emul_reset_all.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64, C.c_int]
     return lib

@@ -40,16 +40,43 @@ static void extras(const B200EnvParams& P, const B200EnvBuffers& B) {
   for (int e = 0; e < N; ++e) B.extras_time_outs[e] = B.time_out_buf[e];
 }
 
-int emul_post_physics_step(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step) {
+}  // extern "C"
+
+// one env step, stage by stage, in the order the CUDA kernel's barriers allow: the history rows move between the
+// element stage and the write-back (all loads of a row before its first store, like the kernel's named barrier)
+template <bool FIXED>
+static void step_all(const B200EnvParams& P, const B200EnvBuffers& B, int64_t step) {
   static EnvScratch S;
-  for (int e = 0; e < p->num_envs; ++e) {
+  static f4_ row[B200_MAX_HIST / 4];
+  static EnvTables T;
+  for (int i = 0; i < B200_MAX_PROPRIO; ++i) env_tables_fill(P, T, i);
+  const int hn4 = P.history_len * (B200_PROPRIO / 4);
+  for (int e = 0; e < P.num_envs; ++e) {
     memset(&S, 0xCD, sizeof(S));   // poison: a stage that reads what no stage wrote shows up as garbage
-    env_warp_pre(*p, *b, S, p->scan_x, p->scan_y, e, 0, 32);
-    env_scalar_stage(*p, *b, S, (uint32_t)e, step);
-    env_warp_post(*p, *b, S, e, step, 0, 32);
+    env_warp_pre<FIXED>(P, B, S, P.scan_x, P.scan_y, e, 0, 32);
+    for (int it = ITEM_COUNT - 1; it >= 0; --it) env_item(P, T, S, it, (uint32_t)e, step);   // order-free (here: reversed)
+    for (int i = 0; i < hn4; ++i) row[i] = env_hist_load<FIXED>(P, B, e, i);
+    for (int i = 0; i < hn4; ++i) env_hist_store<FIXED>(P, B, e, i, row[i], S.early_reset, S.early_refill);
+    for (int part = B200_TERM_PARTS - 1; part >= 0; --part) env_terms_part<FIXED>(P, S, part);
+    if (S.early_reset)
+      for (int b = 0; b < B200_RESET_BLOCKS; ++b) env_reset_draw(P, S.reset_draws, (uint32_t)e, (uint32_t)step, b);
+    env_finalize(P, B, S);
+    env_warp_post<FIXED>(P, B, T, S, e, step, 0, 32);
   }
+}
+
+extern "C" {
+
+// variant: 0 = pick like the library does (layout baked in for the go2 layout), 1 = force the layout-generic code
+int emul_post_physics_step_variant(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step, int force_generic) {
+  if (env_layout_is_go2(*p) && !force_generic) step_all<true>(*p, *b, step);
+  else step_all<false>(*p, *b, step);
   extras(*p, *b);
   return 0;
+}
+
+int emul_post_physics_step(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step) {
+  return emul_post_physics_step_variant(p, b, step, 0);
 }
 
 int emul_reset_all(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step, int init_done) {

@@ -17,8 +17,9 @@ def lib():
     return emul.load()
 
 
+@pytest.mark.parametrize("force_generic", [0, 1], ids=["go2-layout-baked-in", "layout-generic"])
 @pytest.mark.parametrize("task", gu.TASKS)
-def test_kernel_source_matches_reference(lib, task):
+def test_kernel_source_matches_reference(lib, task, force_generic):
     g = gu.load(task)
     p = gu.params_for(task, g)
     bufs = BufferSet(p, "cpu", record_height_index=True)
@@ -37,7 +38,7 @@ def test_kernel_source_matches_reference(lib, task):
         bufs["contact_forces"].copy_(torch.from_numpy(fr["contact"]))
         bufs["rigid_body_states"].copy_(torch.from_numpy(fr["rigid"]))
         step += 1
-        lib.emul_post_physics_step(C.byref(p), C.byref(bufs.struct), step)
+        lib.emul_post_physics_step_variant(C.byref(p), C.byref(bufs.struct), step, force_generic)
         gu.check_step(bufs, gu.expected(g, t), t, report=report)
     hist = bufs["obs_history_buf"].numpy()
     assert gu.rel_err(hist, g["final/obs_history_buf"]) <= gu.RTOL
