@@ -167,34 +167,47 @@ B200_HD YawQuat yaw_quat(const float* q) {
   r.w = q[3] / n;
   return r;
 }
-// point j of the x-major scan grid: ix = j / ny without an integer division ((2j+1)/(2ny) is never within 1/(2ny) of an
-// integer, so the fp32 product truncates to the exact quotient for every j < 192, ny <= 24)
-B200_HD void height_cell(const B200EnvParams& P, int ny, const float* scan_x, const float* scan_y, YawQuat yq, const float* root_pos, int j,
-                         int* px, int* py) {
-  const int gx = (int)((float)(2 * j + 1) * (0.5f / (float)ny));
-  const float vx = scan_x[gx], vy = scan_y[j - gx * ny];
+// x / h for the height-field index, correctly rounded without the division: with y = RN(1/h), two Newton steps on the
+// quotient (q += RN(x - q h) y, FMA residuals) give RN(x / h) -- the sequence div.rn itself runs, minus its reciprocal
+// refinement and special-case branch, which are hoisted because h is a constant of the terrain.  Verified bit for bit
+// against x / h for EVERY fp32 x with 2^-31 <= |x| < 2^24 and h in {0.05, 0.07, 0.1, 0.125, 0.2, 0.25, 0.3, 1/3}
+// (tests/test_div_const.py).  The caller clamps x into that range first.
+B200_HD float div_by_const(float x, float h, float y) {
+  float q = x * y;
+  float r = B200_FMA(-q, h, x);
+  q = B200_FMA(r, y, q);
+  r = B200_FMA(-q, h, x);
+  return B200_FMA(r, y, q);
+}
+// torch: idx = clip((x / h).long(), 0, n - 2).  The numerator is clamped to [-2h, (n + 1) h] first: inside that window
+// nothing changes, outside it the quotient stays on the same side of the final clip (division is monotonic), a NaN lands
+// on cell 0 like (int)NaN does, and the float -> int conversion can no longer overflow.  n * h < 2^24 is checked at
+// env creation, so div_by_const is exact on the clamped value.
+B200_HD int height_index(const B200EnvParams& P, float x, int n, float inv_h) {
+  const float h = P.horizontal_scale;
+  const float lo = -2.0f * h, hi = (float)(n + 1) * h;
+  x = fminf(fmaxf(x, lo), hi);
+  const float q = P.index_div_mode == 0 ? div_by_const(x, h, inv_h) : x * inv_h;
+  const int i = (int)q;                                  // .long() truncates toward zero
+  return i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+}
+// scan point (vx, vy) of the x-major grid -> height-field cell
+B200_HD void height_cell_pt(const B200EnvParams& P, float vx, float vy, YawQuat yq, const float* root_pos, float inv_h, int* px, int* py) {
   // quat_apply((0,0,z,w), (vx,vy,0)): t = cross * 2; b + w*t + cross(xyz, t)
   const float t0 = -(yq.z * vy) * 2.0f, t1 = (yq.z * vx) * 2.0f;
   float rx = (vx + yq.w * t0) + (-(yq.z * t1));
   float ry = (vy + yq.w * t1) + (yq.z * t0);
   rx = (rx + root_pos[0]) + P.border_size;
   ry = (ry + root_pos[1]) + P.border_size;
-  if (P.index_div_mode == 0) {
-    rx = rx / P.horizontal_scale;
-    ry = ry / P.horizontal_scale;
-  } else {
-    const float inv = 1.0f / P.horizontal_scale;
-    rx = rx * inv;
-    ry = ry * inv;
-  }
-  // .long() truncates toward zero; clamp first so the 32-bit conversion cannot overflow (the clip to [0, n-2] that
-  // follows makes the result identical to the int64 path for every finite input)
-  const float hx = (float)(P.hs_rows - 1), hy = (float)(P.hs_cols - 1);
-  int ix = (int)(rx < -1.0f ? -1.0f : (rx > hx ? hx : rx)), iy = (int)(ry < -1.0f ? -1.0f : (ry > hy ? hy : ry));
-  ix = ix < 0 ? 0 : (ix > P.hs_rows - 2 ? P.hs_rows - 2 : ix);
-  iy = iy < 0 ? 0 : (iy > P.hs_cols - 2 ? P.hs_cols - 2 : iy);
-  *px = ix;
-  *py = iy;
+  *px = height_index(P, rx, P.hs_rows, inv_h);
+  *py = height_index(P, ry, P.hs_cols, inv_h);
+}
+// point j of the x-major scan grid: ix = j / ny without an integer division ((2j+1)/(2ny) is never within 1/(2ny) of an
+// integer, so the fp32 product truncates to the exact quotient for every j < 192, ny <= 24)
+B200_HD void scan_point(const B200EnvParams& P, int j, float* vx, float* vy) {
+  const int gx = (int)((float)(2 * j + 1) * (0.5f / (float)P.scan_ny));
+  *vx = P.scan_x[gx];
+  *vy = P.scan_y[j - gx * P.scan_ny];
 }
 B200_HD float height_at(const B200EnvParams& P, const int16_t* hs, int px, int py) {
   const int16_t* p = hs + (px * P.hs_cols + py);        // rows * cols < 2^31 (checked at env creation)
@@ -739,7 +752,7 @@ B200_HD f4_ clamp4(f4_ v, float c) {
 // The CUDA kernel (env_kernels.cu) maps these onto a CTA of 8 envs so that every phase fills its warps.
 // FIXED = true bakes the go2 layout (history 10, scan 12 x 11) into the code: trip counts and row offsets
 // become literals, loops unroll, loads batch.  FIXED = false reads them from P (any other layout).
-// scan_x / scan_y: the scan-point tables (shared-memory copies on the GPU, P.scan_x / P.scan_y on the host)
+// pt_x / pt_y: the num_scan scan points (scan_point), shared-memory tables on the GPU
 #define B200_ENV_DIMS                                                                 \
   constexpr int NP = B200_PROPRIO, NP4 = NP / 4;                                      \
   const int H = FIXED ? B200_GO2_HISTORY : P.history_len;                             \
@@ -759,7 +772,7 @@ B200_HD bool env_layout_is_go2(const B200EnvParams& P) {
 }
 
 template <bool FIXED>
-B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* scan_x, const float* scan_y,
+B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* pt_x, const float* pt_y,
                           int e, int lane_lo, int lane_hi) {
   B200_ENV_DIMS;
 
@@ -838,6 +851,7 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
     int n_out = 0;
     if (P.has_height_samples) {
       const YawQuat yq = yaw_quat(S.root + 3);
+      const float inv_h = 1.0f / P.horizontal_scale;
       constexpr int kMaxPerLane = (B200_MAX_SCAN + 31) / 32;
       const int per_lane = FIXED ? (B200_GO2_SCAN_NX * B200_GO2_SCAN_NY + 31) / 32 : kMaxPerLane;
       int px[kMaxPerLane], py[kMaxPerLane];
@@ -845,7 +859,8 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
 #pragma unroll
       for (int k = 0; k < per_lane; ++k) {
         const int j = lane + 32 * k;
-        height_cell(P, NY, scan_x, scan_y, yq, S.root, j < NS ? j : NS - 1, &px[k], &py[k]);
+        const int jc = j < NS ? j : NS - 1;
+        height_cell_pt(P, pt_x[jc], pt_y[jc], yq, S.root, inv_h, &px[k], &py[k]);
       }
 #pragma unroll
       for (int k = 0; k < per_lane; ++k) {

@@ -46,12 +46,9 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
                     const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EnvScratch* scratch = reinterpret_cast<EnvScratch*>(smem_raw);
-  __shared__ float scan_x[B200_MAX_SCAN_AXIS], scan_y[B200_MAX_SCAN_AXIS];
+  __shared__ float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
   __shared__ EnvTables T;
-  if (threadIdx.x < B200_MAX_SCAN_AXIS) {
-    scan_x[threadIdx.x] = P.scan_x[threadIdx.x];
-    scan_y[threadIdx.x] = P.scan_y[threadIdx.x];
-  }
+  if (threadIdx.x < P.num_scan) scan_point(P, threadIdx.x, &pt_x[threadIdx.x], &pt_y[threadIdx.x]);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + B200_MAX_PROPRIO) env_tables_fill(P, T, threadIdx.x - 64);
   __syncthreads();
   if (step_dev) step = *step_dev;
@@ -70,7 +67,7 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
   const int n_live = min(kEnvsPerCta, P.num_envs - e0);
 
   // ---- A
-  if (live) env_warp_pre<FIXED>(P, B, scratch[warp], scan_x, scan_y, e, lane, lane + 1);
+  if (live) env_warp_pre<FIXED>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1);
   B200_TRACE(1)
   __syncthreads();
 
@@ -165,7 +162,9 @@ heights_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ 
   if (P.has_height_samples) {
     float root[7];
     for (int i = 0; i < 7; ++i) root[i] = B.root_states[(int64_t)e * 13 + i];
-    height_cell(P, P.scan_ny, P.scan_x, P.scan_y, yaw_quat(root + 3), root, j, &px, &py);
+    float vx, vy;
+    scan_point(P, j, &vx, &vy);
+    height_cell_pt(P, vx, vy, yaw_quat(root + 3), root, 1.0f / P.horizontal_scale, &px, &py);
     h = height_at(P, B.height_samples, px, py);
   }
   B.measured_heights[idx] = h;
@@ -200,13 +199,33 @@ extras_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B
   const int k = blockIdx.x, T = B200_NUM_REWARD_TERMS, N = P.num_envs;
   int cnt = 0;
   float acc = 0.0f;
-  for (int e = threadIdx.x; e < N; e += 256) {
-    const int r = B.reset_buf[e] != 0;
-    cnt += r;
-    if (k < T) {
-      if (r) acc += B.reset_episode_sums[(int64_t)e * T + k];
+  // thread t owns envs [16 t, 16 t + 16) of every 4096-env chunk: the 16 reset flags arrive as one 16-byte load and only
+  // the (rare) flagged envs touch reset_episode_sums; fixed order, so the means are deterministic
+  for (int e0 = threadIdx.x * 16; e0 < N; e0 += 256 * 16) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (e0 + 16 <= N && (((uintptr_t)B.reset_buf) & 15) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4*>(B.reset_buf + e0);
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     } else {
-      acc += (float)B.terrain_levels[e];
+      for (int i = 0; i < 16 && e0 + i < N; ++i) w[i >> 2] |= (uint32_t)(B.reset_buf[e0 + i] != 0) << (8 * (i & 3));
+    }
+    if (k < T) {
+      if (w[0] | w[1] | w[2] | w[3]) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) {
+            ++cnt;
+            acc += B.reset_episode_sums[(int64_t)(e0 + i) * T + k];
+          }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (e0 + i < N) {
+          cnt += ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0;
+          acc += (float)B.terrain_levels[e0 + i];
+        }
+      }
     }
   }
   const int count = cta_sum_256<int>(cnt, ism);
@@ -248,6 +267,8 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   B200_CHECK_ARG(p->n_penalised <= B200_NUM_BODIES && p->n_termination <= B200_NUM_BODIES, "b200_env_create: body tables");
   B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2 && (int64_t)p->hs_rows * p->hs_cols < (1ll << 31)),
                  "b200_env_create: height_samples shape");
+  B200_CHECK_ARG(!p->has_height_samples || (p->horizontal_scale > 0.0f && (float)(p->hs_rows + p->hs_cols) * p->horizontal_scale < 8388608.0f),
+                 "b200_env_create: height field extent must stay below 2^23 m");
   B200_CHECK_ARG(p->resample_interval > 0 && p->push_interval > 0, "b200_env_create: intervals must be > 0");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);

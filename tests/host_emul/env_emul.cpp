@@ -49,11 +49,13 @@ static void step_all(const B200EnvParams& P, const B200EnvBuffers& B, int64_t st
   static EnvScratch S;
   static f4_ row[B200_MAX_HIST / 4];
   static EnvTables T;
+  static float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
+  for (int j = 0; j < P.num_scan; ++j) scan_point(P, j, &pt_x[j], &pt_y[j]);
   for (int i = 0; i < B200_MAX_PROPRIO; ++i) env_tables_fill(P, T, i);
   const int hn4 = P.history_len * (B200_PROPRIO / 4);
   for (int e = 0; e < P.num_envs; ++e) {
     memset(&S, 0xCD, sizeof(S));   // poison: a stage that reads what no stage wrote shows up as garbage
-    env_warp_pre<FIXED>(P, B, S, P.scan_x, P.scan_y, e, 0, 32);
+    env_warp_pre<FIXED>(P, B, S, pt_x, pt_y, e, 0, 32);
     for (int it = ITEM_COUNT - 1; it >= 0; --it) env_item(P, T, S, it, (uint32_t)e, step);   // order-free (here: reversed)
     for (int i = 0; i < hn4; ++i) row[i] = env_hist_load<FIXED>(P, B, e, i);
     for (int i = 0; i < hn4; ++i) env_hist_store<FIXED>(P, B, e, i, row[i], S.early_reset, S.early_refill);
