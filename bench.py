@@ -27,6 +27,15 @@ ENV_BYTES_PER_ENV = 12618        # post-physics algorithmic bytes per env-step (
 PD_BYTES_PER_ENV = 288           # one PD-torque pass
 
 
+def _load_traffic():
+    """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full captures under profiles/"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+TRAFFIC = _load_traffic()
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -66,14 +75,16 @@ class Profile:
     """per-ABI-call CUDA-event timing + algorithmic work, installed as the library hook for ONE extra iteration."""
 
     def __init__(self, num_envs):
-        self.n, self.recs, self.count = num_envs, [], 0
+        self.n, self.recs, self.count, self.by_entry = num_envs, [], 0, {}
         self.timing = False
 
     def hook(self, name, raw, args):
         from legged_gym_custom_b200 import _lib
-        if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version"):
+        if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version",
+                    "b200_tc_set_pair_mode", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_tc_linear_supported"):
             return raw(*args)
         self.count += _lib.LAUNCHES.get(name, 1)
+        self.by_entry[name] = self.by_entry.get(name, 0) + _lib.LAUNCHES.get(name, 1)
         if not self.timing:
             return raw(*args)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,18 +92,22 @@ class Profile:
         rc = raw(*args)
         e1.record()
         flops = bytes_ = 0
+        shape = None
         if name in ("b200_linear_forward", "b200_tc_linear_forward"):
-            flops = 2.0 * args[7] * args[8] * args[9]
-        elif name in ("b200_linear_dgrad", "b200_tc_linear_dgrad"):
-            flops = 2.0 * args[8] * args[9] * args[10]
+            shape = (args[7], args[8], args[9])
+        elif name in ("b200_linear_dgrad", "b200_tc_linear_dgrad", "b200_tc_linear_dgrad_bias"):
+            shape = (args[8], args[9], args[10])
         elif name == "b200_linear_wgrad":
-            flops = 2.0 * args[7] * args[8] * args[9]
+            shape = (args[7], args[8], args[9])
         elif name == "b200_tc_linear_wgrad":
-            flops = 2.0 * args[6] * args[7] * args[8]
-        elif name == "b200_post_physics_step":
+            shape = (args[6], args[7], args[8])
+        elif name in ("b200_post_physics_step", "b200_post_physics_step_dev"):
             bytes_ = ENV_BYTES_PER_ENV * self.n
         elif name == "b200_pd_torques":
             bytes_ = PD_BYTES_PER_ENV * self.n
+        if shape is not None:
+            flops = 2.0 * shape[0] * shape[1] * shape[2]
+            name = f"{name}[M={shape[0]},N={shape[1]},K={shape[2]}]"       # one row per kernel PROBLEM, not per entry point
         self.recs.append((name, e0, e1, flops, bytes_))
         return rc
 
@@ -159,6 +174,8 @@ def run_b200(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
     from legged_gym_custom_b200 import _lib
+    if args.no_pairs:
+        _lib.lib().b200_tc_set_pair_mode(0)
     prof = Profile(args.num_envs)
     _lib.lib().hook = prof.hook
     env, runner = build_runner(args, rank, world, device)
@@ -193,13 +210,16 @@ def run_b200(args):
 
     # ---- per-kernel timing of ONE more iteration, launched eagerly (no graph replay) with CUDA events around every
     #      ABI call on the launching stream; also counts the kernels one iteration launches
+    #      (side streams off for this one iteration: concurrent kernels would inflate each other's event intervals)
     graphs = getattr(runner, "use_graphs", False)
     runner.use_graphs = runner.alg.use_graphs = False
+    streams, runner.alg.use_streams = runner.alg.use_streams, False
     prof.count = 0
     prof.timing = True
     runner.iteration(W + K)
     table = prof.table()
     prof.timing = False
+    runner.alg.use_streams = streams
     launches = prof.count * K          # the timed iterations replay exactly these launches (as CUDA graphs when enabled)
     runner.use_graphs = runner.alg.use_graphs = graphs
     peaks = measured_peaks()
@@ -212,10 +232,48 @@ def run_b200(args):
         roof = {"kernel": name, "bound": "hbm", "achieved": by / tsec / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": by / tsec / 1e9 / peaks["hbm"], "traffic": None, "launches": n, "avg_us": tsec / n * 1e6}
     roof["peak_source"] = peaks["source"]
+    roof["traffic"] = TRAFFIC.get(name.split("[")[0] + ("[" + name.split("[")[1] if "[" in name else ""))
+    if roof["bound"] == "tensor":      # the GEMMs run kind::tf32 (the reference's matmul precision); dense TF32 peak = bf16 / 2
+        roof["tf32_peak_equiv"] = peaks["tensor"] / 2
+        roof["frac_of_tf32_peak"] = roof["achieved"] / (peaks["tensor"] / 2)
     total_prof = sum(v[0] for v in table.values())
     breakdown = {k: {"ms": round(v[0] * 1e3, 3), "calls": v[1], "share": round(v[0] / total_prof, 4),
                      **({"tflops": round(v[2] / v[0] / 1e12, 2)} if v[2] else {}), **({"gbs": round(v[3] / v[0] / 1e9, 1)} if v[3] else {})}
                  for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])}
+
+    # ---- the env kernel alone (north_star: env kernels against the HBM roofline): post_physics_kernel launched by itself,
+    #      CUDA events on the launching stream around each launch; once with L2 flushed before every launch (a 512 MB
+    #      write) and once back to back (its 75 MB working set then stays L2-resident, as it does inside the rollout)
+    roof_env = None
+    if world == 1:
+        import ctypes as C
+        lib, h, bs = _lib.lib(), env._handle, env.bufs.struct
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+        step0 = int(env.common_step_counter) + 1000
+
+        def time_env(do_flush, reps=30):
+            ts = []
+            for i in range(reps + 5):
+                if do_flush:
+                    flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _lib.check(lib.b200_post_physics_step_parts(h, C.byref(bs), step0 + i, 1, _lib.stream_ptr()))
+                b.record()
+                b.synchronize()
+                if i >= 5:
+                    ts.append(a.elapsed_time(b) * 1e-3)
+            return float(np.mean(ts))
+        prof_hook, _lib.lib().hook = _lib.lib().hook, None
+        t_cold, t_warm = time_env(True), time_env(False)
+        _lib.lib().hook = prof_hook
+        by = ENV_BYTES_PER_ENV * N
+        roof_env = {"kernel": "post_physics_kernel", "bound": "hbm", "achieved": by / t_cold / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": by / t_cold / 1e9 / peaks["hbm"], "traffic": TRAFFIC.get("post_physics_kernel"), "avg_us": t_cold * 1e6,
+                    "l2": "flushed before every launch", "peak_source": peaks["source"],
+                    "l2_resident": {"avg_us": t_warm * 1e6, "achieved": by / t_warm / 1e9, "frac": by / t_warm / 1e9 / peaks["hbm"]},
+                    "algorithmic_bytes_per_env": ENV_BYTES_PER_ENV}
+        del flush
 
     # ---- end to end: PhysX frames in pinned host memory copied in every substep, results read back every step
     e2e = None
@@ -238,7 +296,9 @@ def run_b200(args):
         t2 = timed_iterations(runner2, 3, args.e2e_steps, world)
         e2e = {"value": T_STEPS * N * world * args.e2e_steps / t2, "unit": "env-steps/s",
                "h2d_bytes_per_step": env2.physx.bytes_per_step * T_STEPS, "d2h_bytes_per_step": T_STEPS * N * 5 + 5 * 4,
-               "ms_per_step": t2 / args.e2e_steps * 1e3}
+               "ms_per_step": t2 / args.e2e_steps * 1e3,
+               "h2d": "dof_state x4, root_states, contact_forces copied from pinned host memory every env step; rigid_body_states "
+                      "(4 of 247 floats per env are read) is read in place from the pinned buffer (zero-copy, counted at 32 B per read)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -255,7 +315,7 @@ def run_b200(args):
                            "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
                            "timed_iterations": f"it {W}..{W + K - 1} (PPO updates; the DAgger iteration it=0 is in the warm-up)",
                            "launch": "CUDA graphs (rollout+GAE: 1 graph; update: 1 graph per minibatch slot)" if not args.no_graphs else "eager"},
-                "e2e": e2e, "split": split, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "e2e": e2e, "split": split, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "roofline_env": roof_env, "cpu_baseline": cpu,
                 "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -369,6 +429,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
+    ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -260,6 +260,9 @@ int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actio
  * `common_step_counter` is the value AFTER this step's increment (go2.py:355). */
 int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter,
                            void* stream);
+/* The same step split into its two kernels, for measurement: `parts` bit 0 = post_physics_kernel (everything per env),
+ * bit 1 = extras_kernel (episode means / time_outs over the envs that reset).  parts = 3 is b200_post_physics_step. */
+int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, int parts, void* stream);
 
 /* Same, with `common_step_counter` kept in DEVICE memory: the call increments *step_counter_dev and then uses
  * it, so a captured CUDA graph of the rollout replays with advancing step numbers. */
@@ -308,11 +311,18 @@ int b200_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float*
 
 /* ---- learner: the same three GEMMs on the tcgen05 / TMEM / TMA path (csrc/mlp_tcgen05.cu, kind::tf32) ----------
  * Same argument meaning as b200_linear_*; bias gradients stay with b200_linear_wgrad / the caller. */
+/* Large forward / dgrad problems run on CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA stages half of B);
+ * `on` = 0 forces the single-CTA kernels everywhere (A/B measurements and tests).  Returns 0. */
+int b200_tc_set_pair_mode(int on);
 int b200_tc_linear_supported(int M, int N, int K);
 int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
                            int M, int N, int K, int act, void* stream);
 int b200_tc_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX,
                          int lddx, int M, int N, int K, int accumulate, void* stream);
+/* Same, and additionally dbias_prev[K] += column sums of dX: dX is d(loss)/d(pre-activation) of the layer below, so its
+ * column sum is that layer's bias gradient (replaces a separate b200_colsum pass over dX).  Needs accumulate = 0. */
+int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX, int lddx,
+                              int M, int N, int K, int accumulate, float* dbias_prev, void* stream);
 int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int ldw, int M, int N, int K,
                          void* stream);
 

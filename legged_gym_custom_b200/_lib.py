@@ -19,6 +19,7 @@ SYMBOLS = {
     "b200_env_set_phase_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_pd_torques": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_int, C.c_void_p]),
     "b200_post_physics_step": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_void_p]),
+    "b200_post_physics_step_parts": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_int, C.c_void_p]),
     "b200_post_physics_step_dev": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_void_p]),
     "b200_counter_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "b200_reset_all": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_int, C.c_void_p]),
@@ -29,9 +30,11 @@ SYMBOLS = {
     "b200_linear_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 5 + [C.c_void_p]),
     "b200_linear_dgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 5 + [C.c_void_p]),
     "b200_linear_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "b200_tc_set_pair_mode": (C.c_int, [C.c_int]),
     "b200_tc_linear_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "b200_tc_linear_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 4 + [C.c_void_p]),
     "b200_tc_linear_dgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 4 + [C.c_void_p]),
+    "b200_tc_linear_dgrad_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "b200_tc_linear_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_int] * 3 + [C.c_void_p]),
     "b200_copy_segments": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),

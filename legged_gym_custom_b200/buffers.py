@@ -69,6 +69,14 @@ class BufferSet:
         self.t[name] = tensor
         setattr(self.struct, name, C.c_void_p(tensor.data_ptr()))
 
+    def rebind_host_mapped(self, name, tensor):
+        """Point a READ-ONLY PhysX-owned slot at a pinned host tensor: under unified addressing the kernels read it in
+        place over PCIe / NVLink-C2C (zero-copy).  Worth it only for sparsely read tensors (rigid_body_states: 4 of 247
+        floats per env are read)."""
+        old = self.t[name]
+        assert tensor.shape == old.shape and tensor.dtype == old.dtype and tensor.is_pinned() and tensor.is_contiguous()
+        setattr(self.struct, name, C.c_void_p(tensor.data_ptr()))
+
     def __getitem__(self, name):
         return self.t[name]
 

@@ -356,14 +356,22 @@ int b200_pd_torques(B200Env* env, const B200EnvBuffers* bufs, const float* actio
   return 0;
 }
 
-int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, void* stream) {
+int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, int parts, void* stream) {
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step")) return rc;
   if (int rc = post_physics_attr()) return rc;
-  launch_post_physics(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream);
-  B200_CHECK_LAUNCH("post_physics_kernel");
-  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
-  B200_CHECK_LAUNCH("extras_kernel");
+  if (parts & 1) {
+    launch_post_physics(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream);
+    B200_CHECK_LAUNCH("post_physics_kernel");
+  }
+  if (parts & 2) {
+    extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+    B200_CHECK_LAUNCH("extras_kernel");
+  }
   return 0;
+}
+
+int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, void* stream) {
+  return b200_post_physics_step_parts(env, bufs, common_step_counter, 3, stream);
 }
 
 __global__ void counter_add_kernel(int64_t* c, int64_t delta) {

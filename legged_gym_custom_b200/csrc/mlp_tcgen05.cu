@@ -26,7 +26,6 @@ namespace {
 
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // 32 fp32 = 128 B = one swizzle row
-constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -124,13 +123,59 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster on one TPC run ONE 256-row UMMA; each stages its own 128
+// rows of A and HALF of B, so a 256 x BN tile costs the L2 -> SM path 2/3 of what two 128 x BN tiles do.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // shared::cluster address -> the same offset in the pair's rank-0 CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by both CTAs: data lands in the issuing CTA's smem, the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 enum Mode { NT = 0, NN = 1, TN = 2 };
 
 struct TcArgs {
   float* C;
   const float* bias;   // NT
   const float* aux;    // NN: Yprev for elu'
-  float* dbias;        // TN (unused here: bias gradients are reduced by the baseline kernel's epilogue path)
+  float* dbias;        // NN: dbias[N] += column sums of the OUTPUT (= bias gradient of the layer below), or nullptr
   int ldc, ldaux;
   int M, N, K;         // output rows, output cols, reduction
   int act, accumulate;
@@ -140,13 +185,27 @@ struct TcArgs {
 // A-operand smem per stage: K-major  [BM rows][32]         = 16 KB
 //                           MN-major 4 chunks x [32 k][32]  = 16 KB   (chunk = 32 fp32 of the M dimension)
 // B-operand smem per stage: K-major  [BN rows][32]; MN-major (BN/32) chunks x [32 k][32]      = BN * 128 B
-template <int MODE, int BN>
+template <int BN, bool PAIR>
+struct TileCfg {
+  static constexpr int BNH = PAIR ? BN / 2 : BN;                  // rows of B this CTA stages
+  static constexpr int BMT = PAIR ? 2 * BM : BM;                  // rows of the output tile (pair: 256)
+  static constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BNH * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  // shared-memory budget of the operand ring: what is left of 227 KB after the epilogue's staging tiles (36 KB), the
+  // dgrad's column-sum buffer (<= 8 KB) and the barriers
+  static constexpr int STAGES_ = (int)((176u * 1024u) / STAGE_BYTES) < 8 ? (int)((176u * 1024u) / STAGE_BYTES) : 8;
+};
+
+template <int MODE, int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
+  using Cfg = TileCfg<BN, PAIR>;
   constexpr bool A_MN = (MODE == TN), B_MN = (MODE != NT);
-  constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BNH = Cfg::BNH, BMT = Cfg::BMT, STAGES = Cfg::STAGES_;
+  constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  constexpr uint32_t IDESC = make_idesc(BM, BN, A_MN, B_MN);
+  constexpr uint32_t IDESC = make_idesc(BMT, BN, A_MN, B_MN);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // 0 = leader (issues the MMAs), 1 = peer
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -155,9 +214,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // NN + dbias: [2 tiles][4 quarters][BN]
+  constexpr int STG_PITCH = 36;                                                // floats per staged row (32 + 4 pad)
+  float* stage = red + (MODE == NN ? 2 * 4 * BN : 0);                          // [8 epilogue warps][32 rows][STG_PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+  const int m_tiles = (g.M + BMT - 1) / BMT, n_tiles = (g.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   int k_lo = 0, k_hi = g.K;
   if (MODE == TN) {
@@ -175,13 +237,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
-      mbar_init(tmem_empty + a, 8);      // one arrive per epilogue warp
+      mbar_init(tmem_empty + a, PAIR ? 16 : 8);      // one arrive per epilogue warp (pair: of both CTAs, on the leader)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS);
+    else tmem_alloc(tmem_ptr, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // the peer's barriers must be initialised before anything is signalled on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -189,35 +255,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m0 = (tile / n_tiles) * BMT + (int)rank * BM;             // pair: this CTA's 128 rows of the 256-row tile
+        const int n0 = (tile % n_tiles) * BN + (int)rank * BNH;             // pair: this CTA's half of the B rows
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          if (!PAIR || rank == 0) mbar_expect_tx(full_bar + s, (PAIR ? 2u : 1u) * STAGE_BYTES);   // pair: both CTAs' bytes
           const int k0 = k_lo + kb * BK;
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if (PAIR) tma_load_2d_pair(dst, map, full_bar + s, c0, c1);
+            else tma_load_2d(dst, map, full_bar + s, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tmap_a, full_bar + s, k0, m0);                 // box [BM rows][32 k]
+            load(sa, &tmap_a, k0, m0);                                      // box [BM rows][32 k]
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &tmap_a, full_bar + s, m0 + c * 32, k0);   // box [32 k][32 m]
+            for (int c = 0; c < BM / 32; ++c) load(sa + c * (BK * 128), &tmap_a, m0 + c * 32, k0);   // box [32 k][32 m]
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmap_b, full_bar + s, k0, n0);                 // box [BN rows][32 k]
+            load(sb, &tmap_b, k0, n0);                                      // box [BNH rows][32 k]
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) tma_load_2d(sb + c * (BK * 128), &tmap_b, full_bar + s, n0 + c * 32, k0);   // box [32 k][32 n]
+            for (int c = 0; c < BNH / 32; ++c) load(sb + c * (BK * 128), &tmap_b, n0 + c * 32, k0);   // box [32 k][32 n]
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t it = 0, local_tile = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_tile) {
         const uint32_t acc = local_tile & 1, acc_ph = (local_tile >> 1) & 1;
         mbar_wait(tmem_empty + acc, acc_ph ^ 1);
         tc_fence_after();
@@ -234,37 +305,85 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // LBO between 32-element chunks along MN), a K=8 step is 8 rows = 1024 B.
             const uint64_t da = A_MN ? make_desc(sa + k * 1024, BK * 128, 512, 1) : make_desc(sa + k * 32, 16, 1024, 2);
             const uint64_t db = B_MN ? make_desc(sb + k * 1024, BK * 128, 512, 1) : make_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32(tmem_d, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_tf32_pair(tmem_d, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_tf32(tmem_d, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + s);               // smem stage reusable once these MMAs retire
+          if (PAIR) umma_commit_pair(empty_bar + s);   // smem stage reusable (in both CTAs) once these MMAs retire
+          else umma_commit(empty_bar + s);
         }
-        umma_commit(tmem_full + acc);               // accumulator complete
+        if (PAIR) umma_commit_pair(tmem_full + acc);   // accumulator complete (both CTAs' epilogues)
+        else umma_commit(tmem_full + acc);
       }
     }
   } else {
     // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4; the two warps of a quarter split the columns =====
+    // tcgen05.ld hands every lane one ROW of a 32 x 32 chunk; global memory wants consecutive lanes on consecutive
+    // addresses.  Each warp therefore owns a 32 x 32 staging tile in shared memory (pitch 36 floats: conflict-free for
+    // both the row-per-lane and the 8-lanes-per-row access): rows go in, 128-byte row segments come out, four rows per
+    // instruction.  The dgrad's elu' input travels the other way (coalesced load -> staging -> row per lane).
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
+    float* stg = stage + (warp - 2) * (32 * STG_PITCH);
+    const int sr = lane >> 3, sc = (lane & 7) * 4;            // staging coordinates of this lane in the "8 lanes per row" view
     uint32_t local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_tile) {
       const uint32_t acc = local_tile & 1, acc_ph = (local_tile >> 1) & 1;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * BMT + (int)rank * BM, n0 = (tile % n_tiles) * BN;
+      const int row0 = m0 + quarter * 32;                     // first row of this warp's chunk rows
+      const int row = row0 + lane;
+      const int ci_lo = half * CH_PER_HALF, ci_hi = min(CHUNKS, (half + 1) * CH_PER_HALF);
+      // dgrad: the stored activation of the layer below (for elu') does not depend on the MMAs -- fetch chunk i + 1 while
+      // chunk i is in flight, and the first chunk before the accumulator is even complete
+      float4 ax_next[8];
+      auto load_aux = [&](int ci) {
+        if (MODE != NN || g.aux == nullptr) return;
+        const int col = n0 + ci * 32 + sc;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = row0 + it * 4 + sr;
+          const float* y = g.aux + (int64_t)r * g.ldaux + col;
+          float4 v4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);    // y > 0 -> factor 1
+          if (r < g.M) {
+            if (col + 3 < g.N && (((uintptr_t)y) & 15) == 0) {
+              v4 = *reinterpret_cast<const float4*>(y);
+            } else {
+              if (col < g.N) v4.x = y[0];
+              if (col + 1 < g.N) v4.y = y[1];
+              if (col + 2 < g.N) v4.z = y[2];
+              if (col + 3 < g.N) v4.w = y[3];
+            }
+          }
+          ax_next[it] = v4;
+        }
+      };
+      if (ci_lo < ci_hi) load_aux(ci_lo);
       mbar_wait(tmem_full + acc, acc_ph);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      const bool want_colsum = (MODE == NN) && g.dbias != nullptr;
+      float* red_tile = red + (local_tile & 1) * 4 * BN + quarter * BN;
 #pragma unroll 1
-      for (int ci = half * CH_PER_HALF; ci < min(CHUNKS, (half + 1) * CH_PER_HALF); ++ci) {
+      for (int ci = ci_lo; ci < ci_hi; ++ci) {
         const int c = ci * 32;
+        const int col0 = n0 + c;
+        float ay[32];
+        if (MODE == NN && g.aux != nullptr) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(stg + (it * 4 + sr) * STG_PITCH + sc) = ax_next[it];
+          if (ci + 1 < ci_hi) load_aux(ci + 1);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 y4 = *reinterpret_cast<const float4*>(stg + lane * STG_PITCH + j);
+            ay[j] = y4.x; ay[j + 1] = y4.y; ay[j + 2] = y4.z; ay[j + 3] = y4.w;
+          }
+          __syncwarp();
+        }
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
-        if (row >= g.M) continue;
-        const int col0 = n0 + c;
-        if (col0 >= g.N) continue;
-        float* crow = g.C + (int64_t)row * g.ldc + col0;
-        const bool full = (col0 + 32 <= g.N);
+        if (col0 >= g.N && !want_colsum) continue;            // warp-uniform
         if (MODE == NT) {
           if (g.bias) {
-            if (full) {
+            if (col0 + 32 <= g.N) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
@@ -284,59 +403,82 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         } else if (MODE == NN) {
-          if (g.aux) {
-            const float* yrow = g.aux + (int64_t)row * g.ldaux + col0;
-            if (full && (((uintptr_t)yrow) & 15) == 0) {
+          if (g.aux != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 y4 = *reinterpret_cast<const float4*>(yrow + j);
-                v[j] *= (y4.x > 0.0f ? 1.0f : y4.x + 1.0f);
-                v[j + 1] *= (y4.y > 0.0f ? 1.0f : y4.y + 1.0f);
-                v[j + 2] *= (y4.z > 0.0f ? 1.0f : y4.z + 1.0f);
-                v[j + 3] *= (y4.w > 0.0f ? 1.0f : y4.w + 1.0f);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < g.N) {
-                  const float y = yrow[j];
-                  v[j] *= (y > 0.0f ? 1.0f : y + 1.0f);
-                }
-            }
+            for (int j = 0; j < 32; ++j) v[j] *= (ay[j] > 0.0f ? 1.0f : ay[j] + 1.0f);     // elu'(y) from the stored y
           }
-          if (g.accumulate) {
+          if (g.accumulate && row < g.M) {                    // rare (the actor's latent columns): row-per-lane access
+            const float* crow = g.C + (int64_t)row * g.ldc + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < g.N) v[j] += crow[j];
           }
         }
-        const bool vec = full && (((uintptr_t)crow) & 15) == 0;
-        if (MODE == TN) {
-          if (vec) {
+        // rows -> staging -> coalesced row segments
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        {
+          const int col = col0 + sc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) atomicAdd(crow + j, v[j]);
+          for (int it = 0; it < 8; ++it) {
+            const int r = row0 + it * 4 + sr;
+            if (r >= g.M || col >= g.N) continue;
+            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + sr) * STG_PITCH + sc);
+            float* dst = g.C + (int64_t)r * g.ldc + col;
+            if (MODE == TN) {
+              if (col + 3 < g.N && (((uintptr_t)dst) & 15) == 0) {
+                atomicAdd(reinterpret_cast<float4*>(dst), x);
+              } else {
+                atomicAdd(dst, x.x);
+                if (col + 1 < g.N) atomicAdd(dst + 1, x.y);
+                if (col + 2 < g.N) atomicAdd(dst + 2, x.z);
+                if (col + 3 < g.N) atomicAdd(dst + 3, x.w);
+              }
+            } else if (col + 3 < g.N && (((uintptr_t)dst) & 15) == 0) {
+              *reinterpret_cast<float4*>(dst) = x;
+            } else {
+              dst[0] = x.x;
+              if (col + 1 < g.N) dst[1] = x.y;
+              if (col + 2 < g.N) dst[2] = x.z;
+              if (col + 3 < g.N) dst[3] = x.w;
+            }
           }
-        } else if (vec) {
+        }
+        if (MODE == NN && want_colsum) {
+          // column `lane` of the staged 32 x 32 chunk (rows past M carry zeros: TMA zero-fills A out of bounds)
+          float cs = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) crow[j] = v[j];
+          for (int r = 0; r < 32; ++r) cs += stg[r * STG_PITCH + lane];
+          red_tile[c + lane] = cs;
+        }
+        __syncwarp();                                         // staging is rewritten by the next chunk
+      }
+      if (MODE == NN && want_colsum) {
+        // the 4 row quarters meet in shared memory: one atomic per column per tile (double-buffered by tile parity, so one
+        // barrier per tile orders both the reads after the writes and the next-but-one tile's writes after these reads)
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int tcol = (int)threadIdx.x - 64;
+        if (tcol < BN && n0 + tcol < g.N) {
+          const float* r = red + (local_tile & 1) * 4 * BN + tcol;
+          atomicAdd(g.dbias + n0 + tcol, (r[0] + r[BN]) + (r[2 * BN] + r[3 * BN]));
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(tmem_empty + acc);
+        else mbar_arrive(tmem_empty + acc);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (PAIR) cluster_sync_all();          // nobody leaves while its partner can still signal its barriers / read its smem
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -387,10 +529,12 @@ int num_sms() {
   return n;
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool PAIR = false>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int splits, cudaStream_t st, const char* name) {
-  constexpr int smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 256 + 1024;
-  auto kern = tc_gemm_kernel<MODE, BN>;
+  using Cfg = TileCfg<BN, PAIR>;
+  constexpr int smem = Cfg::STAGES_ * (int)Cfg::STAGE_BYTES + 256 + (MODE == NN ? 2 * 4 * BN * 4 : 0) + 8 * 32 * 36 * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "tile configuration does not fit shared memory");
+  auto kern = tc_gemm_kernel<MODE, BN, PAIR>;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -400,34 +544,91 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
     }
     done = true;
   }
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-  int ctas = num_sms() / (splits > 1 ? splits : 1);
-  ctas = ctas < 1 ? 1 : ctas;
-  dim3 grid(tiles < ctas ? tiles : ctas, splits);
-  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
+  const int tiles = ((g.M + Cfg::BMT - 1) / Cfg::BMT) * ((g.N + BN - 1) / BN);
+  int workers = (PAIR ? num_sms() / 2 : num_sms()) / (splits > 1 ? splits : 1);
+  workers = workers < 1 ? 1 : workers;
+  workers = tiles < workers ? tiles : workers;
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * workers, splits);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;      // the pair: two CTAs of one TPC
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
+    if (e != cudaSuccess) {
+      b200_set_error("%s: cudaLaunchKernelEx: %s", name, cudaGetErrorString(e));
+      return (int)e;
+    }
+  } else {
+    kern<<<dim3(workers, splits), NUM_THREADS, smem, st>>>(ta, tb, g);
+  }
   B200_CHECK_LAUNCH(name);
   return 0;
 }
 
+// CTA pairs (256-row tiles) pay off once there are enough pair tiles to occupy every pair; the N-tile width is the one
+// that wastes the fewest tile slots over the rounds of the persistent loop (wide tiles preferred at equal waste).
+int g_pair_mode = 1;      // b200_tc_set_pair_mode: 0 = never use the CTA-pair kernels (A/B measurements, tests)
+int pick_pair_bn(int rows, int cols) {
+  if (!g_pair_mode) return 0;
+  const int pairs = num_sms() / 2, m_tiles = (rows + 2 * BM - 1) / (2 * BM);
+  int best = 0;
+  double best_score = 0.0;
+  for (int cand : {256, 128}) {
+    const int padded = (cols + cand - 1) / cand * cand;
+    if (padded * 100 > cols * 113) continue;
+    const int tiles = m_tiles * (padded / cand);
+    if (tiles < pairs || m_tiles < pairs / 2) continue;
+    const int rounds = (tiles + pairs - 1) / pairs;
+    const double score = (double)tiles / ((double)rounds * pairs) * (cand == 256 ? 1.0 : (cand == 128 ? 0.97 : 0.90));
+    if (score > best_score) {
+      best_score = score;
+      best = cand;
+    }
+  }
+  return best;
+}
+
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-// N-tile width: the widest of {256,128,64,32} whose padding of `cols` (TMA zero-fills, stores are guarded) wastes
-// <= 13 % of the MMA work, narrowed while the problem would otherwise leave most SMs without a tile.
-int pick_bn(int rows, int cols, int splits_hint = 1) {
-  const int m_tiles = (rows + BM - 1) / BM;
-  int bn = 32;
+// N-tile width for the persistent single-CTA kernels: among {256,128,64,32} with <= 13 % padding of `cols` (TMA zero-fills,
+// stores are guarded) the one that fills the SMs best over the rounds of the persistent loop, wide tiles preferred at
+// equal fill (operand re-reads).  `split_k` (wgrad): split-K supplies the parallelism, take the widest tile.
+int pick_bn(int rows, int cols, int split_k = 0) {
+  const int m_tiles = (rows + BM - 1) / BM, sms = num_sms();
+  int best = 32;
+  double best_score = -1.0;
   for (int cand : {256, 128, 64, 32}) {
     const int padded = (cols + cand - 1) / cand * cand;
     if (cand > 32 && padded * 100 > cols * 113) continue;
-    bn = cand;
-    if (m_tiles * (padded / cand) * splits_hint >= (num_sms() * 3) / 4) break;
+    if (split_k) return cand;
+    const int tiles = m_tiles * (padded / cand);
+    const int rounds = (tiles + sms - 1) / sms;
+    const double pref = cand == 256 ? 1.0 : (cand == 128 ? 0.95 : (cand == 64 ? 0.85 : 0.70));
+    const double score = (double)tiles / ((double)rounds * sms) * pref;
+    if (score > best_score) {
+      best_score = score;
+      best = cand;
+    }
   }
-  return bn;
+  return best;
 }
 
 }  // namespace
 
 extern "C" {
+
+int b200_tc_set_pair_mode(int on) {
+  g_pair_mode = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 forward only (default), 2 forward + dgrad
+  return 0;
+}
 
 // 1 if the tcgen05 path can run this forward problem (else callers use b200_linear_forward)
 int b200_tc_linear_supported(int M, int N, int K) { return (N >= 8 && K >= 8 && M >= 1) ? 1 : 0; }
@@ -437,13 +638,20 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
   B200_CHECK_ARG(X && W && Y && M > 0 && N > 0 && K > 0, "b200_tc_linear_forward: bad argument");
   B200_CHECK_ARG(b200_tc_linear_supported(M, N, K), "b200_tc_linear_forward: needs N >= 8 and K >= 8 (N=%d K=%d)", N, K);
   B200_CHECK_ARG(ldx % 4 == 0 && ldw % 4 == 0 && aligned16(X) && aligned16(W), "b200_tc_linear_forward: operands need 16-byte rows");
-  const int bn = pick_bn(M, N);
+  const int pbn = pick_pair_bn(M, N);
+  const int bn = pbn ? pbn : pick_bn(M, N);
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, X, M, K, ldx, BM, 0)) return rc;
-  if (int rc = make_tmap(&tb, W, N, K, ldw, bn, 0)) return rc;
+  if (int rc = make_tmap(&tb, W, N, K, ldw, pbn ? bn / 2 : bn, 0)) return rc;   // pair: each CTA stages half of the B rows
   TcArgs g{};
   g.C = Y; g.bias = bias; g.ldc = ldy; g.M = M; g.N = N; g.K = K; g.act = act;
   cudaStream_t st = (cudaStream_t)stream;
+  switch (pbn) {
+    case 256: return launch_tc<NT, 256, true>(ta, tb, g, 1, st, "tc_forward_pair<256>");
+    case 128: return launch_tc<NT, 128, true>(ta, tb, g, 1, st, "tc_forward_pair<128>");
+    case 64: return launch_tc<NT, 64, true>(ta, tb, g, 1, st, "tc_forward_pair<64>");
+    default: break;
+  }
   switch (bn) {
     case 256: return launch_tc<NT, 256>(ta, tb, g, 1, st, "tc_forward<256>");
     case 128: return launch_tc<NT, 128>(ta, tb, g, 1, st, "tc_forward<128>");
@@ -452,18 +660,32 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
   }
 }
 
-// dX[M,K] (+)= (dY[M,N] . W[N,K]) * elu'(Yprev)
+// dX[M,K] (+)= (dY[M,N] . W[N,K]) * elu'(Yprev);  dbias_prev[K] += column sums of dX (the bias gradient of the layer below)
+int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX, int lddx, int M,
+                              int N, int K, int accumulate, float* dbias_prev, void* stream);
 int b200_tc_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX, int lddx, int M,
                          int N, int K, int accumulate, void* stream) {
+  return b200_tc_linear_dgrad_bias(dY, lddy, W, ldw, Yprev, ldyp, dX, lddx, M, N, K, accumulate, nullptr, stream);
+}
+int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw, const float* Yprev, int ldyp, float* dX, int lddx, int M,
+                              int N, int K, int accumulate, float* dbias_prev, void* stream) {
   B200_CHECK_ARG(dY && W && dX && M > 0 && N > 0 && K > 0, "b200_tc_linear_dgrad: bad argument");
+  B200_CHECK_ARG(!(dbias_prev && accumulate), "b200_tc_linear_dgrad_bias: the fused bias gradient needs accumulate = 0");
   B200_CHECK_ARG(lddy % 4 == 0 && ldw % 4 == 0 && aligned16(dY) && aligned16(W), "b200_tc_linear_dgrad: operands need 16-byte rows");
-  const int bn = pick_bn(M, K);
+  const int pbn = g_pair_mode == 2 ? pick_pair_bn(M, K) : 0;   // measured: pairs do not pay for the dgrads (epilogue-bound); 2 = force
+  const int bn = pbn ? pbn : pick_bn(M, K);
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, dY, M, N, lddy, BM, 0)) return rc;          // A K-major: [M rows][N reduction]
   if (int rc = make_tmap(&tb, W, N, K, ldw, BK, 1)) return rc;            // B MN-major: box [32 n][32 k]
   TcArgs g{};
-  g.C = dX; g.aux = Yprev; g.ldc = lddx; g.ldaux = ldyp; g.M = M; g.N = K; g.K = N; g.accumulate = accumulate;
+  g.C = dX; g.aux = Yprev; g.ldc = lddx; g.ldaux = ldyp; g.M = M; g.N = K; g.K = N; g.accumulate = accumulate; g.dbias = dbias_prev;
   cudaStream_t st = (cudaStream_t)stream;
+  switch (pbn) {
+    case 256: return launch_tc<NN, 256, true>(ta, tb, g, 1, st, "tc_dgrad_pair<256>");
+    case 128: return launch_tc<NN, 128, true>(ta, tb, g, 1, st, "tc_dgrad_pair<128>");
+    case 64: return launch_tc<NN, 64, true>(ta, tb, g, 1, st, "tc_dgrad_pair<64>");
+    default: break;
+  }
   switch (bn) {
     case 256: return launch_tc<NN, 256>(ta, tb, g, 1, st, "tc_dgrad<256>");
     case 128: return launch_tc<NN, 128>(ta, tb, g, 1, st, "tc_dgrad<128>");

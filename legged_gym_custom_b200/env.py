@@ -312,10 +312,12 @@ for _name in ("obs_buf", "privileged_obs_buf", "critic_obs_buf", "estimated_obs_
 
 class HostPhysX:
     """PhysX frames living in PINNED HOST memory (the reference's --sim_device=cpu pipeline hands the env host
-    tensors): every substep / refresh copies that step's frame host->device on the current stream.  Used by
-    bench.py's end-to-end measurement; `h2d_bytes` counts what was copied."""
+    tensors): every substep / refresh moves that step's frame host->device on the current stream.  dof_state, root_states
+    and contact_forces are read densely and are copied; rigid_body_states [N*19,13] is read at 4 floats per env (the feet
+    heights, go2.py:272-277), so the kernel reads it IN PLACE from the pinned buffer (zero-copy over PCIe) instead of
+    copying 4 MB per step.  Used by bench.py's end-to-end measurement; `bytes_per_step` counts what crosses the bus."""
 
-    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, **frame_kw):
+    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, zero_copy_rigid=True, **frame_kw):
         rng = np.random.default_rng(seed)
         origins = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
         self.frames = []
@@ -323,8 +325,11 @@ class HostPhysX:
             f = synth.make_frames(num_envs, origins, rng, decimation=decimation, **frame_kw)
             self.frames.append({k: torch.from_numpy(v).pin_memory() for k, v in f.items()})
         self.cursor, self.h2d_bytes = -1, 0
+        self.zero_copy_rigid = bool(zero_copy_rigid)
         f0 = self.frames[0]
-        self.bytes_per_step = 4 * (f0["dof"].numel() + f0["root"].numel() + f0["contact"].numel() + f0["rigid"].numel())
+        # zero-copy reads: 4 feet per env, one 32-byte sector each
+        self.rigid_bytes = num_envs * 4 * 32 if self.zero_copy_rigid else 4 * f0["rigid"].numel()
+        self.bytes_per_step = 4 * (f0["dof"].numel() + f0["root"].numel() + f0["contact"].numel()) + self.rigid_bytes
 
     def begin_step(self, env):
         self.cursor = (self.cursor + 1) % len(self.frames)
@@ -336,9 +341,14 @@ class HostPhysX:
 
     def refresh(self, env):
         f = self.frames[self.cursor]
-        for name, key in (("root_states", "root"), ("contact_forces", "contact"), ("rigid_body_states", "rigid")):
+        for name, key in (("root_states", "root"), ("contact_forces", "contact")):
             env.bufs[name].copy_(f[key], non_blocking=True)
             self.h2d_bytes += f[key].numel() * 4
+        if self.zero_copy_rigid:
+            env.bufs.rebind_host_mapped("rigid_body_states", f["rigid"])
+        else:
+            env.bufs["rigid_body_states"].copy_(f["rigid"], non_blocking=True)
+        self.h2d_bytes += self.rigid_bytes
 
     def push_state(self, env):
         pass

@@ -136,21 +136,30 @@ class Kernels:
             _lib.check(self.lib.b200_linear_forward(X, ldx, lin.w(), lin.ldw, lin.b(), Y, ldy, M, lin.N, lin.K, act, self.precise,
                                                     _lib.stream_ptr()))
 
-    def dgrad(self, lin, dY, lddy, Yprev, ldyp, dX, lddx, M, accumulate=0, wcol=0, K=None):
-        """dX[M,K] (+)= dY[M,N] . W[:, wcol:wcol+K] * elu'(Yprev)"""
+    def dgrad(self, lin, dY, lddy, Yprev, ldyp, dX, lddx, M, accumulate=0, wcol=0, K=None, dbias_prev=None):
+        """dX[M,K] (+)= dY[M,N] . W[:, wcol:wcol+K] * elu'(Yprev).  With `dbias_prev` (the bias-gradient pointer of the layer
+        below) the tcgen05 kernel also reduces the column sums of dX into it; returns True when it did."""
         K = lin.K if K is None else K
         if self.use_tc and lin.N >= 8 and K >= 8:
+            if dbias_prev is not None and not accumulate:
+                _lib.check(self.lib.b200_tc_linear_dgrad_bias(dY, lddy, lin.w(col=wcol), lin.ldw, Yprev, ldyp, dX, lddx, M, lin.N, K, 0,
+                                                              dbias_prev, _lib.stream_ptr()))
+                return True
             _lib.check(self.lib.b200_tc_linear_dgrad(dY, lddy, lin.w(col=wcol), lin.ldw, Yprev, ldyp, dX, lddx, M, lin.N, K, accumulate,
                                                      _lib.stream_ptr()))
         else:
             _lib.check(self.lib.b200_linear_dgrad(dY, lddy, lin.w(col=wcol), lin.ldw, Yprev, ldyp, dX, lddx, M, lin.N, K, accumulate,
                                                   self.precise, _lib.stream_ptr()))
 
-    def wgrad(self, lin, dY, lddy, X, ldx, M, K=None):
+    def wgrad(self, lin, dY, lddy, X, ldx, M, K=None, bias_done=False):
+        """dW += dY^T . X and db += colsum(dY); `bias_done`: the dgrad of the layer above has already reduced db"""
         K = lin.K if K is None else K
         if self.use_tc and lin.N >= 8 and K >= 8 and M >= 32:
             _lib.check(self.lib.b200_tc_linear_wgrad(dY, lddy, X, ldx, lin.w("grads"), lin.ldw, M, lin.N, K, _lib.stream_ptr()))
-            _lib.check(self.lib.b200_colsum(dY, lddy, lin.b("grads"), M, lin.N, _lib.stream_ptr()))
+            if not bias_done:
+                _lib.check(self.lib.b200_colsum(dY, lddy, lin.b("grads"), M, lin.N, _lib.stream_ptr()))
+        elif bias_done:
+            raise RuntimeError("bias gradient was fused into the dgrad above but this layer's wgrad takes the fallback path")
         else:
             _lib.check(self.lib.b200_linear_wgrad(dY, lddy, X, ldx, lin.w("grads"), lin.ldw, lin.b("grads"), M, lin.N, K, self.precise,
                                                   _lib.stream_ptr()))
@@ -172,6 +181,7 @@ def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M):
 def chain_backward(k, layers, ws, tag, X0, ldx0, dOut, lddo, M, need_dx0=False, dX0=None, lddx0=0):
     """backward of chain_forward: wgrad of every layer, dgrad between layers (elu' fused from the stored activation)."""
     dY, lddy = dOut, lddo
+    bias_done = False
     for i in reversed(range(len(layers))):
         lin = layers[i]
         if i > 0:
@@ -179,10 +189,13 @@ def chain_backward(k, layers, ws, tag, X0, ldx0, dOut, lddo, M, need_dx0=False, 
             X = ws.ptr(f"{tag}{i - 1}", M, ldx)
         else:
             X, ldx = X0, ldx0
-        k.wgrad(lin, dY, lddy, X, ldx, M)
+        k.wgrad(lin, dY, lddy, X, ldx, M, bias_done=bias_done)
+        bias_done = False
         if i > 0:
             dX = ws.ptr(f"d{tag}{i - 1}", M, ldx)
-            k.dgrad(lin, dY, lddy, X, ldx, dX, ldx, M)
+            below = layers[i - 1]
+            fuse = k.use_tc and below.N >= 8 and below.K >= 8 and M >= 32      # the layer below takes the tcgen05 wgrad path
+            bias_done = bool(k.dgrad(lin, dY, lddy, X, ldx, dX, ldx, M, dbias_prev=below.b("grads") if fuse else None))
             dY, lddy = dX, ldx
         elif need_dx0:
             k.dgrad(lin, dY, lddy, None, 0, dX0, lddx0, M)

@@ -238,3 +238,26 @@ def test_every_reward_term_active_matches_oracle():
         env.step(actions, frames, step)
         gu.check_step(env.bufs, gu.oracle_expected(orc, out), t_)
     env.close()
+
+
+def test_host_physx_zero_copy_matches_copy():
+    """HostPhysX (bench.py's end-to-end arm): reading rigid_body_states in place from pinned host memory gives
+    bit-identical steps to copying the whole tensor to the device first."""
+    from legged_gym_custom_b200.env import Go2Env, HostPhysX
+
+    class Cfg(configs.Go2ParkourCfg):
+        class env(configs.Go2ParkourCfg.env):
+            num_envs = 512
+    outs = []
+    for zero_copy in (True, False):
+        env = Go2Env(Cfg, sim_device=DEV, seed=3)
+        env.physx = HostPhysX(512, env.bufs["env_origins"], torch.device(DEV), seed=3, decimation=env.params.decimation,
+                              zero_copy_rigid=zero_copy)
+        env.reset()
+        g = torch.Generator(device=DEV).manual_seed(0)
+        for _ in range(5):
+            out = env.step(torch.randn(512, NUM_DOF, device=DEV, generator=g))
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in out[:7]] + [env.bufs["last_contact_heights"].clone()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

@@ -8,6 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from legged_gym_custom_b200 import _lib  # noqa: E402
 
 lib = _lib.lib()
+if os.environ.get("B200_PAIR") is not None:
+    lib.b200_tc_set_pair_mode(int(os.environ["B200_PAIR"]))
 DEV = "cuda:0"
 ld = lambda k: (k + 3) // 4 * 4
 p = lambda t: t.data_ptr()
@@ -32,7 +34,8 @@ def timeit(fn, n=20):
 
 modes = sys.argv[1:] or ["fwd", "dgrad", "wgrad"]
 shapes = [(4096, 512, 627), (24576, 512, 627), (24576, 256, 512), (24576, 128, 256), (24576, 512, 736), (24576, 256, 572), (333, 128, 132),
-          (1000, 64, 128), (500, 32, 64), (24576, 12, 128), (24576, 20, 64)]
+          (1000, 64, 128), (500, 32, 64), (24576, 12, 128), (24576, 20, 64), (24576, 128, 132), (24576, 64, 128), (24500, 256, 512),
+          (65536, 512, 627)]
 torch.backends.cuda.matmul.allow_tf32 = False
 for M, N, K in shapes:
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
@@ -63,6 +66,13 @@ for M, N, K in shapes:
         t_tc = timeit(lambda: lib.b200_tc_linear_dgrad(p(dY), ld(N), p(W), ld(K), p(Yp), ld(K), p(dX), ld(K), M, N, K, 0, st))
         t_mma = timeit(lambda: lib.b200_linear_dgrad(p(dY), ld(N), p(W), ld(K), p(Yp), ld(K), p(dX), ld(K), M, N, K, 0, 0, st))
         line += f" dgrad err {e:.1e} tc {t_tc:7.1f}us ({2 * M * N * K / t_tc / 1e6:6.1f} TF) mma {t_mma:7.1f}us |"
+        db = torch.zeros(ld(K), device=DEV)
+        rc = lib.b200_tc_linear_dgrad_bias(p(dY), ld(N), p(W), ld(K), p(Yp), ld(K), p(dX), ld(K), M, N, K, 0, p(db), st)
+        torch.cuda.synchronize()
+        assert rc == 0, lib.b200_last_error()
+        eb = err(db[:K], (ref - 1.0).sum(0))
+        t_b = timeit(lambda: lib.b200_tc_linear_dgrad_bias(p(dY), ld(N), p(W), ld(K), p(Yp), ld(K), p(dX), ld(K), M, N, K, 0, p(db), st))
+        line += f" +dbias err {eb:.1e} {t_b:7.1f}us |"
     if "wgrad" in modes:
         dW = torch.full((N, ld(K)), 0.5, device=DEV)
         rc = lib.b200_tc_linear_wgrad(p(dY), ld(N), p(X), ld(K), p(dW), ld(K), M, N, K, st)
