@@ -106,8 +106,12 @@ class Profile:
         elif name == "b200_pd_torques":
             bytes_ = PD_BYTES_PER_ENV * self.n
         if shape is not None:
-            flops = 2.0 * shape[0] * shape[1] * shape[2]
-            name = f"{name}[M={shape[0]},N={shape[1]},K={shape[2]}]"       # one row per kernel PROBLEM, not per entry point
+            M_, N_, K_ = shape
+            flops = 2.0 * M_ * N_ * K_
+            # algorithmic bytes of the fp32 problem: forward X[M,K] + W[N,K] + Y[M,N]; dgrad dY[M,N] + W[N,K] + dX[M,K]
+            # (+ the stored activation [M,K] it multiplies by elu'); wgrad dY[M,N] + X[M,K] + dW[N,K]
+            bytes_ = 4.0 * (M_ * K_ + N_ * K_ + M_ * N_ + (M_ * K_ if "dgrad" in name else 0))
+            name = f"{name}[M={M_},N={N_},K={K_}]"       # one row per kernel PROBLEM, not per entry point
         self.recs.append((name, e0, e1, flops, bytes_))
         return rc
 
@@ -225,17 +229,21 @@ def run_b200(args):
     peaks = measured_peaks()
     dom = max(table.items(), key=lambda kv: kv[1][0])
     name, (tsec, n, fl, by) = dom
-    if fl > 0:
+    ridge = peaks["tensor"] * 1e12 / (peaks["hbm"] * 1e9)          # flop per byte above which the tensor roof is the lower one
+    if fl > 0 and (by <= 0 or fl / by >= ridge):
         roof = {"kernel": name, "bound": "tensor", "achieved": fl / tsec / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
                 "frac": fl / tsec / 1e12 / peaks["tensor"], "traffic": None, "launches": n, "avg_us": tsec / n * 1e6}
     else:
         roof = {"kernel": name, "bound": "hbm", "achieved": by / tsec / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": by / tsec / 1e9 / peaks["hbm"], "traffic": None, "launches": n, "avg_us": tsec / n * 1e6}
     roof["peak_source"] = peaks["source"]
-    roof["traffic"] = TRAFFIC.get(name.split("[")[0] + ("[" + name.split("[")[1] if "[" in name else ""))
-    if roof["bound"] == "tensor":      # the GEMMs run kind::tf32 (the reference's matmul precision); dense TF32 peak = bf16 / 2
-        roof["tf32_peak_equiv"] = peaks["tensor"] / 2
-        roof["frac_of_tf32_peak"] = roof["achieved"] / (peaks["tensor"] / 2)
+    roof["traffic"] = TRAFFIC.get(name)
+    if fl > 0:      # a GEMM: say where it sits on the roofline (fp32 operands: most of these problems are below the ridge)
+        roof["arithmetic_intensity_flop_per_byte"] = fl / by
+        roof["ridge_flop_per_byte"] = ridge
+        roof["tflops"] = fl / tsec / 1e12
+        roof["tensor_peak"] = peaks["tensor"]
+        roof["note"] = "kind::tf32 MMAs on fp32 operands (the reference's matmul precision); dense TF32 peak is half the bf16 peak above"
     total_prof = sum(v[0] for v in table.values())
     breakdown = {k: {"ms": round(v[0] * 1e3, 3), "calls": v[1], "share": round(v[0] / total_prof, 4),
                      **({"tflops": round(v[2] / v[0] / 1e12, 2)} if v[2] else {}), **({"gbs": round(v[3] / v[0] / 1e9, 1)} if v[3] else {})}
@@ -252,26 +260,51 @@ def run_b200(args):
         step0 = int(env.common_step_counter) + 1000
 
         def time_env(do_flush, reps=30):
-            ts = []
-            for i in range(reps + 5):
-                if do_flush:
-                    flush.zero_()
+            launch = lambda i: _lib.check(lib.b200_post_physics_step_parts(h, C.byref(bs), step0 + i, 1, _lib.stream_ptr()))
+            for i in range(5):
+                launch(i)
+            if not do_flush:          # back to back: one event pair around the whole train (no launch latency inside)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                _lib.check(lib.b200_post_physics_step_parts(h, C.byref(bs), step0 + i, 1, _lib.stream_ptr()))
+                for i in range(reps):
+                    launch(5 + i)
                 b.record()
                 b.synchronize()
-                if i >= 5:
-                    ts.append(a.elapsed_time(b) * 1e-3)
+                return a.elapsed_time(b) * 1e-3 / reps
+            ts = []
+            for i in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                launch(5 + i)
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b) * 1e-3)
             return float(np.mean(ts))
+
+        def device_span():            # %globaltimer trace written by the kernel itself: last CTA end - first CTA start
+            ctas = (N + 7) // 8
+            trace = torch.zeros(ctas, 8, dtype=torch.int64, device=device)
+            _lib.check(lib.b200_env_set_phase_trace(h, C.c_void_p(trace.data_ptr())))
+            spans = []
+            for i in range(10):
+                _lib.check(lib.b200_post_physics_step_parts(h, C.byref(bs), step0 + 100 + i, 1, _lib.stream_ptr()))
+                torch.cuda.synchronize()
+                t = trace.cpu().numpy()
+                spans.append(float(t[:, 5].max() - t[:, 0].min()) * 1e-9)
+            _lib.check(lib.b200_env_set_phase_trace(h, None))
+            return float(np.median(spans))
         prof_hook, _lib.lib().hook = _lib.lib().hook, None
-        t_cold, t_warm = time_env(True), time_env(False)
+        t_cold, t_warm, t_span = time_env(True), time_env(False), device_span()
         _lib.lib().hook = prof_hook
         by = ENV_BYTES_PER_ENV * N
         roof_env = {"kernel": "post_physics_kernel", "bound": "hbm", "achieved": by / t_cold / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": by / t_cold / 1e9 / peaks["hbm"], "traffic": TRAFFIC.get("post_physics_kernel"), "avg_us": t_cold * 1e6,
                     "l2": "flushed before every launch", "peak_source": peaks["source"],
-                    "l2_resident": {"avg_us": t_warm * 1e6, "achieved": by / t_warm / 1e9, "frac": by / t_warm / 1e9 / peaks["hbm"]},
+                    "l2_resident": {"avg_us": t_warm * 1e6, "achieved": by / t_warm / 1e9, "frac": by / t_warm / 1e9 / peaks["hbm"],
+                                    "how": "30 launches back to back between one CUDA-event pair"},
+                    "device_span": {"us": t_span * 1e6, "achieved": by / t_span / 1e9, "frac": by / t_span / 1e9 / peaks["hbm"],
+                                    "how": "%globaltimer written by the kernel: last CTA end - first CTA start, L2-resident"},
                     "algorithmic_bytes_per_env": ENV_BYTES_PER_ENV}
         del flush
 

@@ -321,26 +321,40 @@ struct AdaptArgs {
   float *proj, *c1, *c2;      // optional [M,320], [M,80], [M,36]
   int M;
 };
-constexpr int AD_S = 16;       // samples per CTA (static shared memory stays under 48 KB)
+constexpr int AD_S = 32;       // samples per CTA pass
+constexpr int AD_THREADS = AD_S * 10;   // stage 1 has one thread per (sample, history step): exactly one pass
+constexpr int AD_W1 = 52, AD_W2 = 120, AD_W3 = 40, AD_W4 = 32;     // weight row pitches (floats, 16-byte rows)
+constexpr int AD_SMEM_FLOATS = 30 * AD_W1 + 20 * AD_W2 + 10 * AD_W3 + 20 * AD_W4 + 32 + 20 + 12 + 20 + AD_S * 10 * 31 + AD_S * 4 * 21 +
+                               AD_S * 3 * 11;
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : expf(x) - 1.0f; }
 
-__global__ void __launch_bounds__(256) adapt_forward_kernel(const __grid_constant__ AdaptArgs a) {
-  __shared__ float W1[30 * 53], W2[20 * 121], W3[10 * 41], W4[20 * 31];
-  __shared__ float B1[32], B2[20], B3[12], B4[20];
-  __shared__ float proj[AD_S][10][31];
-  __shared__ float c1[AD_S][4][21];
-  __shared__ float c2[AD_S][3][11];
+// Every stage is register-tiled the same way: a thread owns one output POSITION (sample, time step) with ALL its output
+// channels, keeps the position's inputs in registers and streams the weight rows as 16-byte shared-memory BROADCASTS (all
+// lanes read the same address), so the inner loops are 4 FMAs per shared-memory instruction instead of 1.
+__global__ void __launch_bounds__(AD_THREADS, 2) adapt_forward_kernel(const __grid_constant__ AdaptArgs a) {
+  extern __shared__ __align__(16) float ad_smem[];
+  float* W1 = ad_smem;                    // [30][52]
+  float* W2 = W1 + 30 * AD_W1;            // [20][4 taps x 30]
+  float* W3 = W2 + 20 * AD_W2;            // [10][2 taps x 20]
+  float* W4 = W3 + 10 * AD_W3;            // [20][32] (3 x 10 used, zero padded)
+  float* B1 = W4 + 20 * AD_W4;            // 32
+  float* B2 = B1 + 32;                    // 20
+  float* B3 = B2 + 20;                    // 12
+  float* B4 = B3 + 12;                    // 20
+  float* proj = B4 + 20;                  // [AD_S][10][31]
+  float* c1 = proj + AD_S * 10 * 31;      // [AD_S][4][21]
+  float* c2 = c1 + AD_S * 4 * 21;         // [AD_S][3][11]
   const int tid = threadIdx.x;
-  for (int i = tid; i < 30 * 52; i += 256) W1[(i / 52) * 53 + i % 52] = a.W1[i];
-  for (int i = tid; i < 20 * 120; i += 256) {           // drop the two zero-pad channels of each tap
+  for (int i = tid; i < 30 * 52; i += AD_THREADS) W1[i] = a.W1[i];
+  for (int i = tid; i < 20 * 120; i += AD_THREADS) {           // drop the two zero-pad channels of each tap
     const int co = i / 120, r = i % 120, k = r / 30, ci = r % 30;
-    W2[co * 121 + r] = a.W2[co * 128 + k * 32 + ci];
+    W2[i] = a.W2[co * 128 + k * 32 + ci];
   }
-  for (int i = tid; i < 10 * 40; i += 256) W3[(i / 40) * 41 + i % 40] = a.W3[i];
-  for (int i = tid; i < 20 * 30; i += 256) {
-    const int o = i / 30, r = i % 30, t = r / 10, c = r % 10;
-    W4[o * 31 + r] = a.W4[o * 36 + t * 12 + c];
+  for (int i = tid; i < 10 * 40; i += AD_THREADS) W3[i] = a.W3[i];
+  for (int i = tid; i < 20 * 32; i += AD_THREADS) {
+    const int o = i / 32, r = i % 32, t = r / 10, c = r % 10;
+    W4[i] = r < 30 ? a.W4[o * 36 + t * 12 + c] : 0.0f;
   }
   if (tid < 30) B1[tid] = a.b1[tid];
   if (tid < 20) { B2[tid] = a.b2[tid]; B4[tid] = a.b4[tid]; }
@@ -348,68 +362,104 @@ __global__ void __launch_bounds__(256) adapt_forward_kernel(const __grid_constan
   __syncthreads();
   for (int row0 = blockIdx.x * AD_S; row0 < a.M; row0 += gridDim.x * AD_S) {
     const int ns = min(AD_S, a.M - row0);
-    // stage 1: one (sample, step) pair per thread, 30 channels each; the 52 inputs sit in registers
-    for (int idx = tid; idx < ns * 10; idx += 256) {
+    // stage 1: Linear(52 -> 30) + ELU on one (sample, step): the 52 inputs sit in registers
+    for (int idx = tid; idx < ns * 10; idx += AD_THREADS) {
       const int s = idx / 10, t = idx % 10;
       const float4* xp = reinterpret_cast<const float4*>(a.X + (int64_t)(row0 + s) * a.ldx + 52 * t);
-      float x[52];
+      float4 x[13];
 #pragma unroll
-      for (int i = 0; i < 13; ++i) {
-        const float4 v = __ldg(xp + i);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-      }
+      for (int i = 0; i < 13; ++i) x[i] = __ldg(xp + i);
+      float* pr = proj + (s * 10 + t) * 31;
+#pragma unroll 3
       for (int c = 0; c < 30; ++c) {
-        float acc = B1[c];
-        const float* w = W1 + c * 53;
+        const float4* w = reinterpret_cast<const float4*>(W1 + c * AD_W1);
+        float acc0 = B1[c], acc1 = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 52; ++i) acc = fmaf(x[i], w[i], acc);
-        const float y = elu1(acc);
-        proj[s][t][c] = y;
+        for (int i = 0; i < 13; ++i) {
+          const float4 w4 = w[i];
+          acc0 = fmaf(x[i].x, w4.x, acc0);
+          acc1 = fmaf(x[i].y, w4.y, acc1);
+          acc0 = fmaf(x[i].z, w4.z, acc0);
+          acc1 = fmaf(x[i].w, w4.w, acc1);
+        }
+        const float y = elu1(acc0 + acc1);
+        pr[c] = y;
         if (a.proj) a.proj[(int64_t)(row0 + s) * 320 + 32 * t + c] = y;
       }
     }
     __syncthreads();
-    // stage 2: Conv1d(30 -> 20, k = 4, stride 2): (sample, t', co)
-    for (int idx = tid; idx < ns * 80; idx += 256) {
-      const int s = idx / 80, r = idx % 80, tp = r / 20, co = r % 20;
-      float acc = B2[co];
-      const float* w = W2 + co * 121;
+    // stage 2: Conv1d(30 -> 20, k = 4, stride 2) + ELU on one (sample, t'): 20 accumulators, one tap's 30 inputs at a time
+    for (int idx = tid; idx < ns * 4; idx += AD_THREADS) {
+      const int s = idx >> 2, tp = idx & 3;
+      float acc[20];
 #pragma unroll
+      for (int co = 0; co < 20; ++co) acc[co] = B2[co];
+#pragma unroll 1
       for (int k = 0; k < 4; ++k) {
-        const float* p = &proj[s][2 * tp + k][0];
+        const float* p = proj + (s * 10 + 2 * tp + k) * 31;
+        float in[32];
 #pragma unroll
-        for (int ci = 0; ci < 30; ++ci) acc = fmaf(p[ci], w[k * 30 + ci], acc);
+        for (int ci = 0; ci < 30; ++ci) in[ci] = p[ci];
+        in[30] = in[31] = 0.0f;
+#pragma unroll
+        for (int co = 0; co < 20; ++co) {
+          const float* wr = W2 + co * AD_W2 + k * 30;     // 30 floats per tap: 8-byte aligned rows -> float2 broadcasts
+          const float2* w2 = reinterpret_cast<const float2*>(wr);
+          float accl = acc[co];
+#pragma unroll
+          for (int i = 0; i < 15; ++i) {
+            const float2 ww = w2[i];
+            accl = fmaf(in[2 * i], ww.x, accl);
+            accl = fmaf(in[2 * i + 1], ww.y, accl);
+          }
+          acc[co] = accl;
+        }
       }
-      const float y = elu1(acc);
-      c1[s][tp][co] = y;
-      if (a.c1) a.c1[(int64_t)(row0 + s) * 80 + 20 * tp + co] = y;
+      float* o = c1 + (s * 4 + tp) * 21;
+#pragma unroll
+      for (int co = 0; co < 20; ++co) {
+        const float y = elu1(acc[co]);
+        o[co] = y;
+        if (a.c1) a.c1[(int64_t)(row0 + s) * 80 + 20 * tp + co] = y;
+      }
     }
     __syncthreads();
-    // stage 3: Conv1d(20 -> 10, k = 2): (sample, t'', co)
-    for (int idx = tid; idx < ns * 30; idx += 256) {
-      const int s = idx / 30, r = idx % 30, tp = r / 10, co = r % 10;
-      float acc = B3[co];
-      const float* w = W3 + co * 41;
+    // stage 3: Conv1d(20 -> 10, k = 2) + ELU on one (sample, t'')
+    for (int idx = tid; idx < ns * 3; idx += AD_THREADS) {
+      const int s = idx / 3, tp = idx % 3;
+      float in[40];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float* p = &c1[s][tp + k][0];
+      for (int k = 0; k < 2; ++k)
 #pragma unroll
-        for (int ci = 0; ci < 20; ++ci) acc = fmaf(p[ci], w[k * 20 + ci], acc);
+        for (int ci = 0; ci < 20; ++ci) in[k * 20 + ci] = c1[(s * 4 + tp + k) * 21 + ci];
+      float* o = c2 + (s * 3 + tp) * 11;
+#pragma unroll 2
+      for (int co = 0; co < 10; ++co) {
+        const float4* w = reinterpret_cast<const float4*>(W3 + co * AD_W3);
+        float acc = B3[co];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const float4 w4 = w[i];
+          acc = fmaf(in[4 * i], w4.x, acc);
+          acc = fmaf(in[4 * i + 1], w4.y, acc);
+          acc = fmaf(in[4 * i + 2], w4.z, acc);
+          acc = fmaf(in[4 * i + 3], w4.w, acc);
+        }
+        const float y = elu1(acc);
+        o[co] = y;
+        if (a.c2) a.c2[(int64_t)(row0 + s) * 36 + 12 * tp + co] = y;
       }
-      const float y = elu1(acc);
-      c2[s][tp][co] = y;
-      if (a.c2) a.c2[(int64_t)(row0 + s) * 36 + 12 * tp + co] = y;
     }
     __syncthreads();
     // stage 4: Flatten + Linear(30 -> 20) + ELU: (sample, o)
-    for (int idx = tid; idx < ns * 20; idx += 256) {
+    for (int idx = tid; idx < ns * 20; idx += AD_THREADS) {
       const int s = idx / 20, o = idx % 20;
       float acc = B4[o];
-      const float* w = W4 + o * 31;
+      const float* w = W4 + o * AD_W4;
 #pragma unroll
       for (int t = 0; t < 3; ++t)
 #pragma unroll
-        for (int c = 0; c < 10; ++c) acc = fmaf(c2[s][t][c], w[t * 10 + c], acc);
+        for (int c = 0; c < 10; ++c) acc = fmaf(c2[(s * 3 + t) * 11 + c], w[t * 10 + c], acc);
       a.out[(int64_t)(row0 + s) * a.ldo + o] = elu1(acc);
     }
     __syncthreads();
@@ -554,9 +604,18 @@ int b200_adaptation_forward(const float* X, int ldx, const float* W1, const floa
   B200_CHECK_ARG(X && W1 && b1 && W2 && b2 && W3 && b3 && W4 && b4 && out && M > 0, "b200_adaptation_forward: null argument");
   B200_CHECK_ARG(ldx % 4 == 0 && ldx >= 520 && (((uintptr_t)X) & 15) == 0, "b200_adaptation_forward: X rows must be 16-byte aligned, >= 520 wide");
   AdaptArgs a{X, ldx, W1, b1, W2, b2, W3, b3, W4, b4, out, ldo, proj, c1, c2, M};
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(adapt_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(AD_SMEM_FLOATS * sizeof(float)));
+    if (e != cudaSuccess) {
+      b200_set_error("adapt_forward_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_done = true;
+  }
   int blocks = (M + AD_S - 1) / AD_S;
-  blocks = blocks > 148 * 4 ? 148 * 4 : blocks;
-  adapt_forward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  blocks = blocks > 148 * 2 ? 148 * 2 : blocks;
+  adapt_forward_kernel<<<blocks, AD_THREADS, AD_SMEM_FLOATS * sizeof(float), (cudaStream_t)stream>>>(a);
   B200_CHECK_LAUNCH("adapt_forward_kernel");
   return 0;
 }

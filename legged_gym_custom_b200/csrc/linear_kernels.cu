@@ -294,6 +294,26 @@ int check_common(const char* who, const void* a, const void* b, const void* c, i
 
 }  // namespace
 
+// dX[m,k] (+)= (sum_{n < N <= 4} dY[m,n] W[n,k]) * elu'(Yprev[m,k]): the dgrad of a 1- or 3-wide head is an outer product,
+// not a GEMM -- one element per thread, consecutive threads on consecutive k
+__global__ void __launch_bounds__(256)
+small_n_dgrad_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ W, int ldw, const float* __restrict__ Yprev, int ldyp,
+                     float* __restrict__ dX, int lddx, int M, int N, int K, int accumulate) {
+  const int64_t total = (int64_t)M * K;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / K;
+    const int k = (int)(i - m * K);
+    float acc = 0.0f;
+    for (int n = 0; n < N; ++n) acc = fmaf(dY[m * lddy + n], __ldg(W + (int64_t)n * ldw + k), acc);
+    if (Yprev) {
+      const float y = Yprev[m * ldyp + k];
+      acc *= (y > 0.0f ? 1.0f : y + 1.0f);
+    }
+    float* o = dX + m * lddx + k;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
 extern "C" {
 
 int b200_linear_forward(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int M, int N,
@@ -315,6 +335,14 @@ int b200_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const 
   // dX[M,K] = dY[M,N] . W[N,K]: output cols = K, reduction = N
   if (int rc = check_common("b200_linear_dgrad", dY, W, dX, lddy, ldw, M, N, K)) return rc;
   B200_CHECK_ARG(lddy >= N && ldw >= K && lddx >= K, "b200_linear_dgrad: bad leading dimension");
+  if (N <= 4) {      // value / estimator heads: a rank-N outer product, pure streaming (exact fp32 in every mode)
+    const int64_t total = (int64_t)M * K;
+    int blocks = (int)((total + 255) / 256);
+    blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
+    small_n_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dY, lddy, W, ldw, Yprev, ldyp, dX, lddx, M, N, K, accumulate);
+    B200_CHECK_LAUNCH("small_n_dgrad_kernel");
+    return 0;
+  }
   GemmArgs g{};
   g.A = dY; g.B = W; g.C = dX; g.aux = Yprev;
   g.lda = lddy; g.ldb = ldw; g.ldc = lddx; g.ldaux = ldyp;

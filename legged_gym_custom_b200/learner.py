@@ -201,6 +201,10 @@ class PPO:
         self.p_priv, self.p_crit, self.p_scan = z(self.batch, ceil4(s.d_priv)), z(self.batch, s.d_crit), z(self.batch, s.d_scan)
         self.p_est, self.p_act = z(self.batch, ceil4(s.d_est)), z(self.batch, s.d_act)
         self.p_val, self.p_ret, self.p_logp, self.p_adv = z(self.batch), z(self.batch), z(self.batch), z(self.batch)
+        # adaptation-encoder latent of every (permuted) sample: the encoder's weights do not move during a PPO update
+        # (ppo.py:213-214 runs it under inference_mode; only update_dagger trains it) and every epoch revisits the same
+        # samples in the same minibatch slots, so it is evaluated ONCE per update instead of once per minibatch pass
+        self.p_lat_a = z(self.batch, ac.latent_dim)
         self.roll_ws = Workspace(self.device)          # rollout-time activations (M = N)
         self.upd_ws = Workspace(self.device)           # update-time activations  (M = minibatch)
         self.loss_sums = z(8)
@@ -299,6 +303,8 @@ class PPO:
         g(_p(s.actions), s.d_act, _p(self.p_act), s.d_act, s.d_act)
         for src, dst in ((s.values, self.p_val), (s.returns, self.p_ret), (s.actions_log_prob, self.p_logp), (s.advantages, self.p_adv)):
             g(_p(src), 1, _p(dst), 1, 1)
+        # the adaptation-encoder latent slab (ppo.py:213-214, see init_storage): one launch over the whole batch
+        ac.fwd_adapt(self.upd_ws, _p(self.p_actor_in), ac.ld_actor_in, _p(self.p_lat_a), ac.latent_dim, B)
 
     def _reg_coef(self):
         stage = min(max((self.total_updates - self.start_step) / self.duration, 0.0), 1.0)     # ppo.py:219-220
@@ -324,9 +330,10 @@ class PPO:
         tgt_est, ldte = _p(self.p_est) + 4 * r0 * self.p_est.shape[1], self.p_est.shape[1]
         L, A = ac.latent_dim, s.d_act
         mu, val = ws.get("mu", M, A), ws.get("val", M, 4)
-        lat_a, pred, dpred = ws.get("lat_a", M, L), ws.get("pred", M, 4), ws.get("dpred", M, 4)
+        pred, dpred = ws.get("pred", M, 4), ws.get("dpred", M, 4)
         dmu, dval, dlat, dscan = ws.get("dmu", M, A), ws.get("dval", M, 4), ws.get("dlat", M, L), ws.get("dscan", M, ac.scan_latent_dim)
-        s_est, s_crit, s_ad = self._fork(3)
+        lat_a_ptr = _p(self.p_lat_a) + 4 * r0 * L
+        s_est, s_crit = self._fork(2)
         # estimator: forward, loss, backward, own optimiser (ppo.py:224-231) -- fully independent chain
         with self._on(s_est):
             est.fwd(ws, X, ld, _p(pred), 4, M)
@@ -336,20 +343,18 @@ class PPO:
             self._adam(est.group)
         with self._on(s_crit):
             ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
-        with self._on(s_ad):
-            ac.fwd_adapt(ws, X, ld, _p(lat_a), L, M)                  # torch.inference_mode() in the reference (ppo.py:213-214)
         # main stream: encoders -> actor
         ac.fwd_priv(ws, priv, ldp, X + 4 * ac.col_latent, ld, M)
         ac.fwd_scan(ws, scan, s.d_scan, X + 4 * ac.col_scan, ld, M)
         ac.fwd_actor(ws, X, ld, _p(mu), A, M)
-        self._join([s_crit, s_ad])
+        self._join([s_crit])
         # PPO loss head (ppo.py:249-270)
         a = _lib.PpoLossArgs()
         a.mu, a.ldmu, a.std, a.actions = _p(mu), A, ac.main.ptr("std"), _p(self.p_act) + 4 * r0 * A
         a.old_logp, a.adv = _p(self.p_logp) + 4 * r0, _p(self.p_adv) + 4 * r0
         a.returns, a.target_values = _p(self.p_ret) + 4 * r0, _p(self.p_val) + 4 * r0
         a.value, a.ldv = _p(val), 4
-        a.latent_p, a.ldlp, a.latent_a, a.ldla = X + 4 * ac.col_latent, ld, _p(lat_a), L
+        a.latent_p, a.ldlp, a.latent_a, a.ldla = X + 4 * ac.col_latent, ld, lat_a_ptr, L
         a.dmu, a.lddmu, a.dvalue, a.lddv, a.dlatent_p, a.lddlp = _p(dmu), A, _p(dval), 4, _p(dlat), L
         a.dstd, a.sums = ac.main.ptr("std", "grads"), _p(self.loss_sums)
         a.M, a.A, a.L = M, A, L
