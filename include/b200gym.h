@@ -233,6 +233,27 @@ int b200_abi_version(void);
 int b200_env_params_size(void);      /* sizeof(B200EnvParams), for the binding's self-check */
 int b200_env_buffers_size(void);
 
+/* Env-creation-time domain randomisation and buffer initialisation: replaces the host loops of
+ * LeggedRobot._process_rigid_shape_props / _process_rigid_body_props (legged_robot.py:306-380: friction buckets, added base
+ * mass, centre-of-mass shift), the kp/kd multipliers of _init_buffers (:696-701), _get_env_origins (:897-930: initial
+ * terrain levels / types / origins, or the plane grid).  Draws are keyed Philox (sites 8-12, env = index, step = 0). */
+typedef struct B200InitParams {
+  int32_t randomize_friction;    /* 0: every env gets dynamic_friction */
+  float friction_lo, friction_hi, dynamic_friction;
+  int32_t randomize_base_mass;
+  float mass_lo, mass_hi;
+  int32_t randomize_com;
+  float com_lo, com_hi;
+  float kp_kd_lo, kp_kd_hi;
+  int32_t num_init_levels;       /* terrain: levels ~ randint(0, num_init_levels); <= 0: no height field (plane grid) */
+  int32_t terrain_cols;
+  float env_spacing;             /* plane grid */
+  int32_t grid_cols;             /* plane grid: floor(sqrt(N)) */
+} B200InitParams;
+/* Writes priv_friction, priv_mass_params, kp_kd_multipliers, terrain_levels, terrain_types, env_origins (the const
+ * qualifiers of those B200EnvBuffers members describe the STEP kernels; this call is their producer). */
+int b200_env_init_randomisation(B200Env* env, const B200EnvBuffers* bufs, const B200InitParams* init, void* stream);
+
 /* Handle lifetime. Copies `params`; `device` is the CUDA ordinal. */
 int b200_env_create(const B200EnvParams* params, int device, B200Env** out);
 int b200_env_destroy(B200Env* env);

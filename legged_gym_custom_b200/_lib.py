@@ -3,7 +3,7 @@ library is missing or an entry point is absent, importing a product class raises
 import ctypes as C
 import os
 
-from .params import EnvBuffers, EnvParams
+from .params import EnvBuffers, EnvParams, InitParams
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200gym.so")
 
@@ -15,6 +15,7 @@ SYMBOLS = {
     "b200_env_buffers_size": (C.c_int, []),
     "b200_env_create": (C.c_int, [C.POINTER(EnvParams), C.c_int, C.POINTER(C.c_void_p)]),
     "b200_env_destroy": (C.c_int, [C.c_void_p]),
+    "b200_env_init_randomisation": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.POINTER(InitParams), C.c_void_p]),
     "b200_env_force_generic_layout": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_env_set_phase_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_pd_torques": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_int, C.c_void_p]),

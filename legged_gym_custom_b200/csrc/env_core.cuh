@@ -1050,6 +1050,41 @@ B200_HD void env_reset_only(const B200EnvParams& P, const B200EnvBuffers& B, int
   B.reset_buf[e] = 1;
 }
 
+// ---- env-creation-time randomisation of one env (legged_robot.py:306-380, :696-701, :897-930) ----
+B200_HD void env_init_one(const B200EnvParams& P, const B200EnvBuffers& B, const B200InitParams& I, int e) {
+  const uint32_t ue = (uint32_t)e;
+  float fr = I.dynamic_friction;
+  if (I.randomize_friction) {                            // 64 buckets ~ U(lo, hi); every env picks one
+    const uint32_t bucket = keyed_u32(P.seed, SITE_INIT_FRICTION_PICK, 0, ue, 0) % 64u;
+    fr = (I.friction_hi - I.friction_lo) * keyed_uniform(P.seed, SITE_INIT_FRICTION_BUCKET, 0, bucket, 0) + I.friction_lo;
+  }
+  const_cast<float*>(B.priv_friction)[e] = fr;
+  float* mp = const_cast<float*>(B.priv_mass_params) + (int64_t)e * 4;
+  mp[0] = I.randomize_base_mass ? (I.mass_hi - I.mass_lo) * keyed_uniform(P.seed, SITE_INIT_MASS, 0, ue, 0) + I.mass_lo : 0.0f;
+  for (int i = 1; i < 4; ++i)
+    mp[i] = I.randomize_com ? (I.com_hi - I.com_lo) * keyed_uniform(P.seed, SITE_INIT_MASS, 0, ue, i) + I.com_lo : 0.0f;
+  float* kpkd = const_cast<float*>(B.kp_kd_multipliers);
+  for (int d = 0; d < B200_NUM_DOF; ++d) {
+    kpkd[(int64_t)e * B200_NUM_DOF + d] = (I.kp_kd_hi - I.kp_kd_lo) * keyed_uniform(P.seed, SITE_INIT_KPKD, 0, ue, d) + I.kp_kd_lo;
+    kpkd[((int64_t)P.num_envs + e) * B200_NUM_DOF + d] =
+        (I.kp_kd_hi - I.kp_kd_lo) * keyed_uniform(P.seed, SITE_INIT_KPKD, 0, ue, B200_NUM_DOF + d) + I.kp_kd_lo;
+  }
+  if (I.num_init_levels > 0) {                           // _get_env_origins with a height field (legged_robot.py:904-917)
+    const int64_t level = (int64_t)(keyed_u32(P.seed, SITE_INIT_LEVEL, 0, ue, 0) % (uint32_t)I.num_init_levels);
+    const int64_t type = (int64_t)floorf((float)e / (float)((double)P.num_envs / (double)I.terrain_cols));
+    B.terrain_levels[e] = level;
+    const_cast<int64_t*>(B.terrain_types)[e] = type;
+    const float* o = B.terrain_origins + (level * I.terrain_cols + type) * 3;
+    for (int i = 0; i < 3; ++i) B.env_origins[(int64_t)e * 3 + i] = B200_LDG(o + i);
+  } else {                                               // plane: grid of env_spacing (legged_robot.py:919-930)
+    B.env_origins[(int64_t)e * 3 + 0] = I.env_spacing * (float)(e / I.grid_cols);
+    B.env_origins[(int64_t)e * 3 + 1] = I.env_spacing * (float)(e % I.grid_cols);
+    B.env_origins[(int64_t)e * 3 + 2] = 0.0f;
+    B.terrain_levels[e] = 0;
+    const_cast<int64_t*>(B.terrain_types)[e] = 0;
+  }
+}
+
 // ---- K1: action clip + PD torques, one (env, dof) element (legged_robot.py:74-75, :440-478) ----
 B200_HD void pd_torque_element(const B200EnvParams& P, const B200EnvBuffers& B, const float* actions_in, int clip_and_store,
                                int64_t idx) {

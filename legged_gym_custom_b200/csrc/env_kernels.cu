@@ -152,6 +152,12 @@ reset_all_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant_
   env_reset_only(P, B, e, step, init_done);
 }
 
+__global__ void __launch_bounds__(128)
+env_init_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, const __grid_constant__ B200InitParams I) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < P.num_envs) env_init_one(P, B, I, e);
+}
+
 __global__ void __launch_bounds__(256)
 heights_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,6 +409,17 @@ int b200_reset_all(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step
   B200_CHECK_LAUNCH("reset_all_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");
+  return 0;
+}
+
+int b200_env_init_randomisation(B200Env* env, const B200EnvBuffers* bufs, const B200InitParams* init, void* stream) {
+  if (int rc = check_bufs(env, bufs, "b200_env_init_randomisation")) return rc;
+  B200_CHECK_ARG(init, "b200_env_init_randomisation: null init params");
+  B200_CHECK_ARG(init->num_init_levels <= 0 || (env->p.has_height_samples && init->terrain_cols > 0 && bufs->terrain_origins),
+                 "b200_env_init_randomisation: terrain levels need terrain_origins / terrain_cols");
+  B200_CHECK_ARG(init->num_init_levels > 0 || init->grid_cols > 0, "b200_env_init_randomisation: grid_cols must be > 0 on a plane");
+  env_init_kernel<<<(env->p.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, *bufs, *init);
+  B200_CHECK_LAUNCH("env_init_kernel");
   return 0;
 }
 

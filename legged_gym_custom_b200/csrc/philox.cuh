@@ -18,7 +18,13 @@ enum B200DrawSite {
   SITE_RESET_ROOT = 4,    // legged_robot.py:520 (xy, only with custom origins) then :526 (6 velocities)
   SITE_CMD_RESET = 5,     // go2.py:230 -> _resample_commands
   SITE_OBS_NOISE = 6,     // go2.py:519 rand_like; lanes 0..num_proprio-1
-  SITE_ACTION_NOISE = 7   // actor_critic.py:204 Normal.sample; lanes 2a, 2a+1
+  SITE_ACTION_NOISE = 7,  // actor_critic.py:204 Normal.sample; lanes 2a, 2a+1
+  // env-creation-time draws (step = 0)
+  SITE_INIT_FRICTION_BUCKET = 8,   // legged_robot.py:318-320: env = bucket id (64 buckets), lane 0
+  SITE_INIT_FRICTION_PICK = 9,     // legged_robot.py:319 randint(0, 64): lane 0 (raw u32 % 64)
+  SITE_INIT_MASS = 10,             // legged_robot.py:363-372: lane 0 added mass, lanes 1..3 centre-of-mass shift
+  SITE_INIT_KPKD = 11,             // legged_robot.py:696-701: lanes 0..11 kp, 12..23 kd
+  SITE_INIT_LEVEL = 12             // legged_robot.py:909 randint(0, max_init_level + 1): lane 0 (raw u32 % count)
 };
 
 struct Philox4 {

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib, synth, terrain as terrain_mod
 from .buffers import BufferSet
-from .params import NUM_BODIES, NUM_DOF, REWARD_INDEX, REWARD_TERMS, env_params_from_cfg
+from .params import NUM_BODIES, NUM_DOF, REWARD_INDEX, REWARD_TERMS, env_params_from_cfg, init_params_from_cfg
 
 
 class SyntheticPhysX:
@@ -136,45 +136,15 @@ class Go2Env:
                                                                     decimation=p.decimation)
         self.init_done = True
 
-    # ---- env-creation-time randomisation (legged_robot.py:306-380, :687-701, :897-930); host torch, runs once
+    # ---- env-creation-time randomisation (legged_robot.py:306-380, :696-701, :897-930): one kernel over the envs
+    #      (b200_env_init_randomisation, keyed Philox draws) instead of the reference's per-env Python loop
     def _init_domain_randomisation(self, cfg, hs, origins, seed):
-        p, b, N = self.params, self.bufs, self.num_envs
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        dr = cfg.domain_rand
-        if getattr(dr, "randomize_friction", False):
-            lo, hi = dr.friction_range
-            buckets = (hi - lo) * torch.rand(64, 1, generator=g) + lo
-            b["priv_friction"].copy_(buckets[torch.randint(0, 64, (N,), generator=g)])
-        else:
-            b["priv_friction"].fill_(cfg.terrain.dynamic_friction)
-        mass = torch.zeros(N, 4)
-        if getattr(dr, "randomize_base_mass", False):
-            lo, hi = dr.added_mass_range
-            mass[:, 0] = (hi - lo) * torch.rand(N, generator=g) + lo
-        if getattr(dr, "randomize_center_of_mass", False):
-            lo, hi = dr.added_com_range
-            mass[:, 1:] = (hi - lo) * torch.rand(N, 3, generator=g) + lo
-        b["priv_mass_params"].copy_(mass)
-        lo, hi = getattr(dr, "kp_kd_range", (1.0, 1.0))
-        b["kp_kd_multipliers"].copy_((hi - lo) * torch.rand(2, N, NUM_DOF, generator=g) + lo)
+        b = self.bufs
         if hs is not None:
             b["height_samples"].copy_(torch.from_numpy(hs))
             b["terrain_origins"].copy_(torch.from_numpy(origins))
-            ter = cfg.terrain
-            max_init = ter.max_init_terrain_level if ter.curriculum else ter.num_rows - 1
-            levels = torch.randint(0, max_init + 1, (N,), generator=g)
-            types = torch.div(torch.arange(N), (N / ter.num_cols), rounding_mode="floor").to(torch.long)
-            b["terrain_levels"].copy_(levels)
-            b["terrain_types"].copy_(types)
-            b["env_origins"].copy_(torch.from_numpy(origins)[levels, types])
-        else:
-            cols = np.floor(np.sqrt(N))
-            rows = np.ceil(N / cols)
-            xx, yy = torch.meshgrid(torch.arange(rows), torch.arange(cols), indexing="ij")
-            o = torch.zeros(N, 3)
-            o[:, 0] = cfg.env.env_spacing * xx.flatten()[:N]
-            o[:, 1] = cfg.env.env_spacing * yy.flatten()[:N]
-            b["env_origins"].copy_(o)
+        self.init_params = init_params_from_cfg(cfg, self.num_envs, hs is not None)
+        _lib.check(self.lib.b200_env_init_randomisation(self._handle, C.byref(b.struct), C.byref(self.init_params), _lib.stream_ptr()))
 
     def __del__(self):
         try:

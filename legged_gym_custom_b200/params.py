@@ -96,6 +96,37 @@ class EnvBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BUFFER_FIELDS]
 
 
+class InitParams(C.Structure):
+    """B200InitParams (include/b200gym.h): env-creation-time randomisation constants."""
+    _fields_ = [("randomize_friction", C.c_int32), ("friction_lo", C.c_float), ("friction_hi", C.c_float), ("dynamic_friction", C.c_float),
+                ("randomize_base_mass", C.c_int32), ("mass_lo", C.c_float), ("mass_hi", C.c_float),
+                ("randomize_com", C.c_int32), ("com_lo", C.c_float), ("com_hi", C.c_float),
+                ("kp_kd_lo", C.c_float), ("kp_kd_hi", C.c_float), ("num_init_levels", C.c_int32), ("terrain_cols", C.c_int32),
+                ("env_spacing", C.c_float), ("grid_cols", C.c_int32)]
+
+
+def init_params_from_cfg(cfg, num_envs, has_height_field):
+    """legged_robot.py:306-380 (friction / mass / com ranges), :696-701 (kp_kd_range), :897-930 (origins)."""
+    dr, ter = cfg.domain_rand, cfg.terrain
+    ip = InitParams()
+    ip.randomize_friction = int(bool(getattr(dr, "randomize_friction", False)))
+    ip.friction_lo, ip.friction_hi = getattr(dr, "friction_range", (1.0, 1.0))
+    ip.dynamic_friction = float(getattr(ter, "dynamic_friction", 1.0))
+    ip.randomize_base_mass = int(bool(getattr(dr, "randomize_base_mass", False)))
+    ip.mass_lo, ip.mass_hi = getattr(dr, "added_mass_range", (0.0, 0.0))
+    ip.randomize_com = int(bool(getattr(dr, "randomize_center_of_mass", False)))
+    ip.com_lo, ip.com_hi = getattr(dr, "added_com_range", (0.0, 0.0))
+    ip.kp_kd_lo, ip.kp_kd_hi = getattr(dr, "kp_kd_range", (1.0, 1.0))
+    if has_height_field:
+        max_init = ter.max_init_terrain_level if ter.curriculum else ter.num_rows - 1
+        ip.num_init_levels, ip.terrain_cols = int(max_init) + 1, int(ter.num_cols)
+    else:
+        ip.num_init_levels, ip.terrain_cols = 0, 0
+    ip.env_spacing = float(getattr(cfg.env, "env_spacing", 3.0))
+    ip.grid_cols = int(np.floor(np.sqrt(num_envs)))
+    return ip
+
+
 def sqrt_threshold_squared(t):
     """largest float32 s with sqrt_rn(s) <= t, so that  sqrt(s) > t  <=>  s > result  (exactly, for every float32 s)"""
     t = np.float32(t)

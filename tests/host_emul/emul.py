@@ -3,7 +3,7 @@ import ctypes as C
 import os
 import subprocess
 
-from legged_gym_custom_b200.params import EnvBuffers, EnvParams
+from legged_gym_custom_b200.params import EnvBuffers, EnvParams, InitParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_env_emul.so")
@@ -27,5 +27,6 @@ def load():
     lib.emul_pd_torques.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_void_p, C.c_int]
     lib.emul_post_physics_step.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64]
     lib.emul_post_physics_step_variant.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64, C.c_int]
+    lib.emul_env_init.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(InitParams)]
     lib.emul_reset_all.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64, C.c_int]
     return lib

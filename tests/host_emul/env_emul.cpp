@@ -81,6 +81,11 @@ int emul_post_physics_step(const B200EnvParams* p, const B200EnvBuffers* b, int6
   return emul_post_physics_step_variant(p, b, step, 0);
 }
 
+int emul_env_init(const B200EnvParams* p, const B200EnvBuffers* b, const B200InitParams* init) {
+  for (int e = 0; e < p->num_envs; ++e) env_init_one(*p, *b, *init, e);
+  return 0;
+}
+
 int emul_reset_all(const B200EnvParams* p, const B200EnvBuffers* b, int64_t step, int init_done) {
   for (int e = 0; e < p->num_envs; ++e) env_reset_only(*p, *b, e, step, init_done);
   extras(*p, *b);

@@ -1,0 +1,76 @@
+"""OnPolicyRunner bookkeeping and checkpoints (on_policy_runner.py:163-173, :283-297): a
+checkpoint carries the actor-critic, the estimator, all three optimisers and `total_updates` (the reference drops the
+last three), restores them bit for bit into a fresh runner, keeps the reference's keys, and a reference-format checkpoint
+(model + per-tensor torch optimiser state) still loads its weights.  Episode statistics are accumulated on the device."""
+import os
+
+import pytest
+import torch
+
+from legged_gym_custom_b200 import configs
+from legged_gym_custom_b200.env import Go2Env
+from legged_gym_custom_b200.runner import OnPolicyRunner, class_to_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _runner(log_dir=None, seed=5):
+    env_cfg, train_cfg = configs.TASKS["go2_parkour"]
+
+    class Cfg(env_cfg):
+        class env(env_cfg.env):
+            num_envs = 256
+    env = Go2Env(Cfg, sim_device=DEV, seed=seed)
+    tc = class_to_dict(train_cfg)
+    tc["runner"]["resume"] = False
+    return OnPolicyRunner(env, tc, log_dir=log_dir, device=DEV)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    a = _runner()
+    for it in range(3):                                   # it 0 is a DAgger iteration, 1-2 are PPO updates
+        a.iteration(it)
+    a.current_learning_iteration = 3
+    path = os.path.join(tmp_path, "model_3.pt")
+    a.save(path, infos={"note": "x"})
+    ck = torch.load(path, map_location="cpu")
+    assert {"model_state_dict", "optimizer_state_dict", "iter", "infos"} <= set(ck)          # the reference's keys
+    assert {"estimator_state_dict", "estimator_optimizer_state_dict", "adaptation_optimizer_state_dict", "total_updates"} <= set(ck)
+    b = _runner(seed=6)
+    assert b.load(path) == {"note": "x"}
+    assert b.current_learning_iteration == 3 and b.alg.total_updates == a.alg.total_updates == 3.0
+    for ga, gb in ((a.alg.actor_critic.main, b.alg.actor_critic.main), (a.alg.actor_critic.adapt, b.alg.actor_critic.adapt),
+                   (a.alg.estimator.group, b.alg.estimator.group)):
+        assert torch.equal(ga.params, gb.params) and torch.equal(ga.exp_avg, gb.exp_avg) and torch.equal(ga.exp_avg_sq, gb.exp_avg_sq)
+        assert torch.equal(ga.state, gb.state)
+    # same weights -> same deterministic policy
+    obs = a.env.get_observations()
+    pa = a.get_inference_policy()
+    pb = b.get_inference_policy()
+    args = (obs, a.env.get_privileged_observations(), a.env.get_estimated_observations(), a.env.get_scan_observations())
+    try:
+        ya, yb = pa(*args), pb(*args)
+    except TypeError:
+        ya, yb = pa(obs), pb(obs)
+    assert torch.equal(ya, yb)
+
+
+def test_reference_format_checkpoint_loads_weights(tmp_path):
+    a, b = _runner(), _runner(seed=9)
+    sd = {k: v.clone() for k, v in a.alg.actor_critic.state_dict().items()}
+    path = os.path.join(tmp_path, "ref.pt")
+    torch.save({"model_state_dict": sd, "optimizer_state_dict": {"state": {}, "param_groups": [{"lr": 1e-3}]}, "iter": 7, "infos": None}, path)
+    b.load(path)
+    assert b.current_learning_iteration == 7
+    for k, v in b.alg.actor_critic.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_episode_statistics_stay_on_device(tmp_path):
+    r = _runner(log_dir=str(tmp_path))
+    r.writer = None
+    r.iteration(0)
+    assert r._ep_stats.is_cuda and r._cur_rew.is_cuda            # no per-step .cpu() (on_policy_runner.py:163-173)
+    srew, slen, cnt = r._ep_stats.tolist()
+    assert cnt >= 0 and slen >= cnt
