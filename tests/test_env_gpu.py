@@ -66,9 +66,12 @@ def test_cuda_env_matches_reference_golden(task, force_generic):
     env.close()
 
 
-@pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 4096, 3), ("go2_parkour_finetune", 1000, 2), ("go2", 777, 2)])
+@pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 4096, 3), ("go2_parkour_finetune", 1000, 2), ("go2", 777, 2),
+                                                 ("go2_parkour", 1, 2), ("go2_parkour", 7, 2), ("go2_parkour", 9, 2),
+                                                 ("go2_parkour", 65536, 1)])
 def test_cuda_env_matches_oracle_at_scale(task, num_envs, steps):
-    """BASELINE config sizes (4096 envs), ragged sizes (not a multiple of the CTA's 4 envs), all three tasks."""
+    """BASELINE config sizes (4096 envs; 65536 = the top of the env-count sweep), ragged sizes (not a multiple of the CTA's
+    8 envs), fewer envs than one CTA holds, all three tasks."""
     cfg = configs.TASKS[task][0]
     hs, origins = gu.terrain_for(task)
     p = env_params_from_cfg(cfg, num_envs=num_envs, seed=99, hs_shape=None if hs is None else hs.shape)
@@ -91,7 +94,7 @@ def test_cuda_env_matches_oracle_at_scale(task, num_envs, steps):
         env.step(actions, frames, step)
         gu.check_step(env.bufs, gu.oracle_expected(orc, out), t)
         total_resets += out["reset_count"]
-    assert total_resets > 0
+    assert total_resets > 0 or num_envs < 64
     env.close()
 
 

@@ -88,7 +88,7 @@ def test_kernel_source_every_reward_term_active(lib):
         gu.check_step(bufs, gu.oracle_expected(orc, out), t)
 
 
-@pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 1500, 3), ("go2", 333, 2)])
+@pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 1500, 3), ("go2", 333, 2), ("go2_parkour", 1, 2), ("go2_parkour", 9, 2)])
 def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
     """same harness as tests/test_env_gpu.py::test_cuda_env_matches_oracle_at_scale, on the host emulator."""
     import state_util as su
@@ -123,4 +123,4 @@ def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
         lib.emul_post_physics_step(C.byref(p), C.byref(bufs.struct), step)
         gu.check_step(bufs, gu.oracle_expected(orc, out), t)
         total += out["reset_count"]
-    assert total > 0
+    assert total > 0 or num_envs < 64
