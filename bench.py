@@ -81,7 +81,7 @@ class Profile:
     def hook(self, name, raw, args):
         from legged_gym_custom_b200 import _lib
         if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version",
-                    "b200_tc_set_pair_mode", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_tc_linear_supported"):
+                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_tc_linear_supported"):
             return raw(*args)
         self.count += _lib.LAUNCHES.get(name, 1)
         self.by_entry[name] = self.by_entry.get(name, 0) + _lib.LAUNCHES.get(name, 1)
@@ -184,6 +184,8 @@ def run_b200(args):
     from legged_gym_custom_b200 import _lib
     if args.no_pairs:
         _lib.lib().b200_tc_set_pair_mode(0)
+    if args.pdl:
+        _lib.lib().b200_tc_set_pdl(1)
     prof = Profile(args.num_envs)
     _lib.lib().hook = prof.hook
     env, runner = build_runner(args, rank, world, device)
@@ -466,6 +468,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
+    ap.add_argument("--pdl", action="store_true", help="launch the tcgen05 GEMMs with programmatic dependent launch (A/B; default off)")
     ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":

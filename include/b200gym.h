@@ -335,6 +335,11 @@ int b200_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float*
 /* Large forward / dgrad problems run on CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA stages half of B);
  * `on` = 0 forces the single-CTA kernels everywhere (A/B measurements and tests).  Returns 0. */
 int b200_tc_set_pair_mode(int on);
+/* Optional: launch the tcgen05 GEMMs with programmatic stream serialisation (PDL): each triggers its dependents at entry
+ * and waits for its predecessor (griddepcontrol.wait) only after its prologue, so barrier init / TMEM allocation /
+ * descriptor prefetch overlap the previous kernel's tail.  Off by default: measured neutral-to-negative for the update
+ * (early-resident CTAs take SMs away from the kernels of the side streams).  Returns 0. */
+int b200_tc_set_pdl(int on);
 int b200_tc_linear_supported(int M, int N, int K);
 int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
                            int M, int N, int K, int act, void* stream);

@@ -218,6 +218,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int STG_PITCH = 36;                                                // floats per staged row (32 + 4 pad)
   float* stage = red + (MODE == NN ? 2 * 4 * BN : 0);                          // [8 epilogue warps][32 rows][STG_PITCH]
 
+  // Programmatic dependent launch: let the NEXT kernel of the stream start launching now (its CTAs land on each SM as ours
+  // leave and run their prologue there); our own reads / writes of global memory wait below until the PREVIOUS kernel of
+  // the stream has completed and flushed (griddepcontrol.wait).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BMT - 1) / BMT, n_tiles = (g.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
@@ -250,6 +254,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -529,6 +534,8 @@ int num_sms() {
   return n;
 }
 
+int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
+
 template <int MODE, int BN, bool PAIR = false>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int splits, cudaStream_t st, const char* name) {
   using Cfg = TileCfg<BN, PAIR>;
@@ -548,26 +555,31 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
   int workers = (PAIR ? num_sms() / 2 : num_sms()) / (splits > 1 ? splits : 1);
   workers = workers < 1 ? 1 : workers;
   workers = tiles < workers ? tiles : workers;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? 2 * workers : workers, splits);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl) {                                               // overlap our prologue with the previous kernel's tail
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (PAIR) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * workers, splits);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;      // the pair: two CTAs of one TPC
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
-    if (e != cudaSuccess) {
-      b200_set_error("%s: cudaLaunchKernelEx: %s", name, cudaGetErrorString(e));
-      return (int)e;
-    }
-  } else {
-    kern<<<dim3(workers, splits), NUM_THREADS, smem, st>>>(ta, tb, g);
+    attr[na].id = cudaLaunchAttributeClusterDimension;      // the pair: two CTAs of one TPC
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
+  if (e != cudaSuccess) {
+    b200_set_error("%s: cudaLaunchKernelEx: %s", name, cudaGetErrorString(e));
+    return (int)e;
   }
   B200_CHECK_LAUNCH(name);
   return 0;
@@ -624,6 +636,11 @@ int pick_bn(int rows, int cols, int split_k = 0) {
 }  // namespace
 
 extern "C" {
+
+int b200_tc_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
+  return 0;
+}
 
 int b200_tc_set_pair_mode(int on) {
   g_pair_mode = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 forward only (default), 2 forward + dgrad
