@@ -335,11 +335,18 @@ int b200_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float*
 /* Large forward / dgrad problems run on CTA pairs (tcgen05 cta_group::2, 256-row tiles, each CTA stages half of B);
  * `on` = 0 forces the single-CTA kernels everywhere (A/B measurements and tests).  Returns 0. */
 int b200_tc_set_pair_mode(int on);
+/* Profiling aid: the i-th tcgen05 GEMM launched after this call min/max-es its CTAs' %globaltimer (ns) into
+ * dev_buf[i] = {first CTA start, last CTA end} (device, uint64 [capacity][2]; the caller fills it with {~0, 0} before every
+ * run) and describes itself in host_meta[i] = {M, N, K, mode * 1000 + tile width (+ 500 for a CTA pair)} (host, int64
+ * [capacity][4], written at call time).  Capture-safe: a CUDA-graph node keeps the slot it was captured with.  NULL = off. */
+int b200_tc_set_trace(unsigned long long* dev_buf, long long* host_meta, int capacity);
 /* Optional: launch the tcgen05 GEMMs with programmatic stream serialisation (PDL): each triggers its dependents at entry
  * and waits for its predecessor (griddepcontrol.wait) only after its prologue, so barrier init / TMEM allocation /
  * descriptor prefetch overlap the previous kernel's tail.  Off by default: measured neutral-to-negative for the update
  * (early-resident CTAs take SMs away from the kernels of the side streams).  Returns 0. */
 int b200_tc_set_pdl(int on);
+/* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
+ * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */
 int b200_tc_linear_supported(int M, int N, int K);
 int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
                            int M, int N, int K, int act, void* stream);

@@ -52,7 +52,7 @@ struct GemmArgs {
   int lda, ldb, ldc, ldaux;
   int M, N, K;          // output rows, output cols, reduction length
   int act;              // NT: 0 none, 1 ELU
-  int accumulate;       // NN: dX += ...
+  int accumulate;       // NN: 0 overwrite dX, 1 add to dX, n > 1 add to its first n columns
   int red_per_split;    // TN: reduction rows per blockIdx.z
 };
 
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(WM* WN * 32) gemm_kernel(const GemmArgs g) {
               v *= (y > 0.0f ? 1.0f : y + 1.0f);                 // elu'(z) = 1 or exp(z) = y + 1
             }
             float* p = g.C + (int64_t)row * g.ldc + c;
-            *p = g.accumulate ? *p + v : v;
+            *p = (g.accumulate == 1 || c < g.accumulate) ? *p + v : v;    // 1 = every column, n > 1 = the first n columns
           } else {
             atomicAdd(g.C + (int64_t)row * g.ldc + c, v);
           }
@@ -310,7 +310,7 @@ small_n_dgrad_kernel(const float* __restrict__ dY, int lddy, const float* __rest
       acc *= (y > 0.0f ? 1.0f : y + 1.0f);
     }
     float* o = dX + m * lddx + k;
-    *o = accumulate ? *o + acc : acc;
+    *o = (accumulate == 1 || k < accumulate) ? *o + acc : acc;
   }
 }
 

@@ -180,6 +180,7 @@ struct TcArgs {
   int M, N, K;         // output rows, output cols, reduction
   int act, accumulate;
   int k_per_split;     // TN: reduction elements per blockIdx.y
+  unsigned long long* trace;   // optional launch timeline (b200_tc_set_trace): this launch's {min CTA start, max CTA end} in %globaltimer ns
 };
 
 // A-operand smem per stage: K-major  [BM rows][32]         = 16 KB
@@ -222,6 +223,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // leave and run their prologue there); our own reads / writes of global memory wait below until the PREVIOUS kernel of
   // the stream has completed and flushed (griddepcontrol.wait).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (g.trace && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    atomicMin(g.trace, t_);
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BMT - 1) / BMT, n_tiles = (g.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
@@ -414,9 +420,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (g.accumulate && row < g.M) {                    // rare (the actor's latent columns): row-per-lane access
             const float* crow = g.C + (int64_t)row * g.ldc + col0;
+            const int acc_cols = g.accumulate == 1 ? g.N : min(g.accumulate, g.N);   // 1 = every column, n > 1 = the first n
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) v[j] += crow[j];
+              if (col0 + j < acc_cols) v[j] += crow[j];
           }
         }
         // rows -> staging -> coalesced row segments
@@ -484,6 +491,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (g.trace && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    atomicMax(g.trace + 1, t_);
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -534,6 +546,13 @@ int num_sms() {
   return n;
 }
 
+// launch timeline (b200_tc_set_trace): launch i of the tcgen05 GEMMs since the call min/max-es its CTAs' %globaltimer into slot i
+// {start, end} of the caller's DEVICE buffer and describes itself in slot i {M, N, K, mode * 1000 + BN + (pair ? 500 : 0)} of the
+// caller's HOST array (a plain store at call time: capture-safe); under CUDA-graph replay a node keeps the slot it was captured with
+unsigned long long* g_trace = nullptr;
+long long* g_trace_meta = nullptr;
+int g_trace_cap = 0, g_trace_next = 0;
+
 int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
 
 template <int MODE, int BN, bool PAIR = false>
@@ -550,6 +569,15 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
       return (int)e;
     }
     done = true;
+  }
+  TcArgs gt = g;
+  if (g_trace && g_trace_next < g_trace_cap) {
+    const int i = g_trace_next++;
+    if (g_trace_meta) {
+      long long* m = g_trace_meta + 4 * (size_t)i;
+      m[0] = g.M; m[1] = g.N; m[2] = g.K; m[3] = MODE * 1000 + BN + (PAIR ? 500 : 0);
+    }
+    gt.trace = g_trace + 2 * (size_t)i;
   }
   const int tiles = ((g.M + Cfg::BMT - 1) / Cfg::BMT) * ((g.N + BN - 1) / BN);
   int workers = (PAIR ? num_sms() / 2 : num_sms()) / (splits > 1 ? splits : 1);
@@ -576,7 +604,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, gt);
   if (e != cudaSuccess) {
     b200_set_error("%s: cudaLaunchKernelEx: %s", name, cudaGetErrorString(e));
     return (int)e;
@@ -636,6 +664,14 @@ int pick_bn(int rows, int cols, int split_k = 0) {
 }  // namespace
 
 extern "C" {
+
+int b200_tc_set_trace(unsigned long long* dev_buf, long long* host_meta, int capacity) {
+  g_trace = dev_buf;
+  g_trace_meta = host_meta;
+  g_trace_cap = dev_buf ? capacity : 0;
+  g_trace_next = 0;
+  return 0;
+}
 
 int b200_tc_set_pdl(int on) {
   g_pdl = on ? 1 : 0;

@@ -331,9 +331,20 @@ class PPO:
         L, A = ac.latent_dim, s.d_act
         mu, val = ws.get("mu", M, A), ws.get("val", M, 4)
         pred, dpred = ws.get("pred", M, 4), ws.get("dpred", M, 4)
-        dmu, dval, dlat, dscan = ws.get("dmu", M, A), ws.get("dval", M, 4), ws.get("dlat", M, L), ws.get("dscan", M, ac.scan_latent_dim)
+        SL = ac.scan_latent_dim
+        assert ac.col_scan == ac.col_latent + L, "latent and scan-latent columns of the actor input must be adjacent"
+        dmu, dval = ws.get("dmu", M, A), ws.get("dval", M, 4)
+        dls = ws.get("dlatscan", M, L + SL)                  # d(loss)/d[latent | scan latent]: ONE dgrad of the actor's first layer
         lat_a_ptr = _p(self.p_lat_a) + 4 * r0 * L
-        s_est, s_crit = self._fork(2)
+        # Streams (the fork / join edges of the captured graph).  The critical path is encoders -> actor -> loss -> actor
+        # backward -> encoder backward; it runs on HIGH-priority streams (s_hi; the scan encoder beside it on s_scan) and
+        # is issued first, so the big estimator / critic GEMMs of the low-priority streams fill in around it instead of
+        # delaying it (measured with tools/trace_update.py: the actor's first layer used to start at 169 us of 741).
+        s_hi, s_scan, s_est, s_crit = self._fork(4)
+        with self._on(s_scan):
+            ac.fwd_scan(ws, scan, s.d_scan, X + 4 * ac.col_scan, ld, M)
+        with self._on(s_hi):
+            ac.fwd_priv(ws, priv, ldp, X + 4 * ac.col_latent, ld, M)
         # estimator: forward, loss, backward, own optimiser (ppo.py:224-231) -- fully independent chain
         with self._on(s_est):
             est.fwd(ws, X, ld, _p(pred), 4, M)
@@ -343,45 +354,50 @@ class PPO:
             self._adam(est.group)
         with self._on(s_crit):
             ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
-        # main stream: encoders -> actor
-        ac.fwd_priv(ws, priv, ldp, X + 4 * ac.col_latent, ld, M)
-        ac.fwd_scan(ws, scan, s.d_scan, X + 4 * ac.col_scan, ld, M)
-        ac.fwd_actor(ws, X, ld, _p(mu), A, M)
-        self._join([s_crit])
-        # PPO loss head (ppo.py:249-270)
-        a = _lib.PpoLossArgs()
-        a.mu, a.ldmu, a.std, a.actions = _p(mu), A, ac.main.ptr("std"), _p(self.p_act) + 4 * r0 * A
-        a.old_logp, a.adv = _p(self.p_logp) + 4 * r0, _p(self.p_adv) + 4 * r0
-        a.returns, a.target_values = _p(self.p_ret) + 4 * r0, _p(self.p_val) + 4 * r0
-        a.value, a.ldv = _p(val), 4
-        a.latent_p, a.ldlp, a.latent_a, a.ldla = X + 4 * ac.col_latent, ld, lat_a_ptr, L
-        a.dmu, a.lddmu, a.dvalue, a.lddv, a.dlatent_p, a.lddlp = _p(dmu), A, _p(dval), 4, _p(dlat), L
-        a.dstd, a.sums = ac.main.ptr("std", "grads"), _p(self.loss_sums)
-        a.M, a.A, a.L = M, A, L
-        a.clip, a.value_coef, a.entropy_coef, a.reg_coef = self.clip_param, self.value_loss_coef, self.entropy_coef, 0.0
-        a.use_clipped_value_loss, a.reg_coef_dev = int(self.use_clipped_value_loss), _p(self.reg_coef_dev)
-        _lib.check(self.lib.b200_ppo_loss(C.byref(a), _lib.stream_ptr()))
-        # backward: critic on its own stream; actor (input gradient only for the latent / scan-latent columns) and encoders here
-        self._fork_onto([s_crit])
+        with self._on(s_hi):
+            self._join([s_scan])
+            ac.fwd_actor(ws, X, ld, _p(mu), A, M)
+            self._join([s_crit])
+            # PPO loss head (ppo.py:249-270)
+            a = _lib.PpoLossArgs()
+            a.mu, a.ldmu, a.std, a.actions = _p(mu), A, ac.main.ptr("std"), _p(self.p_act) + 4 * r0 * A
+            a.old_logp, a.adv = _p(self.p_logp) + 4 * r0, _p(self.p_adv) + 4 * r0
+            a.returns, a.target_values = _p(self.p_ret) + 4 * r0, _p(self.p_val) + 4 * r0
+            a.value, a.ldv = _p(val), 4
+            a.latent_p, a.ldlp, a.latent_a, a.ldla = X + 4 * ac.col_latent, ld, lat_a_ptr, L
+            a.dmu, a.lddmu, a.dvalue, a.lddv, a.dlatent_p, a.lddlp = _p(dmu), A, _p(dval), 4, _p(dls), L + SL
+            a.dstd, a.sums = ac.main.ptr("std", "grads"), _p(self.loss_sums)
+            a.M, a.A, a.L = M, A, L
+            a.clip, a.value_coef, a.entropy_coef, a.reg_coef = self.clip_param, self.value_loss_coef, self.entropy_coef, 0.0
+            a.use_clipped_value_loss, a.reg_coef_dev = int(self.use_clipped_value_loss), _p(self.reg_coef_dev)
+            _lib.check(self.lib.b200_ppo_loss(C.byref(a), _lib.stream_ptr()))
+            # backward: critic on its own stream; actor (input gradient only for the latent / scan-latent columns) here
+            self._fork_onto([s_crit])
         with self._on(s_crit):
             chain_backward(k, ac.critic, ws, "c", crit, s.d_crit, _p(dval), 4, M)
-        chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M)
-        da0, lda0 = ws.ptr("da0", M, ceil4(ac.actor[0].N)), ceil4(ac.actor[0].N)
-        k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dlat), L, M, accumulate=1, wcol=ac.col_latent, K=L)
-        k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dscan), ac.scan_latent_dim, M, accumulate=0, wcol=ac.col_scan, K=ac.scan_latent_dim)
-        chain_backward(k, ac.priv, ws, "p", priv, ldp, _p(dlat), L, M)
-        chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dscan), ac.scan_latent_dim, M)
-        self._join([s_crit, s_est])
+        with self._on(s_hi):
+            chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M)
+            da0, lda0 = ws.ptr("da0", M, ceil4(ac.actor[0].N)), ceil4(ac.actor[0].N)
+            # columns [latent | scan latent] of the first layer's input gradient in one pass; the regulariser's gradient, which
+            # the loss head left in the first L columns, is accumulated (accumulate = number of leading columns)
+            k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dls), L + SL, M, accumulate=L, wcol=ac.col_latent, K=L + SL)
+            self._fork_onto([s_scan])
+            chain_backward(k, ac.priv, ws, "p", priv, ldp, _p(dls), L + SL, M)
+        with self._on(s_scan):
+            chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dls) + 4 * L, L + SL, M)
+        self._join([s_hi, s_scan, s_crit, s_est])
         self._adam(ac.main)
 
     # ---- side streams: estimator / critic / adaptation-encoder chains are independent of the actor chain until the loss
     #      head (and, for the backward, until Adam); forking them lets the small and medium kernels overlap.  Under
     #      CUDA-graph capture the event waits become the fork / join edges of the graph.
     def _fork(self, n):
+        """side streams, in this order: high-priority critical chain, high-priority scan encoder, estimator, critic"""
         if not self.use_streams:
             return [None] * n
         if not hasattr(self, "_side"):
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            lo, hi = 0, -1
+            self._side = [torch.cuda.Stream(device=self.device, priority=p) for p in (hi, hi, lo, lo)]
         self._fork_onto(self._side[:n])
         return self._side[:n]
 
