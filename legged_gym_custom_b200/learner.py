@@ -184,6 +184,8 @@ class PPO:
         self.use_device_counter = False
         self.use_graphs = False
         self.use_streams = True
+        self.defer_critic_join = False      # act(): leave the critic chain running until process_env_step (OnPolicyRunner sets it)
+        self._pending_critic = None
         self._graphs, self._graph_calls = {}, {}
 
     # ---- storage ------------------------------------------------------------------------------------
@@ -234,31 +236,53 @@ class PPO:
         x = ws.get("actor_in", N, ld)
         obs, privileged_obs, critic_obs = obs.contiguous(), privileged_obs.contiguous(), critic_obs.contiguous()
         true_estimated_obs, scan_obs = true_estimated_obs.contiguous(), scan_obs.contiguous()
-        self._copy_segments([
-            (_p(obs), s.d_obs, _p(s.observations[t]), s.d_obs, s.d_obs),
-            (_p(obs), s.d_obs, _p(x), ld, s.d_obs),
-            (_p(privileged_obs), s.d_priv, _p(s._priv[t]), s._priv.shape[2], s.d_priv),
-            (_p(critic_obs), s.d_crit, _p(s.critic_observations[t]), s.d_crit, s.d_crit),
-            (_p(true_estimated_obs), s.d_est, _p(s._est[t]), s._est.shape[2], s.d_est),
-            (_p(scan_obs), s.d_scan, _p(s.scan_observations[t]), s.d_scan, s.d_scan),
-        ], N)
         # estimated obs -> actor input (the rollout acts on the ESTIMATE, ppo.py:134-137); the estimator, the latent
-        # encoder, the scan encoder and the critic are independent until the actor's first layer
-        s_lat, s_scan, s_crit = self._fork(3)
-        est.fwd(ws, _p(x), ld, _p(x, ac.col_est), ld, N)
+        # encoder, the scan encoder and the critic are independent until the actor's first layer.  Estimator -> actor is the
+        # critical path (high-priority stream); the critic's value is not needed before process_env_step, so with
+        # `defer_critic_join` (the runner sets it) its chain keeps running under the env step's kernels.
+        if self._pending_critic is not None:              # act() called twice without process_env_step
+            self._join([self._pending_critic])
+            self._pending_critic = None
+        # The observation copies of RolloutStorage.add_transitions ride on the side streams: the estimator reads the env's
+        # obs buffer in place, [obs -> actor input, priv -> storage] precede the latent encoder, the rest precedes the critic.
+        s_hi, s_scan, s_lat, s_crit = self._fork(4)
+        with self._on(s_hi):
+            est.fwd(ws, _p(obs), s.d_obs, _p(x, ac.col_est), ld, N)
         with self._on(s_lat):
+            self._copy_segments([
+                (_p(obs), s.d_obs, _p(x), ld, s.d_obs),
+                (_p(privileged_obs), s.d_priv, _p(s._priv[t]), s._priv.shape[2], s.d_priv),
+            ], N)
             if adaptation_mode:
                 ac.fwd_adapt(ws, _p(x), ld, _p(x, ac.col_latent), ld, N)
             else:
                 ac.fwd_priv(ws, _p(s._priv[t]), s._priv.shape[2], _p(x, ac.col_latent), ld, N)
         with self._on(s_scan):
             ac.fwd_scan(ws, _p(scan_obs), s.d_scan, _p(x, ac.col_scan), ld, N)
-        with self._on(s_crit):
-            ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
-        self._join([s_lat, s_scan])
         mu = ws.get("mu", N, s.d_act)
-        ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
-        self._join([s_crit])
+        with self._on(s_hi):
+            self._join([s_lat, s_scan])
+            self._fork_onto([s_crit])                     # the critic's big first layer must not take the SMs before this point
+            ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
+        with self._on(s_crit):
+            self._copy_segments([
+                (_p(obs), s.d_obs, _p(s.observations[t]), s.d_obs, s.d_obs),
+                (_p(critic_obs), s.d_crit, _p(s.critic_observations[t]), s.d_crit, s.d_crit),
+                (_p(true_estimated_obs), s.d_est, _p(s._est[t]), s._est.shape[2], s.d_est),
+                (_p(scan_obs), s.d_scan, _p(s.scan_observations[t]), s.d_scan, s.d_scan),
+            ], N)
+            copied = None
+            if s_crit is not None:                        # the env's buffers may be overwritten (env.step) once THIS has run,
+                copied = torch.cuda.Event()               # even if the critic chain itself is still in flight
+                copied.record()
+            ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
+        self._join([s_hi])
+        if copied is not None:
+            torch.cuda.current_stream().wait_event(copied)
+        if self.defer_critic_join and s_crit is not None:
+            self._pending_critic = s_crit
+        else:
+            self._join([s_crit])
         if self.use_device_counter:
             _lib.check(self.lib.b200_sample_actions_dev(_p(mu), s.d_act, ac.main.ptr("std"), self.seed, C.c_void_p(self.act_counter_dev.data_ptr()),
                                                         _p(s.actions[t]), _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act,
@@ -274,6 +298,9 @@ class PPO:
         """ppo.py:156-171: time-out bootstrap + scalar part of add_transitions."""
         s = self.storage
         t = s.step
+        if self._pending_critic is not None:              # values[t] (time-out bootstrap below) come from the critic's stream
+            self._join([self._pending_critic])
+            self._pending_critic = None
         tmo = infos["time_outs"] if "time_outs" in infos else None
         p = lambda x: C.c_void_p(x.data_ptr())
         _lib.check(self.lib.b200_store_step_scalars(p(rewards), p(dones), p(tmo) if tmo is not None else None, p(s.values[t]), self.gamma,
@@ -392,7 +419,8 @@ class PPO:
     #      head (and, for the backward, until Adam); forking them lets the small and medium kernels overlap.  Under
     #      CUDA-graph capture the event waits become the fork / join edges of the graph.
     def _fork(self, n):
-        """side streams, in this order: high-priority critical chain, high-priority scan encoder, estimator, critic"""
+        """side streams, in this order: high-priority critical chain, high-priority scan encoder, estimator (update) / latent
+        encoder (rollout), critic"""
         if not self.use_streams:
             return [None] * n
         if not hasattr(self, "_side"):

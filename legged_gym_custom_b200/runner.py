@@ -45,6 +45,7 @@ class OnPolicyRunner:
         if process_group is not None:      # replicas start from rank 0's weights; afterwards identical reduced gradients keep them in sync
             from .dist import broadcast_parameters
             broadcast_parameters([actor_critic.main, actor_critic.adapt, estimator.group], process_group)
+        self.alg.defer_critic_join = True      # every act() of this runner is followed by process_env_step()
         self.dagger_update_freq = ac_["dagger_update_freq"]
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
         self.alg.init_storage(num_envs=env.num_envs, num_transitions_per_env=self.num_steps_per_env, total_obs_shape=[env.num_obs],
