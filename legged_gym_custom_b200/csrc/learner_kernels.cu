@@ -188,16 +188,41 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const __grid_con
     p.dvalue[(int64_t)i * p.lddv] = p.value_coef * dv * invM;
     // ROA regulariser: mean ||latent_p - latent_a||_2 (ppo.py:216)
     float n2 = 0.0f;
-    for (int l = 0; l < p.L; ++l) {
-      const float e = p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l];
-      n2 += e * e;
-    }
-    const float nrm = sqrtf(n2);
-    part[2] = nrm;
     const float reg_coef = p.reg_coef_dev ? p.reg_coef_dev[0] : p.reg_coef;
-    const float g = nrm > 0.0f ? reg_coef * invM / nrm : 0.0f;
-    for (int l = 0; l < p.L; ++l)
-      p.dlatent_p[(int64_t)i * p.lddlp + l] = g * (p.latent_p[(int64_t)i * p.ldlp + l] - p.latent_a[(int64_t)i * p.ldla + l]);
+    const float* latp = p.latent_p + (int64_t)i * p.ldlp;
+    const float* lata = p.latent_a + (int64_t)i * p.ldla;
+    float* dl = p.dlatent_p + (int64_t)i * p.lddlp;
+    constexpr int kL = 20;                                 // the go2 latent width: 5 x 16-byte vectors per row, loaded once
+    if (p.L == kL && (p.ldlp % 4 == 0) && (p.ldla % 4 == 0) && (p.lddlp % 4 == 0) &&
+        ((((uintptr_t)p.latent_p) | ((uintptr_t)p.latent_a) | ((uintptr_t)p.dlatent_p)) & 15) == 0) {
+      float4 e4[kL / 4];
+#pragma unroll
+      for (int l = 0; l < kL / 4; ++l) {
+        const float4 a4 = reinterpret_cast<const float4*>(latp)[l], b4 = reinterpret_cast<const float4*>(lata)[l];
+        e4[l] = make_float4(a4.x - b4.x, a4.y - b4.y, a4.z - b4.z, a4.w - b4.w);
+      }
+#pragma unroll
+      for (int l = 0; l < kL / 4; ++l) {                   // same summation order as the scalar loop
+        n2 += e4[l].x * e4[l].x;
+        n2 += e4[l].y * e4[l].y;
+        n2 += e4[l].z * e4[l].z;
+        n2 += e4[l].w * e4[l].w;
+      }
+      const float nrm = sqrtf(n2);
+      part[2] = nrm;
+      const float g = nrm > 0.0f ? reg_coef * invM / nrm : 0.0f;
+#pragma unroll
+      for (int l = 0; l < kL / 4; ++l) reinterpret_cast<float4*>(dl)[l] = make_float4(g * e4[l].x, g * e4[l].y, g * e4[l].z, g * e4[l].w);
+    } else {
+      for (int l = 0; l < p.L; ++l) {
+        const float e = latp[l] - lata[l];
+        n2 += e * e;
+      }
+      const float nrm = sqrtf(n2);
+      part[2] = nrm;
+      const float g = nrm > 0.0f ? reg_coef * invM / nrm : 0.0f;
+      for (int l = 0; l < p.L; ++l) dl[l] = g * (latp[l] - lata[l]);
+    }
     part[3] = ent;
   }
   // d(loss)/d(std): warp shuffle reduction, one shared-memory atomic per warp and action
@@ -296,14 +321,28 @@ clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict
   coef = (coef > 1.0f ? 1.0f : coef) * grad_scale;
   const float bc1 = (float)(1.0 - state[2]), bc2_sqrt = (float)sqrt(1.0 - state[3]);
   const float step_size = (float)state[4] / bc1;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const float gi = g[i] * coef;
-    const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-    g[i] = 0.0f;
+  auto step = [&](float& pi, float& gi_, float& mi_, float& vi_) {
+    const float gi = gi_ * coef;
+    const float mi = mi_ + (gi - mi_) * (1.0f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = vi_ * beta2 + (1.0f - beta2) * gi * gi;
+    mi_ = mi;
+    vi_ = vi;
+    pi = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    gi_ = 0.0f;
+  };
+  if ((n & 3) == 0 && ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0) {      // flat buffers: always
+    float4 *p4 = reinterpret_cast<float4*>(p), *g4 = reinterpret_cast<float4*>(g), *m4 = reinterpret_cast<float4*>(m),
+           *v4 = reinterpret_cast<float4*>(v);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n / 4; i += (int64_t)gridDim.x * 256) {
+      float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+      step(pp.x, gg.x, mm.x, vv.x);
+      step(pp.y, gg.y, mm.y, vv.y);
+      step(pp.z, gg.z, mm.z, vv.z);
+      step(pp.w, gg.w, mm.w, vv.w);
+      p4[i] = pp; g4[i] = gg; m4[i] = mm; v4[i] = vv;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) step(p[i], g[i], m[i], v[i]);
   }
 }
 

@@ -310,10 +310,22 @@ class HostPhysX:
         self.h2d_bytes += src.numel() * 4
 
     def refresh(self, env):
+        """root_states and contact_forces become available together (after the last substep): their two copies go out on
+        two streams, so they share the bus / copy engines instead of queueing behind each other."""
         f = self.frames[self.cursor]
-        for name, key in (("root_states", "root"), ("contact_forces", "contact")):
-            env.bufs[name].copy_(f[key], non_blocking=True)
-            self.h2d_bytes += f[key].numel() * 4
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=env.device)
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._copy_stream.wait_event(fork)
+        with torch.cuda.stream(self._copy_stream):
+            env.bufs["root_states"].copy_(f["root"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        env.bufs["contact_forces"].copy_(f["contact"], non_blocking=True)
+        main.wait_event(done)
+        self.h2d_bytes += 4 * (f["root"].numel() + f["contact"].numel())
         if self.zero_copy_rigid:
             env.bufs.rebind_host_mapped("rigid_body_states", f["rigid"])
         else:
