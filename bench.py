@@ -145,7 +145,9 @@ def build_runner(args, rank, world, device, host_physx=False):
     if host_physx:
         env.physx = HostPhysX(args.num_envs, env.bufs["env_origins"], device, seed=1234 + rank, decimation=env.params.decimation)
     tc = class_to_dict(train_cfg)
-    tc["runner"]["resume"] = False
+    # "resume" only selects the ROA schedule here (ppo.py:41-43: coefficient 0.1 from the first update for a resumed /
+    # fine-tuned policy); no checkpoint ships with the reference, so the weights are random-init either way
+    tc["runner"]["resume"] = bool(args.resume if args.resume is not None else args.task.endswith("finetune"))
     runner = OnPolicyRunner(env, tc, log_dir=None, device=device, process_group=pg)
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
     if not args.no_graphs:
@@ -465,6 +467,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--task", default="go2_parkour")
     ap.add_argument("--num-envs", type=int, default=4096)
+    ap.add_argument("--resume", type=int, default=None, help="ROA schedule of a resumed policy (default: on for the finetune task)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
