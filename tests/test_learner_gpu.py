@@ -104,6 +104,90 @@ def test_tcgen05_linear_kernels(M, N, K):
     assert scale_err(db, 0.25 + dY[:, :N].sum(0)) <= 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(24576, 256, 512), (24576, 128, 256), (1000, 64, 128), (333, 512, 52), (129, 30, 52)])
+def test_tcgen05_dgrad_fused_bias_gradient_and_partial_accumulate(M, N, K):
+    """b200_tc_linear_dgrad_bias: dbias_prev += column sums of dX (fp32 atomics: tight tolerance against the column sums of the
+    kernel's own dX); dgrad `accumulate` = n > 1 adds the old contents of the first n output columns only."""
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(7 * M + N + K)
+    ld = lambda k: (k + 3) // 4 * 4
+    W = torch.zeros(N, ld(K)); W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    dY = torch.zeros(M, ld(N)); dY[:, :N] = torch.randn(M, N, generator=g)
+    Yprev = torch.randn(M, ld(K), generator=g)
+    Wd, dYd, Ypd = W.to(DEV), dY.to(DEV), Yprev.to(DEV)
+    p = lambda t: t.data_ptr()
+    st = _lib.stream_ptr()
+    dX, db = torch.zeros(M, ld(K), device=DEV), torch.full((ld(K),), 0.5, device=DEV)
+    _lib.check(lib.b200_tc_linear_dgrad_bias(p(dYd), ld(N), p(Wd), ld(K), p(Ypd), ld(K), p(dX), ld(K), M, N, K, 0, p(db), st))
+    torch.cuda.synchronize()
+    ref = (dY[:, :N] @ W[:, :K]) * torch.where(Yprev[:, :K] > 0, torch.ones(()), Yprev[:, :K] + 1.0)
+    assert scale_err(dX[:, :K], ref) <= 1e-2
+    assert scale_err(db[:K] - 0.5, dX[:, :K].double().sum(0).float()) <= 2e-5
+    if ld(K) > K:
+        assert float((db[K:] - 0.5).abs().max()) == 0.0
+    # partial-column accumulate: the first n columns keep their old contents added, the others are overwritten
+    n = max(2, K // 3)
+    old = torch.randn(M, ld(K), generator=g)
+    dX2 = old.to(DEV).clone()
+    _lib.check(lib.b200_tc_linear_dgrad(p(dYd), ld(N), p(Wd), ld(K), p(Ypd), ld(K), p(dX2), ld(K), M, N, K, n, st))
+    torch.cuda.synchronize()
+    exp = dX[:, :K].cpu().clone()
+    exp[:, :n] += old[:, :n]
+    assert scale_err(dX2[:, :K], exp) <= 1e-5
+    # the mma.sync parity path implements the same `accumulate` contract
+    dX3 = old.to(DEV).clone()
+    _lib.check(lib.b200_linear_dgrad(p(dYd), ld(N), p(Wd), ld(K), p(Ypd), ld(K), p(dX3), ld(K), M, N, K, n, 1, st))
+    torch.cuda.synchronize()
+    ref3 = ref.clone()
+    ref3[:, :n] += old[:, :n]
+    assert scale_err(dX3[:, :K], ref3) <= 5e-5
+
+
+def test_tcgen05_pair_pdl_switches_and_launch_trace():
+    """CTA pairs (cta_group::2) and PDL change how a GEMM is scheduled, not what it computes: bit-identical outputs.  The
+    launch trace records one {start, end} slot and one {M, N, K, code} row per launch."""
+    lib = _lib.lib()
+    M, N, K = 24576, 512, 627
+    g = torch.Generator().manual_seed(5)
+    ld = lambda k: (k + 3) // 4 * 4
+    X = torch.zeros(M, ld(K)); X[:, :K] = torch.randn(M, K, generator=g)
+    W = torch.zeros(N, ld(K)); W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    Xd, Wd, bd = X.to(DEV), W.to(DEV), b.to(DEV)
+    p = lambda t: t.data_ptr()
+    st = _lib.stream_ptr()
+    outs = []
+    try:
+        for pair, pdl in ((1, 0), (0, 0), (1, 1), (0, 1)):
+            lib.b200_tc_set_pair_mode(pair)
+            lib.b200_tc_set_pdl(pdl)
+            Y = torch.zeros(M, ld(N), device=DEV)
+            _lib.check(lib.b200_tc_linear_forward(p(Xd), ld(K), p(Wd), ld(K), p(bd), p(Y), ld(N), M, N, K, 1, st))
+            _lib.check(lib.b200_tc_linear_forward(p(Xd), ld(K), p(Wd), ld(K), p(bd), p(Y), ld(N), M, N, K, 1, st))   # back to back (PDL)
+            torch.cuda.synchronize()
+            outs.append(Y)
+    finally:
+        lib.b200_tc_set_pair_mode(1)
+        lib.b200_tc_set_pdl(0)
+    for Y in outs[1:]:
+        assert torch.equal(Y, outs[0])
+    dev = torch.zeros(4, 2, dtype=torch.int64, device=DEV)
+    dev[:, 0] = torch.iinfo(torch.int64).max
+    meta = np.zeros((4, 4), dtype=np.int64)
+    import ctypes as C
+    lib.b200_tc_set_trace(C.c_void_p(dev.data_ptr()), meta.ctypes.data_as(C.c_void_p), 4)
+    try:
+        for _ in range(2):
+            _lib.check(lib.b200_tc_linear_forward(p(Xd), ld(K), p(Wd), ld(K), p(bd), p(outs[0]), ld(N), M, N, K, 1, st))
+        torch.cuda.synchronize()
+    finally:
+        lib.b200_tc_set_trace(None, None, 0)
+    t = dev.cpu().numpy()
+    assert (meta[:2] == np.array([M, N, K, 0 * 1000 + 256 + 500])).all() and (meta[2:] == 0).all()
+    assert (t[:2, 1] > t[:2, 0]).all() and t[1, 0] >= t[0, 1] - 2000 and (t[2:, 1] == 0).all()
+    assert 5e3 < t[0, 1] - t[0, 0] < 5e5                       # tens of microseconds
+
+
 def assert_params_close(mine, ref, move, name):
     d = (mine.cpu() - ref).abs()
     frac = float((d > 0.02 * move).float().mean())
