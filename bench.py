@@ -338,8 +338,9 @@ def run_b200(args):
         e2e = {"value": T_STEPS * N * world * args.e2e_steps / t2, "unit": "env-steps/s",
                "h2d_bytes_per_step": env2.physx.bytes_per_step * T_STEPS, "d2h_bytes_per_step": T_STEPS * N * 5 + 5 * 4,
                "ms_per_step": t2 / args.e2e_steps * 1e3,
-               "h2d": "dof_state x4, root_states, contact_forces copied from pinned host memory every env step; rigid_body_states "
-                      "(4 of 247 floats per env are read) is read in place from the pinned buffer (zero-copy, counted at 32 B per read)"}
+               "h2d": "per env step, from pinned host memory: root_states, contact_forces and the last substep's dof_state are copied; "
+                      "the dof_state of substeps 0-2 is streamed in place by the next PD-torque kernel and rigid_body_states (4 of 247 "
+                      "floats per env are read) by the post-physics kernel (zero-copy; counted in full, resp. at 32 B per read)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -77,6 +77,10 @@ class BufferSet:
         assert tensor.shape == old.shape and tensor.dtype == old.dtype and tensor.is_pinned() and tensor.is_contiguous()
         setattr(self.struct, name, C.c_void_p(tensor.data_ptr()))
 
+    def unbind_host_mapped(self, name):
+        """back to the device tensor of the slot"""
+        setattr(self.struct, name, C.c_void_p(self.t[name].data_ptr()))
+
     def __getitem__(self, name):
         return self.t[name]
 

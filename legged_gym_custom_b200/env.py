@@ -287,7 +287,7 @@ class HostPhysX:
     heights, go2.py:272-277), so the kernel reads it IN PLACE from the pinned buffer (zero-copy over PCIe) instead of
     copying 4 MB per step.  Used by bench.py's end-to-end measurement; `bytes_per_step` counts what crosses the bus."""
 
-    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, zero_copy_rigid=True, **frame_kw):
+    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, zero_copy_rigid=True, zero_copy_dof=True, **frame_kw):
         rng = np.random.default_rng(seed)
         origins = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
         self.frames = []
@@ -296,6 +296,7 @@ class HostPhysX:
             self.frames.append({k: torch.from_numpy(v).pin_memory() for k, v in f.items()})
         self.cursor, self.h2d_bytes = -1, 0
         self.zero_copy_rigid = bool(zero_copy_rigid)
+        self.zero_copy_dof, self.decimation = bool(zero_copy_dof), int(decimation)
         f0 = self.frames[0]
         # zero-copy reads: 4 feet per env, one 32-byte sector each
         self.rigid_bytes = num_envs * 4 * 32 if self.zero_copy_rigid else 4 * f0["rigid"].numel()
@@ -305,8 +306,17 @@ class HostPhysX:
         self.cursor = (self.cursor + 1) % len(self.frames)
 
     def simulate(self, env, substep):
+        """dof_state after substep k.  Between substeps its only reader is the next PD-torque kernel (legged_robot.py:81-85),
+        which streams it once: that kernel reads the pinned frame in place (`zero_copy_dof`); the frame of the LAST substep
+        is what post_physics_step and the env's `dof_state` attribute see, so it is copied."""
         src = self.frames[self.cursor]["dof"][substep]
-        env.bufs["dof_state"].copy_(src, non_blocking=True)
+        last = substep == self.decimation - 1
+        if self.zero_copy_dof and not last:
+            env.bufs.rebind_host_mapped("dof_state", src)
+        else:
+            if self.zero_copy_dof:
+                env.bufs.unbind_host_mapped("dof_state")
+            env.bufs["dof_state"].copy_(src, non_blocking=True)
         self.h2d_bytes += src.numel() * 4
 
     def refresh(self, env):

@@ -255,7 +255,7 @@ def test_host_physx_zero_copy_matches_copy():
     for zero_copy in (True, False):
         env = Go2Env(Cfg, sim_device=DEV, seed=3)
         env.physx = HostPhysX(512, env.bufs["env_origins"], torch.device(DEV), seed=3, decimation=env.params.decimation,
-                              zero_copy_rigid=zero_copy)
+                              zero_copy_rigid=zero_copy, zero_copy_dof=zero_copy)
         env.reset()
         g = torch.Generator(device=DEV).manual_seed(0)
         for _ in range(5):
