@@ -436,12 +436,14 @@ def cpu_arm(args, budget_s, steps, warmup):
         it_time = (t1 - t0) * T_STEPS / n_env_steps + (t2 - t1) + (t3 - t2) * 20 / n_mb
         if s >= warmup:
             times.append(it_time)
+            parts = {"rollout_24_steps_s": (t1 - t0) * T_STEPS / n_env_steps, "gae_s": t2 - t1, "update_20_minibatches_s": (t3 - t2) * 20 / n_mb}
     it_time = float(np.mean(times))
     value = T_STEPS * N / it_time
     sample = (f"per step: {n_env_steps} of {T_STEPS} oracle env steps (with policy inference) + full GAE + {n_mb} of 20 PPO minibatches "
               f"of {mb} samples, at {N} envs; iteration time extrapolated linearly")
     return {"value": value, "ms_per_step": it_time * 1e3,
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}}
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                             "split": {k: round(v, 4) for k, v in parts.items()}}}
 
 
 def run_reference(args):
