@@ -295,22 +295,54 @@ int check_common(const char* who, const void* a, const void* b, const void* c, i
 }  // namespace
 
 // dX[m,k] (+)= (sum_{n < N <= 4} dY[m,n] W[n,k]) * elu'(Yprev[m,k]): the dgrad of a 1- or 3-wide head is an outer product,
-// not a GEMM -- one element per thread, consecutive threads on consecutive k
+// not a GEMM.  One thread per 4 consecutive k of one row (16-byte accesses; the threads of a row read the same dY values,
+// which the hardware broadcasts); `vec` = 0 falls back to one element per thread.
 __global__ void __launch_bounds__(256)
 small_n_dgrad_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ W, int ldw, const float* __restrict__ Yprev, int ldyp,
-                     float* __restrict__ dX, int lddx, int M, int N, int K, int accumulate) {
-  const int64_t total = (int64_t)M * K;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int64_t m = i / K;
-    const int k = (int)(i - m * K);
-    float acc = 0.0f;
-    for (int n = 0; n < N; ++n) acc = fmaf(dY[m * lddy + n], __ldg(W + (int64_t)n * ldw + k), acc);
-    if (Yprev) {
-      const float y = Yprev[m * ldyp + k];
-      acc *= (y > 0.0f ? 1.0f : y + 1.0f);
+                     float* __restrict__ dX, int lddx, int M, int N, int K, int accumulate, int vec) {
+  const int kw = vec ? 4 : 1, kq = K / kw;                 // work items per row
+  const unsigned total = (unsigned)M * (unsigned)kq;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+    const int m = (int)(i / (unsigned)kq), k = (int)(i - (unsigned)m * (unsigned)kq) * kw;
+    float dy[4];
+    for (int n = 0; n < N; ++n) dy[n] = dY[(int64_t)m * lddy + n];
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int n = 0; n < N; ++n) {
+      if (vec) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * ldw + k));
+        acc[0] = fmaf(dy[n], w4.x, acc[0]);
+        acc[1] = fmaf(dy[n], w4.y, acc[1]);
+        acc[2] = fmaf(dy[n], w4.z, acc[2]);
+        acc[3] = fmaf(dy[n], w4.w, acc[3]);
+      } else {
+        acc[0] = fmaf(dy[n], __ldg(W + (int64_t)n * ldw + k), acc[0]);
+      }
     }
-    float* o = dX + m * lddx + k;
-    *o = (accumulate == 1 || k < accumulate) ? *o + acc : acc;
+    float* o = dX + (int64_t)m * lddx + k;
+    if (vec) {
+      if (Yprev) {
+        const float4 y = *reinterpret_cast<const float4*>(Yprev + (int64_t)m * ldyp + k);
+        acc[0] *= (y.x > 0.0f ? 1.0f : y.x + 1.0f);
+        acc[1] *= (y.y > 0.0f ? 1.0f : y.y + 1.0f);
+        acc[2] *= (y.z > 0.0f ? 1.0f : y.z + 1.0f);
+        acc[3] *= (y.w > 0.0f ? 1.0f : y.w + 1.0f);
+      }
+      float4 r = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(o);
+        if (accumulate == 1 || k + 0 < accumulate) r.x += old.x;
+        if (accumulate == 1 || k + 1 < accumulate) r.y += old.y;
+        if (accumulate == 1 || k + 2 < accumulate) r.z += old.z;
+        if (accumulate == 1 || k + 3 < accumulate) r.w += old.w;
+      }
+      *reinterpret_cast<float4*>(o) = r;
+    } else {
+      if (Yprev) {
+        const float y = Yprev[(int64_t)m * ldyp + k];
+        acc[0] *= (y > 0.0f ? 1.0f : y + 1.0f);
+      }
+      *o = (accumulate == 1 || k < accumulate) ? *o + acc[0] : acc[0];
+    }
   }
 }
 
@@ -336,10 +368,13 @@ int b200_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const 
   if (int rc = check_common("b200_linear_dgrad", dY, W, dX, lddy, ldw, M, N, K)) return rc;
   B200_CHECK_ARG(lddy >= N && ldw >= K && lddx >= K, "b200_linear_dgrad: bad leading dimension");
   if (N <= 4) {      // value / estimator heads: a rank-N outer product, pure streaming (exact fp32 in every mode)
-    const int64_t total = (int64_t)M * K;
+    const int vec = (K % 4 == 0) && (ldw % 4 == 0) && (lddx % 4 == 0) && (!Yprev || ldyp % 4 == 0) &&
+                    (((uintptr_t)W | (uintptr_t)dX | (uintptr_t)(Yprev ? Yprev : W)) & 15) == 0;
+    const int64_t total = (int64_t)M * (vec ? K / 4 : K);
+    B200_CHECK_ARG(total < (1ll << 32), "b200_linear_dgrad: problem too large for the streaming head kernel");
     int blocks = (int)((total + 255) / 256);
     blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
-    small_n_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dY, lddy, W, ldw, Yprev, ldyp, dX, lddx, M, N, K, accumulate);
+    small_n_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dY, lddy, W, ldw, Yprev, ldyp, dX, lddx, M, N, K, accumulate, vec);
     B200_CHECK_LAUNCH("small_n_dgrad_kernel");
     return 0;
   }
