@@ -1,12 +1,13 @@
-// One env step for ONE env, executed by one warp -- shared CUDA / host source.
+// One env step, as pieces that one warp / one thread executes -- shared CUDA / host source.
 //
 // Replaces Go2Robot.post_physics_step and its callees (go2.py:345-387; full list in
-// include/b200gym.h at b200_post_physics_step).  The routine is written as STAGES over
-// lanes: inside a stage lanes are independent; lanes communicate only through the per-warp
-// scratch (shared memory on the GPU) across stage boundaries.  On the GPU a lane is a
-// thread and a boundary is __syncwarp(); tests/host_emul compiles the same source with g++
-// and runs the lanes of a stage sequentially, which is how the kernel source itself is
-// checked against the golden vectors without a GPU.
+// include/b200gym.h at b200_post_physics_step).  The step is cut into PIECES of different
+// natural width (row stages over the 32 lanes of a warp, per-body / per-dof / per-leg items,
+// reward-term parts, one reduce / reset thread per env; see "the whole env step" below).
+// Pieces communicate only through the per-env scratch (shared memory on the GPU); the CUDA
+// kernel (env_kernels.cu) packs them onto a CTA of 8 envs with barriers in between, and
+// tests/host_emul compiles the same source with g++ and runs the pieces one after the other,
+// which is how the kernel source itself is checked against the golden vectors without a GPU.
 //
 // Arithmetic contract (parity with the reference's torch path, SURVEY.md §7 hard part 1):
 //  * this TU is compiled with -fmad=false (g++: -ffp-contract=off): every * and + rounds
@@ -67,17 +68,17 @@ struct alignas(16) EnvScratch {
   int32_t last_contacts[4];
   int32_t outliers[32];
   int64_t ep_len, level, type;
-  // element stage (lane-parallel): per-body contact tests, per-dof products, per-leg gait terms, the four angles
+  // item stage (one thread per item): per-body contact tests, per-dof products, per-leg gait terms, the four angles
   int32_t body_hit[32];          // bit 0: |F| > 1 (termination test), bit 1: |F| > 0.1 (collision test)
   float dofv[10][12];            // per-dof contributions of the dof-summed reward terms (rows: DV_*)
   float leg_sin[4], leg_cos[4];  // sin / cos of 2 pi phase, contact order fl, fr, bl, br
   int32_t leg_stance[4];
   float ang[4];                  // roll, pitch, yaw, heading
-  // termination known before the scalar stage (element stage, lane 20): lets the history rows move while it runs
+  // termination flags (env_item_flags): known before any reward is, which lets the history rows move meanwhile
   int32_t early_reset, early_time_out, early_refill;
   uint32_t reset_draws[4 * 7];   // env_reset_draw (only when early_reset)
   uint32_t pad_[4];              // keeps sizeof / 16 odd (see the static_assert below)
-  // results of the scalar stage
+  // results of the item stage, the reward terms and env_finalize
   float blv[4], bav[4], pg[4], rpy[4], phases[8];
   float cmd_out[4], lch_out[4], fat_out[4];
   float root_out[16], dof_out[24];

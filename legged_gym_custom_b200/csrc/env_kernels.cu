@@ -1,7 +1,7 @@
 // Env-side kernels of libb200gym.so (compiled with -fmad=false, see env_core.cuh).
 //
 //   K1 pd_torques_kernel        one thread per (env, dof)            legged_robot.py:74-75, :440-478
-//   K2 post_physics_kernel      one warp per env (8 per CTA) + 1 thread per env for the scalar stage   go2.py:345-387 and callees
+//   K2 post_physics_kernel      CTA = 8 envs x 8 warps, five phases (see the kernel)   go2.py:345-387 and callees
 //   K3 extras_kernel            one CTA per reward term (+1)         go2.py:246-263 (episode means, time_outs)
 //      reset_all_kernel         one thread per env                   base_task.py:131-133
 //      heights_kernel           one thread per scan point            legged_robot.py:997-1032

@@ -43,7 +43,7 @@ static void extras(const B200EnvParams& P, const B200EnvBuffers& B) {
 }  // extern "C"
 
 // one env step, stage by stage, in the order the CUDA kernel's barriers allow: the history rows move between the
-// element stage and the write-back (all loads of a row before its first store, like the kernel's named barrier)
+// item stage and the write-back (all loads of a row before its first store, like the kernel's barrier between B1 and B2)
 template <bool FIXED>
 static void step_all(const B200EnvParams& P, const B200EnvBuffers& B, int64_t step) {
   static EnvScratch S;
