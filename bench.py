@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 T_STEPS = 24
+SETUP_ITERS = 3                  # build_runner: DAgger iteration, eager + graph capture, first replay
 ENV_BYTES_PER_ENV = 12618        # post-physics algorithmic bytes per env-step
 PD_BYTES_PER_ENV = 288           # one PD-torque pass
 
@@ -152,6 +153,12 @@ def build_runner(args, rank, world, device, host_physx=False):
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
     if not args.no_graphs:
         runner.enable_graphs()
+    # set-up, not measurement: iteration 0 is the DAgger iteration (it % 20 == 0, eager), iteration 1 launches eagerly
+    # (allocations, kernel attributes) and captures the CUDA graphs, iteration 2 is their first replay.  The W warm-up and
+    # K timed iterations that follow are then all steady-state PPO iterations, whatever W is.
+    for it in range(SETUP_ITERS):
+        runner.iteration(it)
+    torch.cuda.synchronize()
     return env, runner
 
 
@@ -192,14 +199,14 @@ def run_b200(args):
     _lib.lib().hook = prof.hook
     env, runner = build_runner(args, rank, world, device)
     N, K, W = args.num_envs, args.steps, args.warmup
-    # iteration 0 is a DAgger iteration (it % 20 == 0); warm-up covers it, the timed ones are PPO updates
-    for it in range(W):
+    for it in range(SETUP_ITERS, SETUP_ITERS + W):
         runner.iteration(it)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    elapsed = timed_iterations(runner, W, K, world)
+    first = SETUP_ITERS + W
+    elapsed = timed_iterations(runner, first, K, world)
     sampler.stop_flag = True
     sampler.join(timeout=3)
     value = T_STEPS * N * world * K / elapsed
@@ -209,7 +216,7 @@ def run_b200(args):
     if world == 1:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         tr = tu = 0.0
-        for it in range(W + K, W + K + 2):
+        for it in range(first + K, first + K + 2):
             ev[0].record()
             runner.rollout(False)
             ev[1].record()
@@ -228,7 +235,7 @@ def run_b200(args):
     streams, runner.alg.use_streams = runner.alg.use_streams, False
     prof.count = 0
     prof.timing = True
-    runner.iteration(W + K)
+    runner.iteration(first + K + 2)
     table = prof.table()
     prof.timing = False
     runner.alg.use_streams = streams
@@ -332,9 +339,9 @@ def run_b200(args):
             d2h[0] += N * 5
             return out
         env2.step = step_with_readback
-        for it in range(3):
+        for it in range(SETUP_ITERS, SETUP_ITERS + 2):
             runner2.iteration(it)
-        t2 = timed_iterations(runner2, 3, args.e2e_steps, world)
+        t2 = timed_iterations(runner2, SETUP_ITERS + 2, args.e2e_steps, world)
         e2e = {"value": T_STEPS * N * world * args.e2e_steps / t2, "unit": "env-steps/s",
                "h2d_bytes_per_step": env2.physx.bytes_per_step * T_STEPS, "d2h_bytes_per_step": T_STEPS * N * 5 + 5 * 4,
                "ms_per_step": t2 / args.e2e_steps * 1e3,
@@ -355,7 +362,8 @@ def run_b200(args):
                                        "PhysX replaced by a ring of replayed synthetic frames",
                            "num_envs_per_gpu": N, "parallelism": f"dp{world} (envs sharded, flat-gradient NCCL all-reduce)",
                            "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
-                           "timed_iterations": f"it {W}..{W + K - 1} (PPO updates; the DAgger iteration it=0 is in the warm-up)",
+                           "timed_iterations": f"it {first}..{first + K - 1} (every 20th is a DAgger iteration, as in the reference's loop; it 0-2 are "
+                                               "set-up: DAgger iteration, eager pass + CUDA-graph capture, first replay)",
                            "launch": "CUDA graphs (rollout+GAE: 1 graph; update: 1 graph per minibatch slot)" if not args.no_graphs else "eager"},
                 "e2e": e2e, "split": split, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "roofline_env": roof_env, "cpu_baseline": cpu,
                 "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}
