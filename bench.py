@@ -82,7 +82,7 @@ class Profile:
     def hook(self, name, raw, args):
         from legged_gym_custom_b200 import _lib
         if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version",
-                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_tc_linear_supported"):
+                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
             return raw(*args)
         self.count += _lib.LAUNCHES.get(name, 1)
         self.by_entry[name] = self.by_entry.get(name, 0) + _lib.LAUNCHES.get(name, 1)

@@ -264,6 +264,11 @@ int b200_env_force_generic_layout(B200Env* env, int on);
  * post-physics kernel records %globaltimer (ns) at its phase boundaries: [0] start, [1] rows loaded + height scan,
  * [2] items, [3] reward terms + history loads, [4] reward sum / reset, [5] end (observations written). */
 int b200_env_set_phase_trace(B200Env* env, unsigned long long* trace);
+/* Performance switch (results are unaffected): `on` != 0 makes every CTA of the post-physics kernel issue L2 prefetches
+ * for its envs' obs_history_buf rows (go2.py:566-576, the largest read of the step) at kernel entry, ahead of the two
+ * dependent round trips (state rows, height gathers) that precede their use.  Off by default: at 4096 envs the rows are
+ * L2-resident between steps. */
+int b200_env_set_prefetch(B200Env* env, int on);
 
 /* Replaces LeggedRobot.step's action clip (legged_robot.py:74-75) + _compute_torques
  * (legged_robot.py:440-478).  `actions_in` [N,12] raw policy actions; when `clip_and_store`

@@ -17,6 +17,7 @@ SYMBOLS = {
     "b200_env_destroy": (C.c_int, [C.c_void_p]),
     "b200_env_init_randomisation": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.POINTER(InitParams), C.c_void_p]),
     "b200_env_force_generic_layout": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_env_set_prefetch": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_env_set_phase_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_pd_torques": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_int, C.c_void_p]),
     "b200_post_physics_step": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_void_p]),

@@ -28,5 +28,6 @@ struct B200Env {
   B200EnvParams p;
   int device;
   unsigned long long* phase_trace;   // device [ceil(num_envs / 8)][8] or NULL (b200_env_set_phase_trace)
+  int prefetch_history;       // b200_env_set_prefetch: L2 prefetch of the history rows at kernel entry
   int force_generic_layout;   // tests: run the layout-generic kernel variant even for the go2 layout
 };

@@ -43,7 +43,7 @@ static_assert(kEnvsPerCta * (B200_NUM_BODIES + B200_NUM_DOF + 1) <= kEnvsPerCta 
 template <bool FIXED>
 __global__ void __launch_bounds__(kEnvsPerCta * 32, 4)
 post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
-                    const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace) {
+                    const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace, int prefetch) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EnvScratch* scratch = reinterpret_cast<EnvScratch*>(smem_raw);
   __shared__ float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
@@ -65,6 +65,15 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
   const int e = e0 + warp;
   const bool live = e < P.num_envs;
   const int n_live = min(kEnvsPerCta, P.num_envs - e0);
+  if (prefetch) {
+    // b200_env_set_prefetch: the CTA's history rows (one contiguous block, first read in B1 behind two dependent round
+    // trips) start towards L2 now; pays only when the rows are not L2-resident (env counts beyond ~32 k, cold benchmarks)
+    const int hn = (FIXED ? B200_GO2_HISTORY : P.history_len) * B200_PROPRIO;
+    const char* hp = reinterpret_cast<const char*>(B.obs_history_buf + (int64_t)e0 * hn);
+    const int bytes = n_live * hn * 4;
+    for (int off = t * 128; off < bytes; off += kEnvsPerCta * 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(hp + off)));
+  }
 
   // ---- A
   if (live) env_warp_pre<FIXED>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1);
@@ -288,6 +297,7 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   env->device = device;
   env->force_generic_layout = 0;
   env->phase_trace = nullptr;
+  env->prefetch_history = 0;
   *out = env;
   return 0;
 }
@@ -306,6 +316,12 @@ int b200_env_set_phase_trace(B200Env* env, unsigned long long* trace) {
 int b200_env_force_generic_layout(B200Env* env, int on) {
   B200_CHECK_ARG(env, "b200_env_force_generic_layout: null handle");
   env->force_generic_layout = on ? 1 : 0;
+  return 0;
+}
+
+int b200_env_set_prefetch(B200Env* env, int on) {
+  B200_CHECK_ARG(env, "b200_env_set_prefetch: null handle");
+  env->prefetch_history = on ? 1 : 0;
   return 0;
 }
 
@@ -330,9 +346,9 @@ static void launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, 
   const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
   const size_t smem = kEnvsPerCta * sizeof(EnvScratch);
   if (env_layout_is_go2(env->p) && !env->force_generic_layout)
-    post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace);
+    post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace, env->prefetch_history);
   else
-    post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace);
+    post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace, env->prefetch_history);
 }
 
 static int check_bufs(const B200Env* env, const B200EnvBuffers* b, const char* who) {

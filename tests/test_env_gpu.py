@@ -24,12 +24,13 @@ DEV = "cuda:0"
 class CudaEnv:
     """thin driver of the C ABI over a BufferSet (what Go2Env does, minus the PhysX provider)."""
 
-    def __init__(self, p, record_height_index=True, force_generic=0):
+    def __init__(self, p, record_height_index=True, force_generic=0, prefetch=0):
         self.lib, self.p = _lib.lib(), p
         self.bufs = BufferSet(p, DEV, record_height_index=record_height_index)
         self.h = C.c_void_p()
         _lib.check(self.lib.b200_env_create(C.byref(p), 0, C.byref(self.h)))
         _lib.check(self.lib.b200_env_force_generic_layout(self.h, force_generic))
+        _lib.check(self.lib.b200_env_set_prefetch(self.h, prefetch))
 
     def step(self, actions, frames, step):
         b, st = self.bufs, _lib.stream_ptr()
@@ -46,12 +47,13 @@ class CudaEnv:
         self.lib.b200_env_destroy(self.h)
 
 
-@pytest.mark.parametrize("force_generic", [0, 1], ids=["go2-layout-baked-in", "layout-generic"])
+@pytest.mark.parametrize("force_generic,prefetch", [(0, 0), (1, 0), (0, 1), (1, 1)],
+                         ids=["go2-layout-baked-in", "layout-generic", "go2-layout-baked-in+prefetch", "layout-generic+prefetch"])
 @pytest.mark.parametrize("task", gu.TASKS)
-def test_cuda_env_matches_reference_golden(task, force_generic):
+def test_cuda_env_matches_reference_golden(task, force_generic, prefetch):
     g = gu.load(task)
     p = gu.params_for(task, g)
-    env = CudaEnv(p, force_generic=force_generic)
+    env = CudaEnv(p, force_generic=force_generic, prefetch=prefetch)
     env.bufs.load_statics(gu.statics_for(task, g))
     st = gu.init_state(g, p)
     step = int(st.pop("common_step_counter"))

@@ -19,6 +19,7 @@ ap.add_argument("--num-envs", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--warmup", type=int, default=10)
 ap.add_argument("--no-flush", action="store_true")
+ap.add_argument("--prefetch", type=int, default=0, help="b200_env_set_prefetch")
 args = ap.parse_args()
 
 
@@ -34,6 +35,7 @@ N = args.num_envs
 actions = torch.randn(N, 12, device="cuda:0")
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")
 lib, h, st = env.lib, env._handle, _lib.stream_ptr()
+_lib.check(lib.b200_env_set_prefetch(h, args.prefetch))
 
 
 def timed(fn, n, warm):
@@ -68,5 +70,6 @@ alg = 13.8e3 * N
 res["algorithmic_GBs_env_step(min)"] = alg / (res["env_step_us(med,min)"][1] * 1e-6) / 1e9
 res["algorithmic_GBs_post_physics(min)"] = 12.618e3 * N / (res["post_physics+extras_us"][1] * 1e-6) / 1e9
 res["num_envs"] = N
+res["prefetch"] = args.prefetch
 res["resets_last_step"] = int(b["reset_count"].item())
 print(json.dumps(res))
