@@ -411,6 +411,14 @@ int b200_ppo_loss(const B200PpoLossArgs* args /* host */, void* stream);
 int b200_mse_rows_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* sum, int M, int D, void* stream);
 int b200_l2_rows_loss(const float* pred, int ldp, const float* target, int ldt, float* dpred, int lddp, float* sum, int M, int D, void* stream);
 int b200_elu_backward(float* dY, int lddy, const float* Y, int ldy, int M, int N, void* stream);
+/* schedule == 'adaptive' (ppo.py:233-246), kept on the device so that minibatches stay graph-replayable.
+ * b200_kl_sum adds sum_i KL(old_i || new_i) of the M samples to acc[0] (`acc` = 2 doubles on the device, zero before the first
+ * call; with several ranks all-reduce acc[0] between the two calls).  b200_adaptive_lr forms kl_mean = acc[0] / count, applies
+ * lr /= 1.5 (floor 1e-5) if kl_mean > 2 desired_kl, lr *= 1.5 (cap 1e-2) if 0 < kl_mean < desired_kl / 2, to the main
+ * optimiser's `adam_state[4]` (see b200_clip_adam), stores kl_mean in acc[1] and clears acc[0]. */
+int b200_kl_sum(const float* mu, int ldmu, const float* std, const float* old_mu, int ldom, const float* old_sigma, int ldos, int M, int A,
+                double* acc, void* stream);
+int b200_adaptive_lr(double* acc, int64_t count, double desired_kl, double* adam_state, void* stream);
 /* clip_grad_norm_ + Adam.step on flat buffers (ppo.py:228-231, :273-276, :336-339); zeroes `grads`.
  * grad_scale = 1/world_size after the NCCL sum all-reduce of `grads`.
  * `state` = 8 doubles on the device: [0] scratch, [1] step, [2] beta1^step, [3] beta2^step, [4] lr -- advanced

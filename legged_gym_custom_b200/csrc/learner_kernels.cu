@@ -7,6 +7,7 @@
 //   mse_rows_loss_kernel   estimator loss  mean ||pred - target||_2^2, fwd + bwd               ppo.py:224-226
 //   l2_rows_loss_kernel    DAgger loss     mean ||target - pred||_2,   fwd + bwd               ppo.py:330-333
 //   sumsq / clip_adam      global grad-norm clip fused with the Adam step on flat buffers      ppo.py:228-231, :273-276
+//   kl_sum / adaptive_lr   schedule='adaptive': KL(old || new) of the minibatch, learning-rate rule on the device   ppo.py:233-246
 //
 // All are streaming, HBM/latency-bound kernels; reductions use warp shuffles + one atomic per CTA.
 #include "common.cuh"
@@ -293,6 +294,41 @@ elu_backward_kernel(float* __restrict__ dY, int lddy, const float* __restrict__ 
 
 // Optimiser state block (device, doubles) so that a captured CUDA graph can be replayed step after step:
 //   [0] sum of squared gradients (scratch)  [1] step  [2] beta1^step  [3] beta2^step  [4] lr
+// schedule == 'adaptive' (ppo.py:233-246).  Per sample, in the reference's fp32 op order:
+//   kl = sum_a [ log(sigma / old_sigma + 1e-5) + (old_sigma^2 + (old_mu - mu)^2) / (2 sigma^2) - 0.5 ]
+// `acc[0]` accumulates the sum over the samples of this rank (fp64 atomics: the order of arrival moves it by ~1e-16 relative).
+__global__ void __launch_bounds__(256)
+kl_sum_kernel(const float* __restrict__ mu, int ldmu, const float* __restrict__ std, const float* __restrict__ old_mu, int ldom,
+              const float* __restrict__ old_sigma, int ldos, int M, int A, double* __restrict__ acc) {
+  __shared__ float red[32];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  float part[1] = {0.0f};
+  if (i < M) {
+    float kl = 0.0f;
+    for (int a = 0; a < A; ++a) {
+      const float sg = std[a], os = old_sigma[(int64_t)i * ldos + a];
+      const float d = old_mu[(int64_t)i * ldom + a] - mu[(int64_t)i * ldmu + a];
+      kl += (logf(sg / os + 1.e-5f) + (os * os + d * d) / (2.0f * (sg * sg))) - 0.5f;
+    }
+    part[0] = kl;
+  }
+  cta_sum<1>(part, red);
+  if (threadIdx.x == 0) atomicAdd(acc, (double)part[0]);
+}
+
+// acc[0] = KL sum over `count` samples (all ranks) -> kl_mean (fp32, like the reference's tensor) -> the rule on the Python
+// float `learning_rate` (fp64 here) -> adam_state[4]; acc[1] keeps kl_mean for the host, acc[0] is cleared for the next minibatch.
+__global__ void adaptive_lr_kernel(double* __restrict__ acc, double count, float hi, float lo, double* __restrict__ adam_state) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float kl_mean = (float)(acc[0] / count);
+  double lr = adam_state[4];
+  if (kl_mean > hi) lr = fmax(1e-5, lr / 1.5);
+  else if (kl_mean < lo && kl_mean > 0.0f) lr = fmin(1e-2, lr * 1.5);
+  adam_state[4] = lr;
+  acc[1] = (double)kl_mean;
+  acc[0] = 0.0;
+}
+
 __global__ void adam_advance_kernel(double* __restrict__ state, double beta1, double beta2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     state[0] = 0.0;
@@ -634,6 +670,22 @@ int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
   B200_CHECK_LAUNCH("sumsq_kernel");
   clip_adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, grad_scale, max_norm, beta1, beta2, eps);
   B200_CHECK_LAUNCH("clip_adam_kernel");
+  return 0;
+}
+
+int b200_kl_sum(const float* mu, int ldmu, const float* std, const float* old_mu, int ldom, const float* old_sigma, int ldos, int M, int A,
+                double* acc, void* stream) {
+  B200_CHECK_ARG(mu && std && old_mu && old_sigma && acc && M > 0 && A > 0, "b200_kl_sum: bad argument");
+  kl_sum_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, old_mu, ldom, old_sigma, ldos, M, A, acc);
+  B200_CHECK_LAUNCH("kl_sum_kernel");
+  return 0;
+}
+
+int b200_adaptive_lr(double* acc, int64_t count, double desired_kl, double* adam_state, void* stream) {
+  B200_CHECK_ARG(acc && adam_state && count > 0 && desired_kl > 0.0, "b200_adaptive_lr: bad argument");
+  // the reference compares an fp32 tensor with Python floats: the thresholds take the tensor's dtype
+  adaptive_lr_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, (double)count, (float)(desired_kl * 2.0), (float)(desired_kl / 2.0), adam_state);
+  B200_CHECK_LAUNCH("adaptive_lr_kernel");
   return 0;
 }
 

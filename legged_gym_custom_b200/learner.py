@@ -151,12 +151,15 @@ class PPO:
                  lam=0.95, value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, estimator_learning_rate=1e-3,
                  max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, resume=False,
                  device="cuda:0", seed=0, process_group=None):
-        if schedule != "fixed":
-            raise NotImplementedError("schedule='adaptive' needs a host decision per minibatch; every go2 config uses 'fixed'")
+        if schedule not in ("fixed", "adaptive"):
+            raise ValueError(f"unknown schedule '{schedule}'")
         self.device = torch.device(device)
         self.lib = _lib.lib()
         self.desired_kl, self.schedule = desired_kl, schedule
-        self.learning_rate, self.estimator_learning_rate = learning_rate, estimator_learning_rate
+        # ppo.py:233: the KL rule runs only for schedule == 'adaptive' with a desired_kl; it lives on the device (kl_sum /
+        # adaptive_lr kernels write the main optimiser's lr slot), so minibatches stay graph-replayable
+        self.adaptive = schedule == "adaptive" and desired_kl is not None
+        self._learning_rate, self.estimator_learning_rate = learning_rate, estimator_learning_rate
         # ROA schedule (ppo.py:40-43)
         self.start_val, self.end_val, self.start_step, self.duration = 0.0, 0.05, 5000, 10000
         if resume:
@@ -188,6 +191,17 @@ class PPO:
         self._pending_critic = None
         self._graphs, self._graph_calls = {}, {}
 
+    @property
+    def learning_rate(self):
+        """the main optimiser's learning rate; under schedule='adaptive' it is read back from the device (one sync)"""
+        if self.adaptive:
+            return float(self.actor_critic.main.state[4].item())
+        return self._learning_rate
+
+    @learning_rate.setter
+    def learning_rate(self, value):
+        self._learning_rate = value
+
     # ---- storage ------------------------------------------------------------------------------------
     def init_storage(self, num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
                      estimated_obs_shape, scan_obs_shape, action_shape):
@@ -210,6 +224,9 @@ class PPO:
         self.roll_ws = Workspace(self.device)          # rollout-time activations (M = N)
         self.upd_ws = Workspace(self.device)           # update-time activations  (M = minibatch)
         self.loss_sums = z(8)
+        if self.adaptive:                              # old mu / sigma slabs + [KL sum, last kl_mean]
+            self.p_mu, self.p_sigma = z(self.batch, s.d_act), z(self.batch, s.d_act)
+            self.kl_acc = z(2, dt=torch.float64)
         self.reg_coef_dev = z(1)
         self.last_values = z(N, 1)
 
@@ -330,6 +347,9 @@ class PPO:
         g(_p(s.actions), s.d_act, _p(self.p_act), s.d_act, s.d_act)
         for src, dst in ((s.values, self.p_val), (s.returns, self.p_ret), (s.actions_log_prob, self.p_logp), (s.advantages, self.p_adv)):
             g(_p(src), 1, _p(dst), 1, 1)
+        if self.adaptive:
+            g(_p(s.mu), s.d_act, _p(self.p_mu), s.d_act, s.d_act)
+            g(_p(s.sigma), s.d_act, _p(self.p_sigma), s.d_act, s.d_act)
         # the adaptation-encoder latent slab (ppo.py:213-214, see init_storage): one launch over the whole batch
         ac.fwd_adapt(self.upd_ws, _p(self.p_actor_in), ac.ld_actor_in, _p(self.p_lat_a), ac.latent_dim, B)
 
@@ -346,6 +366,17 @@ class PPO:
         _lib.check(self.lib.b200_clip_adam(_p(group.params), _p(group.grads), _p(group.exp_avg), _p(group.exp_avg_sq), group.n,
                                            C.c_void_p(group.state.data_ptr()), 1.0 / self.world_size, self.max_grad_norm, 0.9, 0.999, 1e-8,
                                            _lib.stream_ptr()))
+
+    def _adaptive_lr(self, mu, r0, M):
+        """ppo.py:233-246: KL of the minibatch's old / new action distributions -> learning rate of the main optimiser."""
+        A, acc = self.storage.d_act, C.c_void_p(self.kl_acc.data_ptr())
+        _lib.check(self.lib.b200_kl_sum(_p(mu), A, self.actor_critic.main.ptr("std"), _p(self.p_mu) + 4 * r0 * A, A,
+                                        _p(self.p_sigma) + 4 * r0 * A, A, M, A, acc, _lib.stream_ptr()))
+        if self.process_group is not None:             # every rank must take the same decision: KL over all ranks' samples
+            import torch.distributed as dist
+            dist.all_reduce(self.kl_acc[0:1], op=dist.ReduceOp.SUM, group=self.process_group)
+        _lib.check(self.lib.b200_adaptive_lr(acc, M * self.world_size, float(self.desired_kl),
+                                             C.c_void_p(self.actor_critic.main.state.data_ptr()), _lib.stream_ptr()))
 
     def _minibatch(self, r0, M):
         """one PPO minibatch on rows [r0, r0+M) of the permuted slabs (ppo.py:194-276)."""
@@ -384,6 +415,8 @@ class PPO:
         with self._on(s_hi):
             self._join([s_scan])
             ac.fwd_actor(ws, X, ld, _p(mu), A, M)
+            if self.adaptive:
+                self._adaptive_lr(mu, r0, M)
             self._join([s_crit])
             # PPO loss head (ppo.py:249-270)
             a = _lib.PpoLossArgs()

@@ -145,6 +145,19 @@ def ppo_losses(sd, sd_est, b, clip=0.2, value_coef=1.0, entropy_coef=0.01, reg_c
                 mu=mu, value_out=value, lat_p=lat_p, lat_a=lat_a)
 
 
+def adaptive_lr(lr, mu, sigma, old_mu, old_sigma, desired_kl):
+    """The schedule == 'adaptive' block of PPO.update (ppo.py:233-246) -> (new learning rate, kl_mean)."""
+    with torch.no_grad():
+        kl = torch.sum(torch.log(sigma / old_sigma + 1.e-5) + (torch.square(old_sigma) + torch.square(old_mu - mu)) / (2.0 * torch.square(sigma))
+                       - 0.5, axis=-1)
+        kl_mean = torch.mean(kl)
+        if kl_mean > desired_kl * 2.0:
+            lr = max(1e-5, lr / 1.5)
+        elif kl_mean < desired_kl / 2.0 and kl_mean > 0.0:
+            lr = min(1e-2, lr * 1.5)
+    return lr, float(kl_mean)
+
+
 def dagger_loss(sd, b):
     """PPO.update_dagger's loss (ppo.py:322-333)."""
     with torch.no_grad():
@@ -174,10 +187,11 @@ MAIN_PREFIXES = ("actor.", "critic.", "privileged_encoder_.", "std", "scan_encod
 class LearnerOracle:
     """PPO.update / update_dagger over explicit minibatch index lists (the reference draws them with randperm)."""
 
-    def __init__(self, sd, sd_est, lr=2e-4, est_lr=1e-4, max_grad_norm=1.0, **loss_kw):
+    def __init__(self, sd, sd_est, lr=2e-4, est_lr=1e-4, max_grad_norm=1.0, desired_kl=None, **loss_kw):
         self.sd = {k: v.clone().float().requires_grad_(True) for k, v in sd.items()}
         self.sd_est = {k: v.clone().float().requires_grad_(True) for k, v in sd_est.items()}
         self.lr, self.est_lr, self.max_grad_norm, self.loss_kw = lr, est_lr, max_grad_norm, loss_kw
+        self.desired_kl, self.kl_log = desired_kl, []      # desired_kl set = schedule 'adaptive'
         self.main_keys = [k for k in self.sd if k.startswith(MAIN_PREFIXES)]
         self.adapt_keys = [k for k in self.sd if k.startswith("adaptation_encoder_.")]
         mk = lambda keys, d: dict(step=0, m=[torch.zeros_like(d[k]) for k in keys], v=[torch.zeros_like(d[k]) for k in keys])
@@ -192,6 +206,10 @@ class LearnerOracle:
         g = torch.autograd.grad(out["loss"], [self.sd[k] for k in self.main_keys], allow_unused=True)
         g = [torch.zeros_like(self.sd[k]) if gi is None else gi for k, gi in zip(self.main_keys, g)]
         self.last_grads = dict(zip(self.main_keys, g), **dict(zip(self.est_keys, g_est)))
+        if self.desired_kl is not None:
+            mu = out["mu"].detach()
+            self.lr, kl = adaptive_lr(self.lr, mu, mu * 0. + self.sd["std"].detach(), b["mu"], b["sigma"], self.desired_kl)
+            self.kl_log.append((kl, self.lr))
         clip_and_adam([self.sd[k] for k in self.main_keys], g, self.opt_main, self.lr, self.max_grad_norm)
         return {k: float(v.detach()) for k, v in out.items() if v.dim() == 0}
 

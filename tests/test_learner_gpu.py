@@ -228,11 +228,11 @@ def test_state_dict_roundtrip_and_forward_vs_reference_golden():
     assert scale_err(ac.evaluate(b["critic_obs"]), torch.from_numpy(GOLD["act/value"])) <= 1e-4
 
 
-def _ppo(ac, est, N, T, epochs=2, mbs=2, resume=True):
+def _ppo(ac, est, N, T, epochs=2, mbs=2, resume=True, schedule='fixed'):
     from legged_gym_custom_b200.learner import PPO
     ppo = PPO(ac, est, num_learning_epochs=epochs, num_mini_batches=mbs, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
               entropy_coef=0.01, learning_rate=2e-4, estimator_learning_rate=1e-4, max_grad_norm=1.0, use_clipped_value_loss=True,
-              schedule='fixed', desired_kl=0.01, resume=resume, device=DEV, seed=3)
+              schedule=schedule, desired_kl=0.01, resume=resume, device=DEV, seed=3)
     ppo.init_storage(N, T, [572], [29], [736], [3], [132], [12])
     return ppo
 
@@ -282,6 +282,58 @@ def test_dagger_matches_reference_golden():
     after, sd = _gold_sd("dagger/ac/"), ac.state_dict()
     for k in after:
         assert_params_close(sd[k], after[k], 2e-4 * 4, k)
+
+
+@pytest.mark.parametrize("near,graphs", [(False, False), (True, False), (True, True)],
+                         ids=["old-policy-far:lr-shrinks", "old-policy-near:lr-grows-then-holds", "near+cuda-graphs"])
+def test_adaptive_schedule_matches_oracle(near, graphs):
+    """schedule='adaptive' (ppo.py:233-246; oracle pinned to the reference in test_learner_oracle_vs_reference.py): the KL of
+    every minibatch and the learning rate it leaves behind, decided on the device.  The rule is discrete (lr = 2e-4 x 1.5^k in
+    fp64), so the final learning rate must be IDENTICAL; kl_mean to 1e-3 relative once both policies have taken the same number
+    of Adam steps (first minibatch: 1e-4).  3 epochs: with `graphs` the third pass of every minibatch slot is a graph replay."""
+    T, N, epochs = 6, 32, 3
+    ac, est = _build(HID)
+    sd, sd_est = _gold_sd("init/ac/"), _gold_sd("init/est/")
+    ac.load_state_dict(sd); est.load_state_dict(sd_est)
+    ppo = _ppo(ac, est, N, T, epochs=epochs, schedule='adaptive')
+    ppo.use_graphs = graphs
+    st = lu.random_storage(T, N, seed=31)
+    if near:                                     # stored mu / sigma = the current policy's own -> KL ~ 12 x 1e-5
+        f = lambda t: t.flatten(0, 1)
+        with torch.no_grad():
+            mu = lo.actor_mean(sd, f(st["obs"]), f(st["priv"]), f(st["true_est"]), f(st["scan"]))
+        st["mu"], st["sigma"] = mu.view(T, N, -1).clone(), (mu * 0. + sd["std"]).view(T, N, -1).clone()
+    _fill(ppo, st)
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(8))
+    orc = lo.LearnerOracle(sd, sd_est, lr=2e-4, est_lr=1e-4, desired_kl=0.01)
+    mb = T * N // 2
+    for _ in range(epochs):
+        for i in range(2):
+            orc.minibatch(lu.minibatch(st, perm[i * mb:(i + 1) * mb]), reg_coef=0.1)
+    # the fixture must stay clear of the decision thresholds (0.005, 0.02), or the comparison below would be a coin toss
+    assert all(min(abs(kl / 0.005 - 1), abs(kl / 0.02 - 1)) > 0.15 for kl, _ in orc.kl_log), orc.kl_log
+    # first minibatch alone (no Adam step taken yet on either side)
+    ppo._gather_storage(perm.to(DEV))
+    ppo.reg_coef_dev.fill_(0.1)
+    ppo._minibatch(0, mb)
+    kl0 = float(ppo.kl_acc[1].item())
+    assert abs(kl0 - orc.kl_log[0][0]) <= 1e-4 * abs(orc.kl_log[0][0]) and ppo.learning_rate == orc.kl_log[0][1]
+    # the whole update from the same initial state
+    ac.load_state_dict(sd); est.load_state_dict(sd_est)
+    for g in (ac.main, est.group):
+        g.exp_avg.zero_(); g.exp_avg_sq.zero_(); g.grads.zero_()
+        g.state.copy_(torch.tensor([0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64))
+    ac.main.set_lr(2e-4); est.group.set_lr(1e-4)
+    _fill(ppo, st)
+    ppo.update_with_indices(perm.to(DEV))
+    assert ppo.learning_rate == orc.lr, (ppo.learning_rate, orc.kl_log)
+    kl_last = float(ppo.kl_acc[1].item())
+    assert abs(kl_last - orc.kl_log[-1][0]) <= (1e-3 if not near else 5e-2) * abs(orc.kl_log[-1][0]), (kl_last, orc.kl_log[-1])
+    assert float(ppo.kl_acc[0].item()) == 0.0
+    if near:
+        assert orc.lr == 2e-4 * 1.5 ** 4 and [lr for _, lr in orc.kl_log[-2:]] == [orc.lr, orc.lr]     # grew 4x, then held
+    else:
+        assert orc.lr == pytest.approx(2e-4 / 1.5 ** 6, rel=1e-12)
 
 
 @pytest.mark.parametrize("dagger,precise", [(False, True), (True, True), (False, False), (True, False)])

@@ -14,7 +14,7 @@ REF = "/root/reference/rsl_rl"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference not present (GPU box)")
 
 
-def _reference_ppo(T, N, seed=0):
+def _reference_ppo(T, N, seed=0, schedule='fixed'):
     if REF not in sys.path:
         sys.path.insert(0, REF)
     from rsl_rl.algorithms import PPO
@@ -27,7 +27,7 @@ def _reference_ppo(T, N, seed=0):
     est = MlpEstimator(52, 10, 3, hidden_dims=[256, 128], activation='elu', use_history=True)
     ppo = PPO(ac, est, num_learning_epochs=2, num_mini_batches=2, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0,
               entropy_coef=0.01, learning_rate=2e-4, estimator_learning_rate=1e-4, max_grad_norm=1.0, use_clipped_value_loss=True,
-              schedule='fixed', desired_kl=0.01, resume=True, device='cpu')       # resume=True -> ROA coef 0.1 from the second update
+              schedule=schedule, desired_kl=0.01, resume=True, device='cpu')       # resume=True -> ROA coef 0.1 from the second update
     ppo.init_storage(N, T, [572], [29], [736], [3], [132], [12])
     return ppo
 
@@ -83,6 +83,42 @@ def test_update_matches_reference(total_updates, monkeypatch):
         assert torch.allclose(mine, ref, rtol=1e-6, atol=5e-8), k
     for k, ref in ppo.estimator.state_dict().items():
         assert torch.allclose(orc.sd_est[k].detach(), ref, rtol=1e-6, atol=5e-8), k
+
+
+@pytest.mark.parametrize("near", [False, True], ids=["old-policy-far:lr-shrinks", "old-policy-near:lr-grows"])
+def test_adaptive_schedule_matches_reference(near, monkeypatch):
+    """schedule='adaptive' (ppo.py:233-246): same learning-rate trajectory and post-update parameters.  `near`: the stored
+    mu / sigma are the current policy's own (KL ~ 1e-4 < desired/2 -> lr x 1.5 until the policy has moved), else random (KL >> 2 desired)."""
+    T, N = 6, 32
+    ppo = _reference_ppo(T, N, schedule='adaptive')
+    st = lu.random_storage(T, N, seed=2)
+    sd = {k: v.detach().clone() for k, v in ppo.actor_critic.state_dict().items()}
+    sd_est = {k: v.detach().clone() for k, v in ppo.estimator.state_dict().items()}
+    if near:
+        f = lambda t: t.flatten(0, 1)
+        with torch.no_grad():
+            mu = lo.actor_mean(sd, f(st["obs"]), f(st["priv"]), f(st["true_est"]), f(st["scan"]))
+        st["mu"], st["sigma"] = mu.view(T, N, -1).clone(), (mu * 0. + sd["std"]).view(T, N, -1).clone()
+    _fill(ppo, st)
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(6))
+    monkeypatch.setattr(torch, "randperm", lambda *a, **k: perm.clone())
+    ppo.update()
+    orc = lo.LearnerOracle(sd, sd_est, lr=2e-4, est_lr=1e-4, desired_kl=0.01)
+    mb = T * N // 2
+    for _ in range(2):
+        for i in range(2):
+            orc.minibatch(lu.minibatch(st, perm[i * mb:(i + 1) * mb]), reg_coef=0.0)
+    assert orc.lr == ppo.learning_rate, orc.kl_log
+    if near:      # grows while the policy is still close, then holds (desired/2 <= KL <= 2 desired) once it has moved
+        assert ppo.learning_rate > 2e-4
+    else:
+        assert ppo.learning_rate == pytest.approx(2e-4 / 1.5 ** 4, rel=1e-12)
+    assert ppo.optimizer.param_groups[0]['lr'] == orc.lr
+    new = ppo.actor_critic.state_dict()
+    for k in orc.main_keys:
+        mine = orc.sd[k].detach() if k != "std" else torch.min(orc.sd[k].detach(), torch.tensor(1.0))
+        # the 1-ulp-per-Adam-step difference of the other update tests, at up to 2.25 x their learning rate
+        assert torch.allclose(mine, new[k], rtol=1e-6, atol=2e-7), (k, float((mine - new[k]).abs().max()))
 
 
 def test_update_dagger_matches_reference(monkeypatch):
