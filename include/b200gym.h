@@ -163,6 +163,12 @@ typedef struct B200EnvParams {
   float contact_thr2_term, contact_thr2_collision;
   int32_t _pad0;
   uint64_t seed;                       /* Philox key (oracle/philox.py, csrc/philox.cuh) */
+  /* command curriculum (go2.py:80-107, :222-223; cfg.commands.curriculum, off in every shipped go2 cfg).  The reference
+   * keeps the lin_vel_x range as Python floats and moves it with np.clip in double: so do we (B200EnvBuffers.command_ranges) */
+  double cc_vel_increment, cc_max_forward_vel, cc_max_reverse_vel;
+  double cc_range0[2];                 /* cfg.commands.ranges.lin_vel_x as doubles: initial content of command_ranges */
+  float cc_threshold;                  /* fp32(0.8 * reward_scales[tracking_lin_vel]) -- the fp32 tensor comparison of go2.py:91 */
+  int32_t command_curriculum;
 } B200EnvParams;
 
 /* Device buffers of one env shard.  "PhysX" = written by the simulator each step and only
@@ -224,6 +230,10 @@ typedef struct B200EnvBuffers {
   float* extras_episode;         /* [B200_NUM_REWARD_TERMS + 1]: rew_<term> means, then terrain_level */
   int32_t* reset_count;          /* [1] number of envs reset this step */
   float* reset_episode_sums;     /* [N,B200_NUM_REWARD_TERMS] scratch: pre-zeroing sums of envs reset this step */
+  /* command curriculum (only touched when params.command_curriculum != 0) */
+  double* command_ranges;        /* [4] lin_vel_x {lo, hi} in force, then {lo, hi} the resets of THIS step resample from */
+  float* cc_value;               /* [N] scratch: episode_sums[tracking_lin_vel] + this step's term (dry pass) */
+  uint8_t* cc_reset;             /* [N] scratch: the env resets this step (dry pass) */
 } B200EnvBuffers;
 
 typedef struct B200Env B200Env;  /* opaque handle: params in device constant storage + scratch */

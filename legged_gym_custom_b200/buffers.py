@@ -37,6 +37,7 @@ def buffer_specs(p):
         "reset_buf": ((N,), b), "time_out_buf": ((N,), b), "extras_time_outs": ((N,), b),
         "extras_episode": ((NUM_REWARD_TERMS + 1,), f), "reset_count": ((1,), torch.int32),
         "reset_episode_sums": ((N, NUM_REWARD_TERMS), f),
+        "command_ranges": ((4,), torch.float64), "cc_value": ((N,), f), "cc_reset": ((N,), b),
     }
 
 
@@ -52,6 +53,7 @@ class BufferSet:
             self.t[name] = None if spec is None else torch.zeros(spec[0], dtype=spec[1], device=self.device)
         self.t["root_states"][:, 6] = 1.0
         self.t["reset_buf"].fill_(True)                      # base_task.py:83
+        self.set_command_range(p.cc_range0[0], p.cc_range0[1])
         self.struct = EnvBuffers()
         self.refresh_pointers()
 
@@ -81,6 +83,10 @@ class BufferSet:
         """back to the device tensor of the slot"""
         setattr(self.struct, name, C.c_void_p(self.t[name].data_ptr()))
 
+    def set_command_range(self, lo, hi):
+        """lin_vel_x range of the command curriculum (go2.py:80-107): {lo, hi} in force = {lo, hi} of this step's resets"""
+        self.t["command_ranges"].copy_(torch.tensor([lo, hi, lo, hi], dtype=torch.float64))
+
     def __getitem__(self, name):
         return self.t[name]
 
@@ -89,6 +95,9 @@ class BufferSet:
         for k, v in st.items():
             if k == "episode_sums":
                 self.t[k].copy_(torch.as_tensor(v).t())
+            elif k == "command_ranges":
+                lo, hi = (float(x) for x in torch.as_tensor(v).flatten()[:2])
+                self.set_command_range(lo, hi)
             elif k in self.t and self.t[k] is not None:
                 self.t[k].copy_(torch.as_tensor(v).reshape(self.t[k].shape).to(self.t[k].dtype))
 

@@ -53,6 +53,7 @@ class Go2Cfg(NS):
 
     class commands(NS):
         curriculum = False
+        max_forward_vel, max_reverse_vel, vel_increment = 1.0, -1.0, 0.10      # command curriculum (go2_config.py:183-187)
         num_commands = 4
         resampling_time = 10.
         heading_command = False
@@ -138,6 +139,7 @@ class Go2ParkourCfg(Go2Cfg):
 
     class commands(Go2Cfg.commands):
         heading_command = True
+        max_forward_vel, max_reverse_vel, vel_increment = 1.75, 0.5, 0.10      # go2_parkour_config.py:127-131
 
         class ranges(NS):
             lin_vel_x, lin_vel_y, ang_vel_yaw, heading = [0.75, 1.5], [0.0, 0.0], [-0.0, 0.0], [-0.2, 0.2]

@@ -77,7 +77,9 @@ struct alignas(16) EnvScratch {
   // termination flags (env_item_flags): known before any reward is, which lets the history rows move meanwhile
   int32_t early_reset, early_time_out, early_refill;
   uint32_t reset_draws[4 * 7];   // env_reset_draw (only when early_reset)
-  uint32_t pad_[4];              // keeps sizeof / 16 odd (see the static_assert below)
+  // lin_vel_x command range as fp32 {lo, span}: [0] in force (periodic resampling), [1] for the resets of this step --
+  // they differ only on the step a command curriculum moves the range (go2.py:222-223 runs before _resample_commands)
+  float cc_lo[2], cc_span[2];    // (16 bytes: also keeps sizeof / 16 odd, see the static_assert below)
   // results of the item stage, the reward terms and env_finalize
   float blv[4], bav[4], pg[4], rpy[4], phases[8];
   float cmd_out[4], lch_out[4], fat_out[4];
@@ -221,14 +223,16 @@ B200_HD float height_at(const B200EnvParams& P, const int16_t* hs, int px, int p
 }
 
 // ---- command resampling for one env (go2.py:413-464) -------------------------------------
-B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v, const float* quat, float* cmd);
-B200_HD void resample_commands(const B200EnvParams& P, uint32_t site, uint32_t step, uint32_t e, const float* quat, float* cmd) {
+// (`lo_x`, `span_x`: the lin_vel_x range -- P.cmd_lo[0] / P.cmd_span[0] unless a command curriculum moves it)
+B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v, const float* quat, float* cmd, float lo_x, float span_x);
+B200_HD void resample_commands(const B200EnvParams& P, uint32_t site, uint32_t step, uint32_t e, const float* quat, float* cmd,
+                               float lo_x, float span_x) {
   const Philox4 r = keyed_block(P.seed, site, step, e, 0);
-  resample_commands_from(P, r.v, quat, cmd);
+  resample_commands_from(P, r.v, quat, cmd, lo_x, span_x);
 }
-B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v, const float* quat, float* cmd) {
+B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v, const float* quat, float* cmd, float lo_x, float span_x) {
   struct { uint32_t v[4]; } r = {{r_v[0], r_v[1], r_v[2], r_v[3]}};
-  cmd[0] = P.cmd_span[0] * u32_to_uniform(r.v[0]) + P.cmd_lo[0];
+  cmd[0] = span_x * u32_to_uniform(r.v[0]) + lo_x;
   cmd[1] = P.cmd_span[1] * u32_to_uniform(r.v[1]) + P.cmd_lo[1];
   if (P.heading_command)
     cmd[3] = P.cmd_span[3] * u32_to_uniform(r.v[2]) + P.cmd_lo[3];
@@ -245,10 +249,36 @@ B200_HD void resample_commands_from(const B200EnvParams& P, const uint32_t* r_v,
   }
 }
 
+// ---- command curriculum (go2.py:80-107) ------------------------------------------------------
+// fp32 {lo, span} of a double {lo, hi} pair: torch_rand_float forms (upper - lower) in double, then multiplies in fp32
+B200_HD void command_range_f32(const double* lo_hi, float* lo, float* span) {
+  *lo = (float)lo_hi[0];
+  *span = (float)(lo_hi[1] - lo_hi[0]);
+}
+// `count` envs reset on a step with common_step_counter % max_episode_length == 0 and `sum` is the sum of their
+// episode_sums[tracking_lin_vel] (this step's term included): new {lo, hi} from the one in force, in the reference's
+// arithmetic -- the mean and its comparison in fp32 (0-dim tensor vs Python float), np.clip on Python floats in double.
+B200_HD void command_curriculum_rule(const B200EnvParams& P, int count, double sum, const double* in_force, double* next) {
+  double lo = in_force[0], hi = in_force[1];
+  if (count > 0) {
+    const float mean = (float)(sum / (double)count) / (float)P.max_episode_length;
+    if (mean > P.cc_threshold) {
+      const double d = P.cc_vel_increment, a = lo - d;
+      // np.clip(a, a_min, a_max) = minimum(a_max, maximum(a, a_min)); go2.py:100-103 passes a_max = a itself
+      const double a_min = P.cc_max_reverse_vel, a_max = P.cc_max_reverse_vel < 0.0 ? 0.0 : a;
+      lo = fmin(a_max, fmax(a, a_min));
+      hi = fmin(P.cc_max_forward_vel, fmax(hi + d, 0.0));
+    }
+  }
+  next[0] = lo;
+  next[1] = hi;
+}
+
 // ---- reset of one env (go2.py:207-263 with legged_robot.py:481-574) ----------------------
 // Operates on the caller's register copies (no shared-memory read-modify-write).
 struct ResetState {
   float root[13], dof[24], cmd[4], origin[3], lch[4], fat[4];
+  float cc_lo, cc_span;          // lin_vel_x range the reset resamples from
   int32_t contact_cur[4];
   int64_t level, ep_len;
 };
@@ -293,7 +323,7 @@ B200_HD void reset_env(const B200EnvParams& P, const B200EnvBuffers& B, ResetSta
     lane0 = 2;
   }
   for (int i = 0; i < 6; ++i) R.root[7 + i] = 1.0f * u32_to_uniform(draws[12 + lane0 + i]) + -0.5f;
-  resample_commands_from(P, draws + 24, R.root + 3, R.cmd);
+  resample_commands_from(P, draws + 24, R.root + 3, R.cmd, R.cc_lo, R.cc_span);
   for (int f = 0; f < 4; ++f) {
     R.lch[f] = 0.0f;
     R.fat[f] = 0.0f;
@@ -380,7 +410,7 @@ B200_HD void env_item_angle(const B200EnvParams& P, EnvScratch& S, int a, uint32
   if (a == 3) {
     float cmd[4] = {S.cmd[0], S.cmd[1], S.cmd[2], S.cmd[3]};
     const int64_t ep = S.ep_len + 1;                      // go2.py:354
-    if ((uint32_t)ep % (uint32_t)P.resample_interval == 0u) resample_commands(P, SITE_CMD_PERIODIC, step, e, S.root + 3, cmd);
+    if ((uint32_t)ep % (uint32_t)P.resample_interval == 0u) resample_commands(P, SITE_CMD_PERIODIC, step, e, S.root + 3, cmd, S.cc_lo[0], S.cc_span[0]);
     if (P.heading_command) cmd[2] = clampf(wrap_to_pi(cmd[3] - v) * P.heading_error_gain, -1.0f, 1.0f);
     for (int i = 0; i < 4; ++i) S.cmd_out[i] = cmd[i];
   }
@@ -643,6 +673,17 @@ B200_HD void env_terms_part(const B200EnvParams& P, EnvScratch& S, int part) {
 #undef B200_MINE
 }
 
+// ---- dry pass of a command-curriculum step (go2.py:222-223, :87): update_command_curriculum needs the mean of
+// episode_sums[tracking_lin_vel] over the envs that reset on this step BEFORE any of them resamples its command.  After
+// stage 0 and the item stage of env e: evaluate the part that holds the term, publish (sum so far + this step's term,
+// reset flag); nothing else leaves the scratch.
+template <bool FIXED>
+B200_HD void env_cc_probe(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, int e) {
+  env_terms_part<FIXED>(P, S, B200_REW_tracking_lin_vel % B200_TERM_PARTS);
+  B.cc_value[e] = S.sums[B200_REW_tracking_lin_vel] + S.term[B200_REW_tracking_lin_vel];
+  B.cc_reset[e] = (uint8_t)S.early_reset;
+}
+
 // ---- compute_reward's sum (alphabetical, legged_robot.py:216-237), the termination reward, and reset_idx on this env if
 // flagged (go2.py:375-376).  One thread per env, after every part of env_terms_part.
 // (needs EnvScratch::reset_draws when the env resets: env_reset_draw, blocks 0..6)
@@ -676,6 +717,8 @@ B200_HD void env_finalize(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
     for (int i = 0; i < 3; ++i) R.origin[i] = S.origin_out[i];
     R.level = S.level;
     R.ep_len = S.ep_len + 1;
+    R.cc_lo = S.cc_lo[1];
+    R.cc_span = S.cc_span[1];
     reset_env(P, B, R, S.type, S.reset_draws, 1);
     for (int i = 0; i < 13; ++i) S.root_out[i] = R.root[i];
     for (int i = 0; i < 24; ++i) S.dof_out[i] = R.dof[i];
@@ -842,6 +885,11 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
       S.jump_flag = r_jf;
       S.level = r_lv;
       S.type = r_ty;
+    }
+    if (lane < 2) {
+      S.cc_lo[lane] = P.cmd_lo[0];
+      S.cc_span[lane] = P.cmd_span[0];
+      if (P.command_curriculum) command_range_f32(B.command_ranges + 2 * lane, &S.cc_lo[lane], &S.cc_span[lane]);
     }
   }
   B200_WARP_SYNC();
@@ -1019,6 +1067,9 @@ B200_HD void env_reset_only(const B200EnvParams& P, const B200EnvBuffers& B, int
   for (int i = 0; i < 3; ++i) R.origin[i] = B.env_origins[(int64_t)e * 3 + i];
   R.level = B.terrain_levels[e];
   R.ep_len = 0;
+  R.cc_lo = P.cmd_lo[0];
+  R.cc_span = P.cmd_span[0];
+  if (P.command_curriculum) command_range_f32(B.command_ranges, &R.cc_lo, &R.cc_span);   // the range in force
   uint32_t draws[4 * B200_RESET_BLOCKS];
   for (int b = 0; b < B200_RESET_BLOCKS; ++b) env_reset_draw(P, draws, (uint32_t)e, (uint32_t)step64, b);
   reset_env(P, B, R, B.terrain_types[e], draws, init_done);

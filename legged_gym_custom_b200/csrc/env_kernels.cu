@@ -43,7 +43,7 @@ static_assert(kEnvsPerCta * (B200_NUM_BODIES + B200_NUM_DOF + 1) <= kEnvsPerCta 
 template <bool FIXED>
 __global__ void __launch_bounds__(kEnvsPerCta * 32, 4)
 post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
-                    const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace, int prefetch) {
+                    const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace, int prefetch, int dry) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   EnvScratch* scratch = reinterpret_cast<EnvScratch*>(smem_raw);
   __shared__ float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
@@ -52,6 +52,8 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
   if (threadIdx.x >= 64 && threadIdx.x < 64 + B200_MAX_PROPRIO) env_tables_fill(P, T, threadIdx.x - 64);
   __syncthreads();
   if (step_dev) step = *step_dev;
+  // `dry`: the probe pass of a command curriculum (launched only when P.command_curriculum): an ordinary step ends here
+  if (dry && step % P.max_episode_length != 0) return;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   // optional phase trace (b200_env_set_phase_trace): %globaltimer of warp 0 at the phase boundaries, [cta][8]
 #define B200_TRACE(slot)                                                                          \
@@ -105,6 +107,10 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
   }
   B200_TRACE(2)
   __syncthreads();
+  if (dry) {      // go2.py:222-223: (episode sum of tracking_lin_vel, reset flag) of every env, nothing else is written
+    if (warp == 0 && lane < n_live) env_cc_probe<FIXED>(P, B, scratch[lane], e0 + lane);
+    return;
+  }
 
   // ---- B1 / B2
   const int hn4 = (FIXED ? B200_GO2_HISTORY : P.history_len) * (B200_PROPRIO / 4);
@@ -285,6 +291,7 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   B200_CHECK_ARG(!p->has_height_samples || (p->horizontal_scale > 0.0f && (float)(p->hs_rows + p->hs_cols) * p->horizontal_scale < 8388608.0f),
                  "b200_env_create: height field extent must stay below 2^23 m");
   B200_CHECK_ARG(p->resample_interval > 0 && p->push_interval > 0, "b200_env_create: intervals must be > 0");
+  B200_CHECK_ARG(!p->command_curriculum || p->max_episode_length >= 2, "b200_env_create: command curriculum needs max_episode_length >= 2");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess) {
@@ -342,13 +349,51 @@ static int post_physics_attr() {
 }
 
 // the go2 layout (history 10, scan 12 x 11) runs the variant with the layout baked in
-static void launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st) {
+static void launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st,
+                                int dry = 0) {
   const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
   const size_t smem = kEnvsPerCta * sizeof(EnvScratch);
   if (env_layout_is_go2(env->p) && !env->force_generic_layout)
-    post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace, env->prefetch_history);
+    post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, dry ? nullptr : env->phase_trace, env->prefetch_history, dry);
   else
-    post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace, env->prefetch_history);
+    post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, dry ? nullptr : env->phase_trace,
+                                                                     env->prefetch_history, dry);
+}
+
+// Command curriculum (go2.py:80-107, :222-223), one CTA per step when P.command_curriculum:
+//   command_ranges[0:2] <- command_ranges[2:4]       (the move decided on the previous curriculum step is now in force)
+//   on a step with common_step_counter % max_episode_length == 0:
+//   command_ranges[2:4] <- rule(mean of cc_value over the envs with cc_reset)      (fixed-order sums: deterministic)
+__global__ void __launch_bounds__(256)
+command_curriculum_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
+                          const int64_t* __restrict__ step_dev) {
+  __shared__ double dsm[256];
+  __shared__ int ism[256];
+  if (step_dev) step = *step_dev;
+  double* cr = B.command_ranges;
+  if (threadIdx.x == 0) {
+    cr[0] = cr[2];
+    cr[1] = cr[3];
+  }
+  if (step % P.max_episode_length != 0) return;
+  int cnt = 0;
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < P.num_envs; e += 256)
+    if (B.cc_reset[e]) {
+      ++cnt;
+      acc += (double)B.cc_value[e];
+    }
+  const int count = cta_sum_256<int>(cnt, ism);
+  const double sum = cta_sum_256<double>(acc, dsm);
+  if (threadIdx.x == 0) command_curriculum_rule(P, count, sum, cr + 2, cr + 2);
+}
+
+static int launch_command_curriculum(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st) {
+  launch_post_physics(env, bufs, step, step_dev, st, /*dry=*/1);
+  B200_CHECK_LAUNCH("post_physics_kernel (command-curriculum probe)");
+  command_curriculum_kernel<<<1, 256, 0, st>>>(env->p, *bufs, step, step_dev);
+  B200_CHECK_LAUNCH("command_curriculum_kernel");
+  return 0;
 }
 
 static int check_bufs(const B200Env* env, const B200EnvBuffers* b, const char* who) {
@@ -382,6 +427,8 @@ int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step")) return rc;
   if (int rc = post_physics_attr()) return rc;
   if (parts & 1) {
+    if (env->p.command_curriculum)
+      if (int rc = launch_command_curriculum(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream)) return rc;
     launch_post_physics(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream);
     B200_CHECK_LAUNCH("post_physics_kernel");
   }
@@ -412,6 +459,8 @@ int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t
   B200_CHECK_ARG(step_counter_dev, "b200_post_physics_step_dev: null counter");
   counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev, 1);       // go2.py:355
   if (int rc = post_physics_attr()) return rc;
+  if (env->p.command_curriculum)
+    if (int rc = launch_command_curriculum(env, bufs, 0, step_counter_dev, (cudaStream_t)stream)) return rc;
   launch_post_physics(env, bufs, 0, step_counter_dev, (cudaStream_t)stream);
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);

@@ -224,10 +224,23 @@ class Go2Env:
             episode = {"rew_" + n: ep[REWARD_INDEX[n]] for n in REWARD_TERMS if self.params.reward_scales[REWARD_INDEX[n]] != 0.0}
             if self.params.curriculum:
                 episode["terrain_level"] = ep[len(REWARD_TERMS)]
+            if self.params.command_curriculum:             # go2.py:255-259; the lin_vel_x range lives on the device
+                cr, rng = self.bufs["command_ranges"], self.cfg.commands.ranges
+                episode.update(max_command_x=cr[3], min_command_x=cr[2], max_command_y=rng.lin_vel_y[1], max_command_yaw=rng.ang_vel_yaw[1])
             self._extras = {"episode": episode}
             if getattr(self.cfg.env, "send_timeouts", True):
                 self._extras["time_outs"] = self.bufs["extras_time_outs"]
         return self._extras
+
+    @property
+    def command_ranges(self):
+        """legged_robot.py:949 `command_ranges` (lists of Python floats); with a command curriculum the lin_vel_x entry is
+        read back from the device buffer the kernels move (one sync)"""
+        rng = self.cfg.commands.ranges
+        out = {k: list(getattr(rng, k)) for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading")}
+        if self.params.command_curriculum:
+            out["lin_vel_x"] = self.bufs["command_ranges"][2:4].tolist()
+        return out
 
     @property
     def episode_sums(self):

@@ -72,6 +72,9 @@ class EnvParams(C.Structure):
         ("hip_joints", i32 * 4), ("thigh_joints", i32 * 4), ("calf_joints", i32 * 4),
         ("contact_thr2_term", f32), ("contact_thr2_collision", f32), ("_pad0", i32),
         ("seed", C.c_uint64),
+        ("cc_vel_increment", C.c_double), ("cc_max_forward_vel", C.c_double), ("cc_max_reverse_vel", C.c_double),
+        ("cc_range0", C.c_double * 2),
+        ("cc_threshold", f32), ("command_curriculum", i32),
     ]
 
     def reward_names(self):
@@ -88,7 +91,7 @@ BUFFER_FIELDS = [
     "terrain_types", "env_origins", "base_lin_vel", "base_ang_vel", "projected_gravity", "rpy", "measured_heights",
     "height_index", "phases", "foot_contacts", "obs_buf", "privileged_obs_buf", "critic_obs_buf",
     "estimated_obs_buf", "scan_obs_buf", "rew_buf", "reset_buf", "time_out_buf", "extras_time_outs",
-    "extras_episode", "reset_count", "reset_episode_sums",
+    "extras_episode", "reset_count", "reset_episode_sums", "command_ranges", "cc_value", "cc_reset",
 ]
 
 
@@ -201,7 +204,11 @@ def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shap
     p.heading_error_gain = _get(cmd, "heading_error_gain", 0.5)
     p.zero_command, p.zero_command_prob = int(bool(_get(cmd, "zero_command", False))), _get(cmd, "zero_command_prob", 0.1)
     assert len(_get(cmd, "user_command", [])) == 0, "user_command override is a play-time feature, not on the hot path"
-    assert not _get(cmd, "curriculum", False), "command curriculum is off in every go2 cfg (host-side numpy logic)"
+    # command curriculum (go2.py:80-107): the thresholds are Python floats compared with / clipped against fp32 tensors
+    p.command_curriculum = int(bool(_get(cmd, "curriculum", False)))
+    p.cc_vel_increment = float(_get(cmd, "vel_increment", 0.0))
+    p.cc_max_forward_vel, p.cc_max_reverse_vel = float(_get(cmd, "max_forward_vel", 0.0)), float(_get(cmd, "max_reverse_vel", 0.0))
+    p.cc_range0[0], p.cc_range0[1] = float(rng.lin_vel_x[0]), float(rng.lin_vel_x[1])
 
     mesh = ter.mesh_type
     p.has_height_samples = int(mesh in ("heightfield", "trimesh"))
@@ -250,6 +257,7 @@ def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shap
             raise KeyError(f"reward scale '{name}' has no _reward_{name} in the reference")
         p.reward_scales[REWARD_INDEX[name]] = val * dt     # legged_robot.py:740
     p.only_positive_rewards = int(bool(rew.only_positive_rewards))
+    p.cc_threshold = 0.8 * (_get(rew.scales, "tracking_lin_vel", 0.0) * dt)     # go2.py:91 (0.8 * the dt-scaled scale)
     p.tracking_sigma, p.base_height_target = rew.tracking_sigma, rew.base_height_target
     p.max_contact_force, p.max_foot_height = rew.max_contact_force, _get(rew, "max_foot_height", 0.08)
     p.stance_threshold = 2.0 * _get(rew, "percent_time_on_ground", 0.5) - 1.0

@@ -97,6 +97,9 @@ class Go2Oracle:
         self.forward_vec = torch.tensor([1., 0., 0.]).repeat(self.N, 1)
         self.active = [n for n in REWARD_TERMS[:-1] if p.reward_scales[REWARD_INDEX[n]] != 0.0]
         self.out = {}
+        # command_ranges["lin_vel_x"] (legged_robot.py:949): Python floats, moved by update_command_curriculum
+        if "command_ranges" not in self.st:
+            self.st["command_ranges"] = torch.tensor([p.cc_range0[0], p.cc_range0[1]], dtype=torch.float64)
 
     # ---- construction helpers ------------------------------------------------------------
     @staticmethod
@@ -193,7 +196,11 @@ class Go2Oracle:
         if len(env_ids) == 0:
             return
         u = self._u(site, env_ids, [0, 1, 2, 3])
-        cmd[env_ids, 0] = p.cmd_span[0] * u[:, 0] + p.cmd_lo[0]
+        lo_x, span_x = p.cmd_lo[0], p.cmd_span[0]
+        if p.command_curriculum:      # torch_rand_float(lower, upper): (upper - lower) in double, then fp32 arithmetic
+            lo, hi = (float(v) for v in self.st["command_ranges"])
+            lo_x, span_x = float(np.float32(lo)), float(np.float32(hi - lo))
+        cmd[env_ids, 0] = span_x * u[:, 0] + lo_x
         cmd[env_ids, 1] = p.cmd_span[1] * u[:, 1] + p.cmd_lo[1]
         if p.heading_command:
             cmd[env_ids, 3] = p.cmd_span[3] * u[:, 2] + p.cmd_lo[3]
@@ -339,6 +346,20 @@ class Go2Oracle:
             return torch.sum(sq(dq), dim=1) * (cmd_norm3 < 0.2).float()
         raise KeyError(name)
 
+    # ---- command curriculum: go2.py:80-107 ------------------------------------------------------
+    def update_command_curriculum(self, env_ids):
+        p, st = self.p, self.st
+        mean = torch.mean(st["episode_sums"][REWARD_INDEX["tracking_lin_vel"]][env_ids]) / p.max_episode_length
+        lo, hi = (float(v) for v in st["command_ranges"])
+        delta = p.cc_vel_increment
+        if mean > torch.tensor(p.cc_threshold):                            # fp32 tensor vs Python float: compared in fp32
+            if p.cc_max_reverse_vel < 0.0:
+                lo = np.clip(lo - delta, p.cc_max_reverse_vel, 0.)
+            else:                                                          # go2.py:100-103: a_max is the value itself
+                lo = np.clip(lo - delta, p.cc_max_reverse_vel, lo - delta)
+            hi = np.clip(hi + delta, 0., p.cc_max_forward_vel)
+        st["command_ranges"] = torch.tensor([float(lo), float(hi)], dtype=torch.float64)
+
     # ---- reset: go2.py:207-263, legged_robot.py:481-574 -------------------------------------
     def reset_idx(self, env_ids, init_done=True):
         p, st = self.p, self.st
@@ -357,6 +378,9 @@ class Go2Oracle:
             rnd = torch.from_numpy((self._u32(philox.SITE_CURRICULUM, env_ids, [0])[:, 0] % np.uint32(p.max_terrain_level)).astype(np.int64))
             lv[env_ids] = torch.where(lv[env_ids] >= p.max_terrain_level, rnd, torch.clip(lv[env_ids], 0))
             st["env_origins"][env_ids] = self.terrain_origins[lv[env_ids], st["terrain_types"][env_ids]]
+        # go2.py:222-223 (reset() at step 0 sees all-zero episode sums: no move, so only in-step resets are restated)
+        if p.command_curriculum and init_done and int(st["common_step_counter"]) % p.max_episode_length == 0:
+            self.update_command_curriculum(env_ids)
         # _reset_dofs (legged_robot.py:481-506)
         u = self._u(philox.SITE_RESET_DOFS, env_ids, list(range(NUM_DOF)))
         dof = st["dof_state"].view(self.N, NUM_DOF, 2)

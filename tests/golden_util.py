@@ -11,7 +11,22 @@ from legged_gym_custom_b200.params import env_params_from_cfg, REWARD_TERMS, REW
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TASKS = ("go2_parkour", "go2_parkour_finetune", "go2")
+# replays with cfg.commands.curriculum = True (oracle/make_golden.py CC_SCENARIOS); every helper below takes either a task
+# name or one of these scenario names
+CC_SCENARIOS = ("go2_parkour+cc_move", "go2+cc_move", "go2_parkour+cc_hold")
 _terrain_cache = {}
+
+
+def task_of(name):
+    return name.split("+")[0]
+
+
+def cfg_for(name):
+    cfg = configs.TASKS[task_of(name)][0]
+    if "+cc" in name:
+        commands = type("commands", (cfg.commands,), {"curriculum": True})
+        cfg = type(cfg.__name__ + "CommandCurriculum", (cfg,), {"commands": commands})
+    return cfg
 
 
 def load(task):
@@ -20,6 +35,7 @@ def load(task):
 
 def terrain_for(task):
     """(height_samples int16 | None, terrain_origins | None), regenerated and sha-pinned."""
+    task = task_of(task)
     cfg = configs.TASKS[task][0]
     if cfg.terrain.mesh_type == "plane":
         return None, None
@@ -34,7 +50,7 @@ def terrain_for(task):
 
 
 def params_for(task, g, index_div_mode=0):
-    cfg = configs.TASKS[task][0]
+    cfg = cfg_for(task)
     hs, _ = terrain_for(task)
     return env_params_from_cfg(cfg, num_envs=int(g["num_envs"]), seed=int(g["seed"]), index_div_mode=index_div_mode,
                                hs_shape=None if hs is None else hs.shape)
@@ -72,6 +88,8 @@ def init_state(g, p):
         extras_time_outs=t("extras/time_outs").bool() if "init/extras/time_outs" in g.files else torch.zeros(N, dtype=torch.bool),
         extras_episode=ep, common_step_counter=torch.tensor(int(g["init/common_step_counter"]), dtype=torch.int64),
     )
+    if "init/command_ranges" in g.files:
+        st["command_ranges"] = t("command_ranges")
     return st
 
 
@@ -176,6 +194,8 @@ def check_step(bufs, exp, t, rtol=RTOL, report=None):
     if "extras/time_outs" in exp:
         assert (get("extras_time_outs").astype(bool) == exp["extras/time_outs"].astype(bool)).all(), ("extras_time_outs", t)
     assert int(get("reset_count")[0]) == int(exp["n_reset"]), ("reset_count", t)
+    if "command_ranges" in exp:        # Python floats in the reference, doubles here: identical
+        assert (get("command_ranges")[2:4] == exp["command_ranges"]).all(), ("command_ranges", t, get("command_ranges"), exp["command_ranges"])
 
 
 def oracle_expected(orc, out):
@@ -197,6 +217,8 @@ def oracle_expected(orc, out):
     e["extras/time_outs"] = st["extras_time_outs"].numpy()
     e["n_reset"] = out["reset_count"]
     e["rew_terms_abs"] = out["rew_terms_abs"].numpy()
+    if orc.p.command_curriculum:
+        e["command_ranges"] = st["command_ranges"].numpy()
     return e
 
 

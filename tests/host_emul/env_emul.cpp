@@ -53,6 +53,27 @@ static void step_all(const B200EnvParams& P, const B200EnvBuffers& B, int64_t st
   for (int j = 0; j < P.num_scan; ++j) scan_point(P, j, &pt_x[j], &pt_y[j]);
   for (int i = 0; i < B200_MAX_PROPRIO; ++i) env_tables_fill(P, T, i);
   const int hn4 = P.history_len * (B200_PROPRIO / 4);
+  if (P.command_curriculum) {     // launch_command_curriculum (env_kernels.cu): probe pass, then the range update
+    double* cr = B.command_ranges;
+    cr[0] = cr[2];
+    cr[1] = cr[3];
+    if (step % P.max_episode_length == 0) {
+      for (int e = 0; e < P.num_envs; ++e) {
+        memset(&S, 0xCD, sizeof(S));
+        env_warp_pre<FIXED>(P, B, S, pt_x, pt_y, e, 0, 32);
+        for (int it = 0; it < ITEM_COUNT; ++it) env_item(P, T, S, it, (uint32_t)e, step);
+        env_cc_probe<FIXED>(P, B, S, e);
+      }
+      int count = 0;
+      double sum = 0.0;
+      for (int e = 0; e < P.num_envs; ++e)
+        if (B.cc_reset[e]) {
+          ++count;
+          sum += (double)B.cc_value[e];
+        }
+      command_curriculum_rule(P, count, sum, cr + 2, cr + 2);
+    }
+  }
   for (int e = 0; e < P.num_envs; ++e) {
     memset(&S, 0xCD, sizeof(S));   // poison: a stage that reads what no stage wrote shows up as garbage
     env_warp_pre<FIXED>(P, B, S, pt_x, pt_y, e, 0, 32);

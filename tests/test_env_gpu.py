@@ -32,7 +32,8 @@ class CudaEnv:
         _lib.check(self.lib.b200_env_force_generic_layout(self.h, force_generic))
         _lib.check(self.lib.b200_env_set_prefetch(self.h, prefetch))
 
-    def step(self, actions, frames, step):
+    def step(self, actions, frames, step, counter=None):
+        """`counter`: int64 device tensor holding the step count BEFORE this step -> the graph-replay flavour of the call"""
         b, st = self.bufs, _lib.stream_ptr()
         a = torch.as_tensor(actions).to(DEV).contiguous()
         for k in range(self.p.decimation):
@@ -40,7 +41,10 @@ class CudaEnv:
             b["dof_state"].copy_(torch.as_tensor(frames["dof"][k]))
         for name, key in (("root_states", "root"), ("contact_forces", "contact"), ("rigid_body_states", "rigid")):
             b[name].copy_(torch.as_tensor(frames[key]))
-        _lib.check(self.lib.b200_post_physics_step(self.h, C.byref(b.struct), step, st))
+        if counter is not None:
+            _lib.check(self.lib.b200_post_physics_step_dev(self.h, C.byref(b.struct), C.c_void_p(counter.data_ptr()), st))
+        else:
+            _lib.check(self.lib.b200_post_physics_step(self.h, C.byref(b.struct), step, st))
         torch.cuda.synchronize()
 
     def close(self):
@@ -49,7 +53,7 @@ class CudaEnv:
 
 @pytest.mark.parametrize("force_generic,prefetch", [(0, 0), (1, 0), (0, 1), (1, 1)],
                          ids=["go2-layout-baked-in", "layout-generic", "go2-layout-baked-in+prefetch", "layout-generic+prefetch"])
-@pytest.mark.parametrize("task", gu.TASKS)
+@pytest.mark.parametrize("task", gu.TASKS + gu.CC_SCENARIOS)
 def test_cuda_env_matches_reference_golden(task, force_generic, prefetch):
     g = gu.load(task)
     p = gu.params_for(task, g)
@@ -65,6 +69,24 @@ def test_cuda_env_matches_reference_golden(task, force_generic, prefetch):
         gu.check_step(env.bufs, gu.expected(g, t), t, report=report)
     assert gu.rel_err(env.bufs["obs_history_buf"].cpu().numpy(), g["final/obs_history_buf"]) <= gu.RTOL
     print(task, {k: f"{v:.1e}" for k, v in sorted(report.items(), key=lambda kv: -kv[1])[:5]})
+    env.close()
+
+
+@pytest.mark.parametrize("task", gu.CC_SCENARIOS)
+def test_command_curriculum_with_device_step_counter(task):
+    """b200_post_physics_step_dev (common_step_counter in device memory, as under CUDA-graph replay): the probe pass and the
+    range update of the command curriculum (go2.py:80-107, :222-223) take their decision from the device counter"""
+    g = gu.load(task)
+    p = gu.params_for(task, g)
+    env = CudaEnv(p)
+    env.bufs.load_statics(gu.statics_for(task, g))
+    st = gu.init_state(g, p)
+    counter = torch.tensor([int(st.pop("common_step_counter"))], dtype=torch.int64, device=DEV)
+    env.bufs.load_state(st)
+    for t in range(int(g["steps"])):
+        env.step(g[f"step{t}/in/actions"], gu.frames_of(g, t), None, counter=counter)
+        gu.check_step(env.bufs, gu.expected(g, t), t)
+    assert int(counter.item()) == int(g["init/common_step_counter"]) + int(g["steps"])
     env.close()
 
 

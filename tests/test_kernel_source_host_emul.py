@@ -18,7 +18,7 @@ def lib():
 
 
 @pytest.mark.parametrize("force_generic", [0, 1], ids=["go2-layout-baked-in", "layout-generic"])
-@pytest.mark.parametrize("task", gu.TASKS)
+@pytest.mark.parametrize("task", gu.TASKS + gu.CC_SCENARIOS)
 def test_kernel_source_matches_reference(lib, task, force_generic):
     g = gu.load(task)
     p = gu.params_for(task, g)

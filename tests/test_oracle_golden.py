@@ -28,7 +28,7 @@ def _same(a, b, name, t):
     assert ok.all(), f"{name} step {t}: {int((~ok).sum())} of {ok.size} differ; max abs {np.abs(a.astype(np.float64) - b).max()}"
 
 
-@pytest.mark.parametrize("task", gu.TASKS)
+@pytest.mark.parametrize("task", gu.TASKS + gu.CC_SCENARIOS)
 def test_oracle_reproduces_reference(task):
     g = gu.load(task)
     p = gu.params_for(task, g)
@@ -43,6 +43,8 @@ def test_oracle_reproduces_reference(task):
             if k in exp:
                 _same(orc.st[k], exp[k], k, t)
         assert out["reset_count"] == int(exp["n_reset"])
+        if "command_ranges" in exp:                       # command curriculum: Python floats moved by np.clip in double
+            assert orc.st["command_ranges"].tolist() == exp["command_ranges"].tolist(), (t, orc.st["command_ranges"], exp["command_ranges"])
         assert gu.critic_sha(out["obs_buf"].numpy(), out["privileged_obs_buf"].numpy(), out["estimated_obs_buf"].numpy(),
                              out["scan_obs_buf"].numpy()) == str(exp["critic_sha"])
         _same(out["critic_obs_buf"], np.concatenate([exp["obs_buf"], exp["privileged_obs_buf"], exp["estimated_obs_buf"],
