@@ -27,6 +27,7 @@ def load():
     lib.emul_pd_torques.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_void_p, C.c_int]
     lib.emul_post_physics_step.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64]
     lib.emul_post_physics_step_variant.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64, C.c_int]
+    lib.emul_command_curriculum_rule.argtypes = [C.POINTER(EnvParams), C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.emul_env_init.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.POINTER(InitParams)]
     lib.emul_reset_all.argtypes = [C.POINTER(EnvParams), C.POINTER(EnvBuffers), C.c_int64, C.c_int]
     return lib

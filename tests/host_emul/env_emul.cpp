@@ -102,6 +102,12 @@ int emul_post_physics_step(const B200EnvParams* p, const B200EnvBuffers* b, int6
   return emul_post_physics_step_variant(p, b, step, 0);
 }
 
+// the command-curriculum rule alone (go2.py:87-107): {lo, hi} in force -> {lo, hi} after `count` resets with episode-sum `sum`
+int emul_command_curriculum_rule(const B200EnvParams* p, int count, double sum, const double* in_force, double* next) {
+  command_curriculum_rule(*p, count, sum, in_force, next);
+  return 0;
+}
+
 int emul_env_init(const B200EnvParams* p, const B200EnvBuffers* b, const B200InitParams* init) {
   for (int e = 0; e < p->num_envs; ++e) env_init_one(*p, *b, *init, e);
   return 0;

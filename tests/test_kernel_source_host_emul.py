@@ -124,3 +124,42 @@ def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
         gu.check_step(bufs, gu.oracle_expected(orc, out), t)
         total += out["reset_count"]
     assert total > 0 or num_envs < 64
+
+
+def test_command_curriculum_rule_matches_reference_arithmetic(lib):
+    """go2.py:87-107 restated with the reference's own types (fp32 0-dim tensor mean, Python-float thresholds, np.clip on
+    Python floats) against command_curriculum_rule of the kernel source, over random ranges / limits / sums -- including the
+    positive-max_reverse_vel branch whose np.clip upper bound is the value itself and sums right at the 80 % mark."""
+    from legged_gym_custom_b200.params import EnvParams
+    rng = np.random.default_rng(5)
+    moved = 0
+    for trial in range(400):
+        p = EnvParams()
+        scale_dt = float(rng.uniform(0.01, 0.1))
+        p.max_episode_length = int(rng.integers(2, 2000))
+        p.cc_threshold = 0.8 * scale_dt
+        p.cc_vel_increment = float(rng.choice([0.05, 0.1, 0.25]))
+        p.cc_max_forward_vel = float(rng.uniform(0.5, 3.0))
+        p.cc_max_reverse_vel = float(rng.uniform(-2.0, 1.0))
+        lo, hi = sorted(float(v) for v in rng.uniform(-1.5, 2.5, 2))
+        n = int(rng.integers(0, 6))
+        frac = float(rng.choice([0.5, 0.79999, 0.8, 0.80001, 1.2]))
+        sums = torch.full((max(n, 1),), frac * scale_dt * p.max_episode_length) * torch.from_numpy(rng.uniform(0.999, 1.001, max(n, 1))).float()
+        want_lo, want_hi = lo, hi
+        if n > 0:                                                        # reset_idx returns before the curriculum when nothing resets
+            mean = torch.mean(sums[:n]) / p.max_episode_length
+            if mean > 0.8 * scale_dt:
+                d = p.cc_vel_increment
+                if p.cc_max_reverse_vel < 0.0:
+                    want_lo = float(np.clip(lo - d, p.cc_max_reverse_vel, 0.))
+                else:
+                    want_lo = float(np.clip(lo - d, p.cc_max_reverse_vel, lo - d))
+                want_hi = float(np.clip(hi + d, 0., p.cc_max_forward_vel))
+                moved += 1
+        src, dst = (C.c_double * 2)(lo, hi), (C.c_double * 2)()
+        total = float(sums[:n].double().sum()) if n else 0.0
+        lib.emul_command_curriculum_rule(C.byref(p), n, total, src, dst)
+        # the kernel forms the mean from an fp64 sum: equal to torch's fp32 mean up to its last bit, so only trials whose mean
+        # sits within one ulp of the mark may legitimately differ -- there are none by construction (0.79999 / 0.80001)
+        assert (dst[0], dst[1]) == (want_lo, want_hi), (trial, n, frac, (lo, hi), (dst[0], dst[1]), (want_lo, want_hi))
+    assert 50 < moved < 350
