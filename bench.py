@@ -82,7 +82,7 @@ class Profile:
     def hook(self, name, raw, args):
         from legged_gym_custom_b200 import _lib
         if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version",
-                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
+                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_tc_set_sm_cap", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
             return raw(*args)
         self.count += _lib.LAUNCHES.get(name, 1)
         self.by_entry[name] = self.by_entry.get(name, 0) + _lib.LAUNCHES.get(name, 1)
@@ -150,6 +150,10 @@ def build_runner(args, rank, world, device, host_physx=False):
     # fine-tuned policy); no checkpoint ships with the reference, so the weights are random-init either way
     tc["runner"]["resume"] = bool(args.resume if args.resume is not None else args.task.endswith("finetune"))
     runner = OnPolicyRunner(env, tc, log_dir=None, device=device, process_group=pg)
+    if args.side_sm_cap is not None:
+        runner.alg.side_sm_cap = args.side_sm_cap
+    if args.side_sm_cap_forward is not None:
+        runner.alg.side_sm_cap_forward = args.side_sm_cap_forward
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
     if not args.no_graphs:
         runner.enable_graphs()
@@ -483,6 +487,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--pdl", action="store_true", help="launch the tcgen05 GEMMs with programmatic dependent launch (A/B; default off)")
+    ap.add_argument("--side-sm-cap", type=int, default=None, help="SMs the low-priority side chains of the update may occupy (A/B; 0 = all)")
+    ap.add_argument("--side-sm-cap-forward", type=int, default=None, help="the same for the side chains' forward GEMMs only (default: = --side-sm-cap)")
     ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":

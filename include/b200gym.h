@@ -360,6 +360,10 @@ int b200_tc_set_trace(unsigned long long* dev_buf, long long* host_meta, int cap
  * descriptor prefetch overlap the previous kernel's tail.  Off by default: measured neutral-to-negative for the update
  * (early-resident CTAs take SMs away from the kernels of the side streams).  Returns 0. */
 int b200_tc_set_pdl(int on);
+/* GEMM launches issued while a cap is set size their persistent grid (and the wgrad split-K) for `sms` SMs instead of the whole
+ * device; 0 = no cap.  The learner caps the low-priority side-stream chains (critic, estimator) so that their one-wave
+ * persistent kernels leave SMs to the small kernels of the critical path.  Host-side state, read at launch time. */
+int b200_tc_set_sm_cap(int sms);
 /* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
  * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */
 int b200_tc_linear_supported(int M, int N, int K);

@@ -552,6 +552,16 @@ unsigned long long* g_trace = nullptr;
 long long* g_trace_meta = nullptr;
 int g_trace_cap = 0, g_trace_next = 0;
 
+// b200_tc_set_sm_cap: launches issued while a cap is set size their persistent grid (and the wgrad's split-K) for `cap` SMs
+// instead of all of them.  A persistent one-wave kernel holds every SM until it ends, so a LOW-priority big GEMM starves the
+// small kernels of the critical path no matter what the stream priorities say (priorities only order PENDING CTAs): the
+// learner caps the side-stream chains and leaves the rest of the machine to the critical path.
+int g_sm_cap = 0;
+int avail_sms() {
+  const int n = num_sms();
+  return (g_sm_cap > 0 && g_sm_cap < n) ? g_sm_cap : n;
+}
+
 int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
 
 template <int MODE, int BN, bool PAIR = false>
@@ -579,7 +589,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
     gt.trace = g_trace + 2 * (size_t)i;
   }
   const int tiles = ((g.M + Cfg::BMT - 1) / Cfg::BMT) * ((g.N + BN - 1) / BN);
-  int workers = (PAIR ? num_sms() / 2 : num_sms()) / (splits > 1 ? splits : 1);
+  int workers = (PAIR ? avail_sms() / 2 : avail_sms()) / (splits > 1 ? splits : 1);
   workers = workers < 1 ? 1 : workers;
   workers = tiles < workers ? tiles : workers;
   cudaLaunchConfig_t cfg = {};
@@ -677,6 +687,11 @@ int b200_tc_set_pdl(int on) {
   return 0;
 }
 
+int b200_tc_set_sm_cap(int sms) {
+  g_sm_cap = sms > 0 ? sms : 0;
+  return 0;
+}
+
 int b200_tc_set_pair_mode(int on) {
   g_pair_mode = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 forward only (default), 2 forward + dgrad
   return 0;
@@ -759,7 +774,7 @@ int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, flo
   TcArgs g{};
   g.C = dW; g.ldc = ldw; g.M = N; g.N = K; g.K = M;
   const int tiles = ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
-  int splits = num_sms() / (tiles < 1 ? 1 : tiles);
+  int splits = avail_sms() / (tiles < 1 ? 1 : tiles);
   const int max_splits = (M + 8 * BK - 1) / (8 * BK);
   splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
   int per = (M + splits - 1) / splits;

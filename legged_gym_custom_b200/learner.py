@@ -187,6 +187,12 @@ class PPO:
         self.use_device_counter = False
         self.use_graphs = False
         self.use_streams = True
+        # SMs the low-priority side chains of a minibatch (estimator, critic) may occupy; 0 = all.  Their big GEMMs are
+        # one-wave persistent kernels that hold every SM until they end, which starves the small kernels of the critical
+        # path whatever the stream priorities are (b200_tc_set_sm_cap).  Measured on B200 (148 SMs), update of 20 minibatches:
+        # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt)
+        self.side_sm_cap = 116
+        self.side_sm_cap_forward = None      # cap of the side chains' FORWARD GEMMs; None = the same as side_sm_cap
         self.defer_critic_join = False      # act(): leave the critic chain running until process_env_step (OnPolicyRunner sets it)
         self._pending_critic = None
         self._graphs, self._graph_calls = {}, {}
@@ -404,13 +410,14 @@ class PPO:
         with self._on(s_hi):
             ac.fwd_priv(ws, priv, ldp, X + 4 * ac.col_latent, ld, M)
         # estimator: forward, loss, backward, own optimiser (ppo.py:224-231) -- fully independent chain
-        with self._on(s_est):
+        with self._capped(s_est, forward=True):
             est.fwd(ws, X, ld, _p(pred), 4, M)
             _lib.check(self.lib.b200_mse_rows_loss(_p(pred), 4, tgt_est, ldte, _p(dpred), 4, _p(self.loss_sums, 4), M, est.output_dim,
                                                    _lib.stream_ptr()))
+        with self._capped(s_est):
             chain_backward(est.k, est.layers, ws, "e", X + 4 * est.in_col, ld, _p(dpred), 4, M)
             self._adam(est.group)
-        with self._on(s_crit):
+        with self._capped(s_crit, forward=True):
             ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
         with self._on(s_hi):
             self._join([s_scan])
@@ -433,7 +440,7 @@ class PPO:
             _lib.check(self.lib.b200_ppo_loss(C.byref(a), _lib.stream_ptr()))
             # backward: critic on its own stream; actor (input gradient only for the latent / scan-latent columns) here
             self._fork_onto([s_crit])
-        with self._on(s_crit):
+        with self._capped(s_crit):
             chain_backward(k, ac.critic, ws, "c", crit, s.d_crit, _p(dval), 4, M)
         with self._on(s_hi):
             chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M)
@@ -475,6 +482,24 @@ class PPO:
     def _on(self, stream):
         import contextlib
         return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def _capped(self, stream, forward=False):
+        """`_on(stream)` for a LOW-priority chain of the update: its GEMM launches are sized for `side_sm_cap` SMs"""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            cap = self.side_sm_cap_forward if (forward and self.side_sm_cap_forward is not None) else self.side_sm_cap
+            cap = cap if (self.use_streams and stream is not None) else 0
+            if cap:
+                self.lib.b200_tc_set_sm_cap(int(cap))
+            try:
+                with self._on(stream):
+                    yield
+            finally:
+                if cap:
+                    self.lib.b200_tc_set_sm_cap(0)
+        return ctx()
 
     def _join(self, streams):
         for s in streams:
