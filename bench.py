@@ -152,6 +152,8 @@ def build_runner(args, rank, world, device, host_physx=False):
     runner = OnPolicyRunner(env, tc, log_dir=None, device=device, process_group=pg)
     if args.side_sm_cap is not None:
         runner.alg.side_sm_cap = args.side_sm_cap
+    if args.offload_wgrads is not None:
+        runner.alg.offload_wgrads = bool(args.offload_wgrads)
     if args.side_sm_cap_forward is not None:
         runner.alg.side_sm_cap_forward = args.side_sm_cap_forward
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
@@ -489,6 +491,7 @@ def main():
     ap.add_argument("--pdl", action="store_true", help="launch the tcgen05 GEMMs with programmatic dependent launch (A/B; default off)")
     ap.add_argument("--side-sm-cap", type=int, default=None, help="SMs the low-priority side chains of the update may occupy (A/B; 0 = all)")
     ap.add_argument("--side-sm-cap-forward", type=int, default=None, help="the same for the side chains' forward GEMMs only (default: = --side-sm-cap)")
+    ap.add_argument("--offload-wgrads", type=int, default=None, help="actor / encoder weight-gradient GEMMs on their own low-priority stream (A/B)")
     ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":

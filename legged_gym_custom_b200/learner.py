@@ -193,6 +193,9 @@ class PPO:
         # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt)
         self.side_sm_cap = 116
         self.side_sm_cap_forward = None      # cap of the side chains' FORWARD GEMMs; None = the same as side_sm_cap
+        # weight-gradient GEMMs of the actor / encoder chains on a fifth (low-priority, capped) stream: the dgrad chain that
+        # the encoders' backward waits for no longer queues behind them
+        self.offload_wgrads = False
         self.defer_critic_join = False      # act(): leave the critic chain running until process_env_step (OnPolicyRunner sets it)
         self._pending_critic = None
         self._graphs, self._graph_calls = {}, {}
@@ -404,7 +407,8 @@ class PPO:
         # backward -> encoder backward; it runs on HIGH-priority streams (s_hi; the scan encoder beside it on s_scan) and
         # is issued first, so the big estimator / critic GEMMs of the low-priority streams fill in around it instead of
         # delaying it (measured with tools/trace_update.py: the actor's first layer used to start at 169 us of 741).
-        s_hi, s_scan, s_est, s_crit = self._fork(4)
+        s_hi, s_scan, s_est, s_crit, s_w = self._fork(5)
+        off = self._offload(s_w) if self.offload_wgrads else None
         with self._on(s_scan):
             ac.fwd_scan(ws, scan, s.d_scan, X + 4 * ac.col_scan, ld, M)
         with self._on(s_hi):
@@ -443,16 +447,16 @@ class PPO:
         with self._capped(s_crit):
             chain_backward(k, ac.critic, ws, "c", crit, s.d_crit, _p(dval), 4, M)
         with self._on(s_hi):
-            chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M)
+            chain_backward(k, ac.actor, ws, "a", X, ld, _p(dmu), A, M, wgrad_on=off)
             da0, lda0 = ws.ptr("da0", M, ceil4(ac.actor[0].N)), ceil4(ac.actor[0].N)
             # columns [latent | scan latent] of the first layer's input gradient in one pass; the regulariser's gradient, which
             # the loss head left in the first L columns, is accumulated (accumulate = number of leading columns)
             k.dgrad(ac.actor[0], da0, lda0, None, 0, _p(dls), L + SL, M, accumulate=L, wcol=ac.col_latent, K=L + SL)
             self._fork_onto([s_scan])
-            chain_backward(k, ac.priv, ws, "p", priv, ldp, _p(dls), L + SL, M)
+            chain_backward(k, ac.priv, ws, "p", priv, ldp, _p(dls), L + SL, M, wgrad_on=off)
         with self._on(s_scan):
-            chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dls) + 4 * L, L + SL, M)
-        self._join([s_hi, s_scan, s_crit, s_est])
+            chain_backward(k, ac.scan, ws, "s", scan, s.d_scan, _p(dls) + 4 * L, L + SL, M, wgrad_on=off)
+        self._join([s_hi, s_scan, s_crit, s_est, s_w])
         self._adam(ac.main)
 
     # ---- side streams: estimator / critic / adaptation-encoder chains are independent of the actor chain until the loss
@@ -465,7 +469,7 @@ class PPO:
             return [None] * n
         if not hasattr(self, "_side"):
             lo, hi = 0, -1
-            self._side = [torch.cuda.Stream(device=self.device, priority=p) for p in (hi, hi, lo, lo)]
+            self._side = [torch.cuda.Stream(device=self.device, priority=p) for p in (hi, hi, lo, lo, lo)]
         self._fork_onto(self._side[:n])
         return self._side[:n]
 
@@ -482,6 +486,20 @@ class PPO:
     def _on(self, stream):
         import contextlib
         return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def _offload(self, stream):
+        """-> run(fn): launch `fn`'s kernels on `stream` (capped like the other low-priority chains), ordered after everything
+        queued on the CURRENT stream so far; None when there is no side stream (then callers launch inline)"""
+        if stream is None:
+            return None
+
+        def run(fn):
+            ev = torch.cuda.Event()
+            ev.record()
+            stream.wait_event(ev)
+            with self._capped(stream):
+                fn()
+        return run
 
     def _capped(self, stream, forward=False):
         """`_on(stream)` for a LOW-priority chain of the update: its GEMM launches are sized for `side_sm_cap` SMs"""

@@ -178,8 +178,10 @@ def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M):
         X, ldx = Y, ldy
 
 
-def chain_backward(k, layers, ws, tag, X0, ldx0, dOut, lddo, M, need_dx0=False, dX0=None, lddx0=0):
-    """backward of chain_forward: wgrad of every layer, dgrad between layers (elu' fused from the stored activation)."""
+def chain_backward(k, layers, ws, tag, X0, ldx0, dOut, lddo, M, need_dx0=False, dX0=None, lddx0=0, wgrad_on=None):
+    """backward of chain_forward: wgrad of every layer, dgrad between layers (elu' fused from the stored activation).
+    `wgrad_on(fn)`: run the weight-gradient launches `fn` elsewhere (another stream, ordered after everything queued here so
+    far): a layer's wgrad and dgrad both only READ dY, so the dgrad chain -- the critical path -- need not wait for the wgrads."""
     dY, lddy = dOut, lddo
     bias_done = False
     for i in reversed(range(len(layers))):
@@ -189,7 +191,10 @@ def chain_backward(k, layers, ws, tag, X0, ldx0, dOut, lddo, M, need_dx0=False, 
             X = ws.ptr(f"{tag}{i - 1}", M, ldx)
         else:
             X, ldx = X0, ldx0
-        k.wgrad(lin, dY, lddy, X, ldx, M, bias_done=bias_done)
+        if wgrad_on is not None:
+            wgrad_on(lambda lin=lin, dY=dY, lddy=lddy, X=X, ldx=ldx, bd=bias_done: k.wgrad(lin, dY, lddy, X, ldx, M, bias_done=bd))
+        else:
+            k.wgrad(lin, dY, lddy, X, ldx, M, bias_done=bias_done)
         bias_done = False
         if i > 0:
             dX = ws.ptr(f"d{tag}{i - 1}", M, ldx)

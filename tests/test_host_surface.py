@@ -7,7 +7,7 @@ from legged_gym_custom_b200 import env, learner, networks, runner
 def test_methods_exist():
     for cls, names in ((learner.PPO, ["act", "process_env_step", "compute_returns", "update", "update_dagger", "update_with_indices",
                                       "update_dagger_with_indices", "set_device_counter", "_run_captured", "_minibatch", "_dagger_minibatch",
-                                      "_fork", "_fork_onto", "_join", "_on", "_capped", "_adaptive_lr", "_adam", "_gather_storage", "init_storage", "enforce_max_std"]),
+                                      "_fork", "_fork_onto", "_join", "_on", "_capped", "_offload", "_adaptive_lr", "_adam", "_gather_storage", "init_storage", "enforce_max_std"]),
                        (runner.OnPolicyRunner, ["learn", "iteration", "rollout", "_rollout_eager", "enable_graphs", "save", "load",
                                                 "get_inference_policy", "log"]),
                        (env.Go2Env, ["step", "step5", "reset", "reset_idx", "set_device_counter", "get_observations",

@@ -246,12 +246,16 @@ def _fill(ppo, st):
     s.actions_log_prob.copy_(d(st["old_logp"])); s.mu.copy_(d(st["mu"])); s.sigma.copy_(d(st["sigma"]))
 
 
-def test_update_matches_reference_golden():
-    """PPO.update on the reference's golden storage / weights / permutation."""
+@pytest.mark.parametrize("offload_wgrads,graphs", [(False, False), (True, False), (True, True)],
+                         ids=["inline-wgrads", "wgrads-on-their-own-stream", "wgrads-on-their-own-stream+cuda-graphs"])
+def test_update_matches_reference_golden(offload_wgrads, graphs):
+    """PPO.update on the reference's golden storage / weights / permutation (the schedule of the launches -- weight
+    gradients inline or on a fifth stream, eager or graph-replayed -- must not change what is computed)."""
     T, N = 6, 32
     ac, est = _build(HID)
     ac.load_state_dict(_gold_sd("init/ac/")); est.load_state_dict(_gold_sd("init/est/"))
     ppo = _ppo(ac, est, N, T)
+    ppo.offload_wgrads, ppo.use_graphs = offload_wgrads, graphs
     ppo.total_updates = 2.0
     st = {k[len("storage/"):]: torch.from_numpy(GOLD[k]) for k in GOLD.files if k.startswith("storage/")}
     _fill(ppo, st)
