@@ -20,6 +20,6 @@ echo "racecheck env rc=$?"
 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_learner_$tag.log \
   python -m pytest tests/test_learner_gpu.py -q -x -k "update_matches or dagger_matches or adaptive" > gpurun_out/sanitize_learner_$tag.out 2>&1
 echo "memcheck learner rc=$?"
-python tools/trace_update.py > gpurun_out/minibatch_timeline_$tag.csv 2> gpurun_out/minibatch_timeline_$tag.err
+python tools/trace_update.py gpurun_out/minibatch_timeline_$tag.json > gpurun_out/minibatch_timeline_$tag.txt 2> gpurun_out/minibatch_timeline_$tag.err
 python bench.py > gpurun_out/bench_${tag}_1gpu.json 2> gpurun_out/bench_${tag}.err
 tail -c 600 gpurun_out/bench_${tag}_1gpu.json
