@@ -126,6 +126,40 @@ def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
     assert total > 0 or num_envs < 64
 
 
+@pytest.mark.parametrize("control_type,randomize", [("V", True), ("T", True), ("P", False)])
+def test_kernel_source_torque_control_variants(lib, control_type, randomize):
+    """_compute_torques' other branches (legged_robot.py:456-471): velocity control, direct torque control, and position
+    control without kp / kd randomisation -- no go2 cfg selects them, the oracle and the kernel source must still agree
+    bit for bit (same fp32 operations in the same order)."""
+    import state_util as su
+    from legged_gym_custom_b200 import configs
+    from legged_gym_custom_b200.params import NUM_DOF, env_params_from_cfg
+    from oracle.go2_oracle import Go2Oracle
+    base = configs.TASKS["go2"][0]
+    cfg = type("Cfg", (base,), {"control": type("control", (base.control,), {"control_type": control_type}),
+                                "domain_rand": type("domain_rand", (base.domain_rand,), {"randomize_kp_kd": randomize})})
+    N = 257
+    p = env_params_from_cfg(cfg, num_envs=N, seed=5)
+    assert p.control_type == {"P": 0, "V": 1, "T": 2}[control_type] and p.randomize_kp_kd == int(randomize)
+    rng = np.random.default_rng(11)
+    statics, st = su.random_statics(p, rng), su.random_state(p, rng)
+    st["dof_state"] = torch.from_numpy(np.stack([rng.normal(0, 0.5, N * NUM_DOF), rng.normal(0, 2.0, N * NUM_DOF)], 1).astype(np.float32))
+    orc = Go2Oracle(p, statics, st)
+    bufs = BufferSet(p, "cpu")
+    bufs.load_statics(statics)
+    st2 = dict(st)
+    st2.pop("common_step_counter")
+    bufs.load_state(st2)
+    actions = torch.from_numpy(rng.normal(0, 2.5, (N, NUM_DOF)).astype(np.float32))     # beyond clip_actions and the torque limits
+    orc.clip_actions(actions)
+    want = orc.compute_torques()
+    lib.emul_pd_torques(C.byref(p), C.byref(bufs.struct), C.c_void_p(actions.data_ptr()), 1)
+    assert torch.equal(bufs["actions"], orc.st["actions"])
+    assert torch.equal(bufs["torques"], want)
+    if control_type != "T":                      # direct torques (action x 0.25) never reach the limits; the PD modes must
+        assert (want.abs() == torch.tensor(list(p.torque_limits))).any() and (want.abs() < torch.tensor(list(p.torque_limits))).any()
+
+
 def test_command_curriculum_rule_matches_reference_arithmetic(lib):
     """go2.py:87-107 restated with the reference's own types (fp32 0-dim tensor mean, Python-float thresholds, np.clip on
     Python floats) against command_curriculum_rule of the kernel source, over random ranges / limits / sums -- including the
