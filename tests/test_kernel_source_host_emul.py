@@ -126,6 +126,52 @@ def test_kernel_source_matches_oracle_at_scale(lib, task, num_envs, steps):
     assert total > 0 or num_envs < 64
 
 
+@pytest.mark.parametrize("flag", ["noise.add_noise", "rewards.only_positive_rewards", "domain_rand.push_robots", "commands.zero_command"])
+def test_kernel_source_with_cfg_switches_flipped(lib, flag):
+    """the cfg switches every shipped go2 cfg leaves at one value, flipped: observation noise off, negative total rewards
+    kept (legged_robot.py:230-231), no pushes, no zero-command draws (go2.py:450-456).  5 steps from counter 397, so the
+    push step (400) is inside the window.  Oracle (pinned to the reference for the shipped values) vs kernel source."""
+    import state_util as su
+    from legged_gym_custom_b200 import configs, synth
+    from legged_gym_custom_b200.params import NUM_DOF, env_params_from_cfg
+    from oracle.go2_oracle import Go2Oracle
+    base = configs.TASKS["go2_parkour"][0]
+    group, name = flag.split(".")
+    sub = getattr(base, group)
+    cfg = type("Cfg", (base,), {group: type(group, (sub,), {name: not getattr(sub, name)})})
+    hs, origins = gu.terrain_for("go2_parkour")
+    N = 300
+    p = env_params_from_cfg(cfg, num_envs=N, seed=17, hs_shape=hs.shape)
+    assert getattr(p, {"add_noise": "add_noise", "only_positive_rewards": "only_positive_rewards", "push_robots": "push_robots",
+                       "zero_command": "zero_command"}[name]) == int(not getattr(sub, name))
+    rng = np.random.default_rng(23)
+    statics, st = su.random_statics(p, rng, hs, origins), su.random_state(p, rng, origins, step0=397)
+    orc = Go2Oracle(p, statics, st)
+    bufs = BufferSet(p, "cpu", record_height_index=True)
+    bufs.load_statics(statics)
+    st2 = dict(st)
+    step = int(st2.pop("common_step_counter"))
+    bufs.load_state(st2)
+    origins0 = st["env_origins"].numpy()
+    negative = 0
+    for t in range(5):
+        frames = synth.make_frames(N, origins0, rng, hole_prob=0.01, flip_prob=0.01)
+        actions = torch.from_numpy(rng.normal(0, 1.5, (N, NUM_DOF)).astype(np.float32))
+        out = orc.step(actions, frames)
+        for k in range(p.decimation):
+            lib.emul_pd_torques(C.byref(p), C.byref(bufs.struct), C.c_void_p(actions.data_ptr()), int(k == 0))
+            bufs["dof_state"].copy_(torch.from_numpy(frames["dof"][k]))
+        bufs["root_states"].copy_(torch.from_numpy(frames["root"]))
+        bufs["contact_forces"].copy_(torch.from_numpy(frames["contact"]))
+        bufs["rigid_body_states"].copy_(torch.from_numpy(frames["rigid"]))
+        step += 1
+        lib.emul_post_physics_step(C.byref(p), C.byref(bufs.struct), step)
+        gu.check_step(bufs, gu.oracle_expected(orc, out), t)
+        negative += int((out["rew_buf"] < 0).sum())
+    if name == "only_positive_rewards":
+        assert negative > 0                    # the un-clipped branch was really exercised
+
+
 @pytest.mark.parametrize("control_type,randomize", [("V", True), ("T", True), ("P", False)])
 def test_kernel_source_torque_control_variants(lib, control_type, randomize):
     """_compute_torques' other branches (legged_robot.py:456-471): velocity control, direct torque control, and position
