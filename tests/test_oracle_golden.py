@@ -32,7 +32,12 @@ def _same(a, b, name, t):
 def test_oracle_reproduces_reference(task):
     g = gu.load(task)
     p = gu.params_for(task, g)
-    orc = Go2Oracle(p, gu.statics_for(task, g), gu.init_state(g, p))
+    replay_oracle(g, p, gu.statics_for(task, g))
+
+
+def replay_oracle(g, p, statics):
+    """step the oracle through the replay `g` (npz or dict-like with .files) and require every tensor bit for bit"""
+    orc = Go2Oracle(p, statics, gu.init_state(g, p))
     for t in range(int(g["steps"])):
         out = orc.step(torch.from_numpy(g[f"step{t}/in/actions"]), gu.frames_of(g, t))
         exp = gu.expected(g, t)
