@@ -10,8 +10,10 @@ parkour layouts the go2 tasks use -- `parkour_curriculum` (terrain.py:103-115,
 reference nor a 19 MB fixture.  tests/test_terrain.py pins it against the reference's
 own `Terrain` output (sha256 in tests/golden/terrain_sha.json).
 
-The trimesh conversion for PhysX (terrain_utils.convert_heightfield_to_trimesh) is the
-simulator's input, not the hot path's, and is out of scope.
+`heightfield_to_trimesh` is the simulator-side half of SURVEY.md §8(f1): the vertex / triangle arrays PhysX is fed
+(terrain_utils.py:401-465, called from terrain.py:52-57), so that an Isaac Gym adapter needs nothing from the reference's
+terrain modules.  Init-time host numpy (~1 s for the 3860 x 2500 parkour field, the same as the reference's row loop): the
+arrays go to `gym.add_triangle_mesh`, never to our kernels.
 """
 import numpy as np
 
@@ -70,3 +72,39 @@ def make_parkour_terrain(tcfg):
             field[r0:r0 + length_px, c0:c0 + width_px] = tile
             origins[i, j] = [i * tcfg.terrain_length, (j + 0.5) * tcfg.terrain_width, 0.0]   # start line, centred in y
     return field, origins.astype(np.float32)
+
+
+def heightfield_to_trimesh(height_field_raw, horizontal_scale, vertical_scale, slope_threshold=None):
+    """-> (vertices float32 [rows*cols, 3], triangles uint32 [2*(rows-1)*(cols-1), 3]), identical to the reference's
+    convert_heightfield_to_trimesh (terrain_utils.py:401-465).
+
+    Vertex (i, j) sits at (i, j) * horizontal_scale, height * vertical_scale.  With a slope threshold, a vertex at the foot of
+    a step steeper than the threshold is pulled under the step's edge (+1 cell) and a vertex at its top is pushed out over the
+    foot (-1 cell), along x, along y, and -- where neither applies -- along the diagonal, which turns steep ramps into
+    vertical walls.  Cell (i, j) contributes the triangles (v00, v11, v01) and (v00, v10, v11)."""
+    hf = np.asarray(height_field_raw)
+    rows, cols = hf.shape
+    # float64 grid like np.linspace / np.meshgrid in the reference (the fp32 cast happens when the vertices are stored)
+    yy, xx = np.meshgrid(np.linspace(0, (cols - 1) * horizontal_scale, cols), np.linspace(0, (rows - 1) * horizontal_scale, rows))
+    if slope_threshold is not None:
+        thr = slope_threshold * horizontal_scale / vertical_scale
+        rise_x = np.diff(hf, axis=0)                      # hf[i+1, j] - hf[i, j]   (int16 arithmetic, as in the reference)
+        rise_y = np.diff(hf, axis=1)
+        rise_d = hf[1:, 1:] - hf[:-1, :-1]
+        move_x, move_y, move_d = (np.zeros((rows, cols)) for _ in range(3))
+        move_x[:-1, :] += rise_x > thr
+        move_x[1:, :] -= -rise_x > thr
+        move_y[:, :-1] += rise_y > thr
+        move_y[:, 1:] -= -rise_y > thr
+        move_d[:-1, :-1] += rise_d > thr
+        move_d[1:, 1:] -= -rise_d > thr
+        xx = xx + (move_x + move_d * (move_x == 0)) * horizontal_scale
+        yy = yy + (move_y + move_d * (move_y == 0)) * horizontal_scale
+    vertices = np.empty((rows * cols, 3), dtype=np.float32)
+    vertices[:, 0], vertices[:, 1], vertices[:, 2] = xx.ravel(), yy.ravel(), hf.ravel() * vertical_scale
+    v00 = (np.arange(rows - 1, dtype=np.uint32)[:, None] * np.uint32(cols) + np.arange(cols - 1, dtype=np.uint32)[None, :]).ravel()
+    v01, v10, v11 = v00 + np.uint32(1), v00 + np.uint32(cols), v00 + np.uint32(cols + 1)
+    triangles = np.empty((2 * v00.size, 3), dtype=np.uint32)
+    triangles[0::2] = np.stack((v00, v11, v01), axis=1)
+    triangles[1::2] = np.stack((v00, v10, v11), axis=1)
+    return vertices, triangles
