@@ -51,6 +51,57 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _kl_worker(rank, world, port, out):
+    """schedule='adaptive' across ranks (learner.PPO._adaptive_lr): every rank adds its minibatch's KL SUM, the sums are
+    all-reduced, and the rule is applied to sum / (M * world) -- so all replicas move their learning rate together"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    pg = bdist.init_process_group("gloo")
+    lr, log = 2e-4, []
+    for step in range(4):
+        mu, old_mu, sigma, old_sigma = _kl_batch(step, rank)
+        kl = torch.sum(torch.log(sigma / old_sigma + 1.e-5) + (old_sigma ** 2 + (old_mu - mu) ** 2) / (2.0 * sigma ** 2) - 0.5, dim=-1)
+        acc = kl.double().sum().reshape(1)                          # kl_sum_kernel's accumulator
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=pg)
+        kl_mean = (acc / (mu.shape[0] * world)).float()             # adaptive_lr_kernel
+        if kl_mean > 0.01 * 2.0:
+            lr = max(1e-5, lr / 1.5)
+        elif kl_mean < 0.01 / 2.0 and kl_mean > 0.0:
+            lr = min(1e-2, lr * 1.5)
+        log.append(lr)
+    out.put((rank, log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _kl_batch(step, rank, M=64, A=12):
+    g = torch.Generator().manual_seed(100 * step + rank)
+    spread = [0.0, 0.02, 0.5, 0.5][step] * (1 + rank)               # rank 1 always sees the larger policy change
+    mu = torch.randn(M, A, generator=g)
+    return mu, mu + spread * torch.randn(M, A, generator=g), torch.ones(M, A), torch.ones(M, A)
+
+
+def test_two_rank_adaptive_kl_decision_is_global():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_kl_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    logs = dict(out.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert logs[0] == logs[1]
+    # single-process oracle on the concatenated minibatches (oracle.learner_oracle.adaptive_lr = ppo.py:233-246)
+    lr, want = 2e-4, []
+    for step in range(4):
+        b = [_kl_batch(step, r) for r in range(world)]
+        mu, old_mu, sigma, old_sigma = (torch.cat([x[i] for x in b]) for i in range(4))
+        lr, _ = lo.adaptive_lr(lr, mu, sigma, old_mu, old_sigma, 0.01)
+        want.append(lr)
+    assert logs[0] == want and len(set(want)) >= 3                  # grows, holds / shrinks: more than one branch taken
+
+
 def test_two_rank_gradient_exchange_keeps_replicas_identical():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
