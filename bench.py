@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 T_STEPS = 24
-SETUP_ITERS = 3                  # build_runner: DAgger iteration, eager + graph capture, first replay
+SETUP_ITERS = 1                  # build_runner: every CUDA graph is captured up front (runner.capture_graphs), then iteration 0 (DAgger)
 ENV_BYTES_PER_ENV = 12618        # post-physics algorithmic bytes per env-step
 PD_BYTES_PER_ENV = 288           # one PD-torque pass
 
@@ -46,30 +46,57 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region, sampled IN PROCESS through NVML (rank 0 only: one poller per
+    box, no forked nvidia-smi competing for the driver lock with the timed loop); nvidia-smi only if NVML cannot be loaded."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.how = index, [], False, "nvml"
+        self.h = self.nv = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h, self.nv = nv.nvmlDeviceGetHandleByIndex(phys), nv
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.how = "nvidia-smi"
 
-    def run(self):
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        bits = [getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return [sm, self.max_sm] + [bool(r & b) for b in bits]
+
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        x = [v.strip() for v in out.split(",")]
+        return [float(x[0]), float(x[1])] + [v.lower().startswith("active") for v in x[2:6]]
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.rows.append(self._sample_nvml() if self.h is not None else self._sample_smi())
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.h is not None else 0.2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "how": self.how}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows), "how": self.how}
 
 
 class Profile:
@@ -159,10 +186,11 @@ def build_runner(args, rank, world, device, host_physx=False):
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
     if not args.no_graphs:
         runner.enable_graphs()
-    # set-up, not measurement: iteration 0 is the DAgger iteration (it % 20 == 0, eager), iteration 1 launches eagerly
-    # (allocations, kernel attributes) and captures the CUDA graphs, iteration 2 is their first replay.  The W warm-up and
-    # K timed iterations that follow are then all steady-state PPO iterations, whatever W is.
-    for it in range(SETUP_ITERS):
+        # set-up, not measurement: BOTH rollout graphs (adaptation_mode on / off) and every PPO / DAgger minibatch graph are
+        # captured here, so no capture (synchronize + instantiate of a ~1 400-node graph) can fall into a timed window
+        # whichever iterations it covers (every 20th is a DAgger iteration with the adaptation-mode rollout).
+        runner.capture_graphs()
+    for it in range(SETUP_ITERS):          # iteration 0: the DAgger iteration the reference's loop starts with
         runner.iteration(it)
     torch.cuda.synchronize()
     return env, runner
@@ -208,13 +236,15 @@ def run_b200(args):
     for it in range(SETUP_ITERS, SETUP_ITERS + W):
         runner.iteration(it)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    sampler = ClockSampler(local) if rank == 0 else None      # one in-process NVML poller per box
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.2)
     first = SETUP_ITERS + W
     elapsed = timed_iterations(runner, first, K, world)
-    sampler.stop_flag = True
-    sampler.join(timeout=3)
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
     value = T_STEPS * N * world * K / elapsed
 
     # ---- where the time goes: rollout (+GAE) vs update, CUDA events around the two halves of 2 more iterations
@@ -332,28 +362,20 @@ def run_b200(args):
     # ---- end to end: PhysX frames in pinned host memory copied in every substep, results read back every step
     e2e = None
     if args.e2e_steps > 0:
-        env2, runner2 = build_runner(args, rank, world, device, host_physx=True)
-        host_rew = torch.zeros(N).pin_memory()
-        host_done = torch.zeros(N, dtype=torch.bool).pin_memory()
-        d2h = [0]
-        orig_step = env2.step
-
-        def step_with_readback(actions):
-            out = orig_step(actions)
-            host_rew.copy_(out[5], non_blocking=True)
-            host_done.copy_(out[6], non_blocking=True)
-            d2h[0] += N * 5
-            return out
-        env2.step = step_with_readback
+        env2, runner2 = build_runner(args, rank, world, device, host_physx=True)      # HostPhysX is part of every captured env step
         for it in range(SETUP_ITERS, SETUP_ITERS + 2):
             runner2.iteration(it)
         t2 = timed_iterations(runner2, SETUP_ITERS + 2, args.e2e_steps, world)
+        px = env2.physx
         e2e = {"value": T_STEPS * N * world * args.e2e_steps / t2, "unit": "env-steps/s",
-               "h2d_bytes_per_step": env2.physx.bytes_per_step * T_STEPS, "d2h_bytes_per_step": T_STEPS * N * 5 + 5 * 4,
+               "h2d_bytes_per_step": px.bytes_per_step * T_STEPS, "d2h_bytes_per_step": px.d2h_bytes_per_step * T_STEPS + 5 * 4,
                "ms_per_step": t2 / args.e2e_steps * 1e3,
                "h2d": "per env step, from pinned host memory: root_states, contact_forces and the last substep's dof_state are copied; "
                       "the dof_state of substeps 0-2 is streamed in place by the next PD-torque kernel and rigid_body_states (4 of 247 "
-                      "floats per env are read) by the post-physics kernel (zero-copy; counted in full, resp. at 32 B per read)"}
+                      "floats per env are read) by the post-physics kernel (zero-copy; counted in full, resp. at 32 B per read)",
+               "d2h": "per env step, into pinned host memory: the torques of each of the 4 substeps (what a host simulator is actuated "
+                      "with), root_states + dof_state + reset flags after the step (the rows the reference pushes back on reset / "
+                      "push, sent whole), rewards and dones; per iteration: the 5 logged loss means"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,8 +390,8 @@ def run_b200(args):
                                        "PhysX replaced by a ring of replayed synthetic frames",
                            "num_envs_per_gpu": N, "parallelism": f"dp{world} (envs sharded, flat-gradient NCCL all-reduce)",
                            "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
-                           "timed_iterations": f"it {first}..{first + K - 1} (every 20th is a DAgger iteration, as in the reference's loop; it 0-2 are "
-                                               "set-up: DAgger iteration, eager pass + CUDA-graph capture, first replay)",
+                           "timed_iterations": f"it {first}..{first + K - 1} (every 20th is a DAgger iteration with the adaptation-mode rollout, as in the "
+                                               "reference's loop; all CUDA graphs are captured during set-up, before it 0)",
                            "launch": "CUDA graphs (rollout+GAE: 1 graph; update: 1 graph per minibatch slot)" if not args.no_graphs else "eager"},
                 "e2e": e2e, "split": split, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "roofline_env": roof_env, "cpu_baseline": cpu,
                 "kernels": breakdown, "losses": {k: round(float(v), 6) for k, v in runner.last_losses.items()}}

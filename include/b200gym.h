@@ -436,7 +436,11 @@ int b200_adaptive_lr(double* acc, int64_t count, double desired_kl, double* adam
 /* clip_grad_norm_ + Adam.step on flat buffers (ppo.py:228-231, :273-276, :336-339); zeroes `grads`.
  * grad_scale = 1/world_size after the NCCL sum all-reduce of `grads`.
  * `state` = 8 doubles on the device: [0] scratch, [1] step, [2] beta1^step, [3] beta2^step, [4] lr -- advanced
- * by the call itself so a captured CUDA graph replays correctly (initialise to {0, 0, 1, 1, lr}). */
+ * by the call itself so a captured CUDA graph replays correctly (initialise to {0, 0, 1, 1, lr, 0, 0, 0}).
+ * [7] (in) squared norm of gradients OUTSIDE `grads` that the reference's clip_grad_norm_ call also covers (ppo.py:274
+ * clips actor_critic.parameters(): the adaptation encoder's stale post-clip .grad of the last update_dagger is part of
+ * the norm and is rescaled with it); the call consumes it as [5] and leaves the rescaled value in [7] for the next step.
+ * [6] (out) post-clip squared norm of `grads` -- what update_dagger hands to the main optimiser's [7]. */
 int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
                    float grad_scale, float max_norm, float beta1, float beta2, float eps, void* stream);
 /* AdaptationEncoder.forward (support_networks.py:128-175) fused into one fp32 kernel.  X [M, >=520] = observation rows

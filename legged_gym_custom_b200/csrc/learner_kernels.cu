@@ -335,6 +335,7 @@ __global__ void adam_advance_kernel(double* __restrict__ state, double beta1, do
     state[1] += 1.0;
     state[2] *= beta1;
     state[3] *= beta2;
+    state[5] = state[7];      // stale squared norm covered by this step's clip (see clip_adam_kernel)
   }
 }
 
@@ -351,10 +352,21 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 // buffer is zeroed for the next accumulation.
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                 const double* __restrict__ state, float grad_scale, float max_norm, float beta1, float beta2, float eps) {
-  const float total_norm = (float)sqrt(state[0]) * grad_scale;
+                 double* state, float grad_scale, float max_norm, float beta1, float beta2, float eps) {
+  // state[5]: squared norm of gradients OUTSIDE this buffer that the same clip_grad_norm_ call covers and rescales --
+  // ppo.py:274 clips actor_critic.parameters(), which includes the adaptation encoder's stale .grad left (post-clip) by the
+  // last update_dagger; optimizer.zero_grad() never clears it.  0 unless the caller seeded state[7].
+  const double extra = state[5];
+  const float own_norm = (float)sqrt(state[0]) * grad_scale;
+  const float total_norm = extra > 0.0 ? (float)sqrt((double)own_norm * (double)own_norm + extra) : own_norm;
   float coef = max_norm / (total_norm + 1e-6f);
-  coef = (coef > 1.0f ? 1.0f : coef) * grad_scale;
+  coef = coef > 1.0f ? 1.0f : coef;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double* st_out = state;
+    st_out[6] = (double)own_norm * (double)own_norm * (double)coef * (double)coef;   // this buffer's post-clip squared norm
+    st_out[7] = extra * (double)coef * (double)coef;                                  // the stale gradients shrink with the clip
+  }
+  coef *= grad_scale;
   const float bc1 = (float)(1.0 - state[2]), bc2_sqrt = (float)sqrt(1.0 - state[3]);
   const float step_size = (float)state[4] / bc1;
   auto step = [&](float& pi, float& gi_, float& mi_, float& vi_) {

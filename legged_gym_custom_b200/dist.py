@@ -30,7 +30,7 @@ def init_process_group(backend=None, device=None):
 
 def shard_seed(seed, rank):
     """each rank owns its envs, its RNG keys and its minibatch permutation"""
-    return int(seed) + int(rank)
+    return int(seed) + 7919 * int(rank)
 
 
 def allreduce_flat_grads(groups, process_group):

@@ -294,34 +294,55 @@ for _name in ("obs_buf", "privileged_obs_buf", "critic_obs_buf", "estimated_obs_
 
 
 class HostPhysX:
-    """PhysX frames living in PINNED HOST memory (the reference's --sim_device=cpu pipeline hands the env host
-    tensors): every substep / refresh moves that step's frame host->device on the current stream.  dof_state, root_states
-    and contact_forces are read densely and are copied; rigid_body_states [N*19,13] is read at 4 floats per env (the feet
-    heights, go2.py:272-277), so the kernel reads it IN PLACE from the pinned buffer (zero-copy over PCIe) instead of
-    copying 4 MB per step.  Used by bench.py's end-to-end measurement; `bytes_per_step` counts what crosses the bus."""
+    """PhysX living on the HOST (the reference's --sim_device=cpu pipeline: the simulator reads and writes host tensors).
+    Every tensor that crosses the simulator boundary crosses the bus inside `Go2Env.step`, on the current stream:
 
-    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, zero_copy_rigid=True, zero_copy_dof=True, **frame_kw):
+    host -> device (pinned frames): dof_state after every substep (legged_robot.py:84-85), root_states, contact_forces and
+        rigid_body_states after the last one (go2.py:352-353, :272).  dof_state, root_states and contact_forces are read
+        densely and are copied -- except the dof_state of substeps 0..2, whose only reader is the next PD-torque kernel:
+        that kernel streams the pinned frame in place (`zero_copy_dof`); rigid_body_states [N*19,13] is read at 4 floats
+        per env (the feet heights), so the kernel reads it in place too (`zero_copy_rigid`) instead of copying 4 MB.
+    device -> host (pinned mirrors): the torques of EVERY substep (gym.set_dof_actuation_force_tensor, legged_robot.py:81-83),
+        and after the step the state the reference pushes back with set_dof_state_tensor_indexed /
+        set_actor_root_state_tensor_indexed (legged_robot.py:504-506, :530-532, :539): root_states, dof_state and the reset
+        flags that select the rows -- copied whole (a fixed-size, graph-capturable transfer; an upper bound of the rows the
+        reference sends), plus the step's rewards and dones (`read_back_results`).
+    `bytes_per_step` / `d2h_bytes_per_step` count what crosses the bus per env step.  Used by bench.py's end-to-end leg."""
+
+    def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, zero_copy_rigid=True, zero_copy_dof=True,
+                 read_back_results=True, **frame_kw):
         rng = np.random.default_rng(seed)
         origins = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
         self.frames = []
         for _ in range(ring):
             f = synth.make_frames(num_envs, origins, rng, decimation=decimation, **frame_kw)
             self.frames.append({k: torch.from_numpy(v).pin_memory() for k, v in f.items()})
-        self.cursor, self.h2d_bytes = -1, 0
+        self.cursor, self.h2d_bytes, self.d2h_bytes = -1, 0, 0
         self.zero_copy_rigid = bool(zero_copy_rigid)
         self.zero_copy_dof, self.decimation = bool(zero_copy_dof), int(decimation)
         f0 = self.frames[0]
         # zero-copy reads: 4 feet per env, one 32-byte sector each
         self.rigid_bytes = num_envs * 4 * 32 if self.zero_copy_rigid else 4 * f0["rigid"].numel()
         self.bytes_per_step = 4 * (f0["dof"].numel() + f0["root"].numel() + f0["contact"].numel()) + self.rigid_bytes
+        pin = lambda *shape, dt=torch.float32: torch.zeros(*shape, dtype=dt).pin_memory()
+        self.host_torques = pin(decimation, num_envs, NUM_DOF)       # what the host simulator is actuated with
+        self.host_root, self.host_dof = pin(num_envs, 13), pin(num_envs * NUM_DOF, 2)
+        self.host_reset = pin(num_envs, dt=torch.bool)
+        self.read_back_results = bool(read_back_results)
+        self.host_rew, self.host_done = pin(num_envs), pin(num_envs, dt=torch.bool)
+        self.d2h_bytes_per_step = 4 * (self.host_torques.numel() + self.host_root.numel() + self.host_dof.numel()) + num_envs \
+            + (5 * num_envs if self.read_back_results else 0)
 
     def begin_step(self, env):
         self.cursor = (self.cursor + 1) % len(self.frames)
 
     def simulate(self, env, substep):
-        """dof_state after substep k.  Between substeps its only reader is the next PD-torque kernel (legged_robot.py:81-85),
-        which streams it once: that kernel reads the pinned frame in place (`zero_copy_dof`); the frame of the LAST substep
-        is what post_physics_step and the env's `dof_state` attribute see, so it is copied."""
+        """torques of this substep -> host; dof_state after substep k -> device.  Between substeps the only reader of
+        dof_state is the next PD-torque kernel (legged_robot.py:81-85), which streams it once: that kernel reads the pinned
+        frame in place (`zero_copy_dof`); the frame of the LAST substep is what post_physics_step and the env's `dof_state`
+        attribute see, so it is copied."""
+        self.host_torques[substep].copy_(env.bufs["torques"], non_blocking=True)
+        self.d2h_bytes += 4 * env.bufs["torques"].numel()
         src = self.frames[self.cursor]["dof"][substep]
         last = substep == self.decimation - 1
         if self.zero_copy_dof and not last:
@@ -356,4 +377,13 @@ class HostPhysX:
         self.h2d_bytes += self.rigid_bytes
 
     def push_state(self, env):
-        pass
+        """the reset / pushed rows go back to the host simulator (whole tensors + the flags that select the rows), and the
+        step's rewards / dones to the host caller"""
+        b = env.bufs
+        self.host_root.copy_(b["root_states"], non_blocking=True)
+        self.host_dof.copy_(b["dof_state"], non_blocking=True)
+        self.host_reset.copy_(b["reset_buf"], non_blocking=True)
+        if self.read_back_results:
+            self.host_rew.copy_(b["rew_buf"], non_blocking=True)
+            self.host_done.copy_(b["reset_buf"], non_blocking=True)
+        self.d2h_bytes += self.d2h_bytes_per_step - 4 * self.host_torques.numel()

@@ -209,7 +209,11 @@ class PPO:
 
     @learning_rate.setter
     def learning_rate(self, value):
-        self._learning_rate = value
+        """the lr the kernels use lives in the optimiser's device state: assigning `alg.learning_rate` (as code written
+        against the reference does, ppo.py:244-246) moves it there; graph replays pick it up"""
+        self._learning_rate = float(value)
+        self.optimizer.param_groups[0]["lr"] = float(value)
+        self.actor_critic.main.set_lr(float(value))
 
     # ---- storage ------------------------------------------------------------------------------------
     def init_storage(self, num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
@@ -328,11 +332,33 @@ class PPO:
             self._join([self._pending_critic])
             self._pending_critic = None
         tmo = infos["time_outs"] if "time_outs" in infos else None
+        rewards, dones, tmo = self._as_step_scalars(rewards, dones, tmo)
         p = lambda x: C.c_void_p(x.data_ptr())
         _lib.check(self.lib.b200_store_step_scalars(p(rewards), p(dones), p(tmo) if tmo is not None else None, p(s.values[t]), self.gamma,
                                                     p(s.rewards[t]), p(s.dones[t]), s.num_envs, _lib.stream_ptr()))
         s.step += 1
         self.transition.clear()
+
+    def _as_step_scalars(self, rewards, dones, time_outs):
+        """the kernel reads fp32 rewards and 1-byte flags from raw addresses: convert what a duck-typed env hands over
+        (int64 dones, float time_outs, strided views) instead of misreading it"""
+        N = self.storage.num_envs
+
+        def flag(x, name):
+            if x is None:
+                return None
+            if x.dtype not in (torch.bool, torch.uint8):
+                x = x != 0
+            if not x.is_cuda or not x.is_contiguous():
+                x = x.to(self.device).contiguous()
+            if x.numel() != N:
+                raise ValueError(f"process_env_step: {name} has {x.numel()} elements, expected {N}")
+            return x
+        if rewards.dtype != torch.float32 or not rewards.is_cuda or not rewards.is_contiguous():
+            rewards = rewards.to(self.device, torch.float32).contiguous()
+        if rewards.numel() != N:
+            raise ValueError(f"process_env_step: rewards has {rewards.numel()} elements, expected {N}")
+        return rewards, flag(dones, "dones"), flag(time_outs, "time_outs")
 
     def compute_returns(self, last_critic_obs):
         """ppo.py:174-179."""
@@ -599,6 +625,10 @@ class PPO:
                 self._run_captured(("dagger", i), lambda i=i: self._dagger_minibatch(i * self.mb, self.mb))
         n = self.num_learning_epochs * self.num_mini_batches
         loss = float(self.loss_sums[5].item()) / (n * self.mb)
+        # ppo.py:274 clips actor_critic.parameters(): the adaptation encoder's .grad left by THIS update (post-clip, never
+        # zeroed by optimizer.zero_grad()) is part of the norm of every later PPO minibatch -- hand its squared norm over
+        ac = self.actor_critic
+        ac.main.state[7:8].copy_(ac.adapt.state[6:7])
         self.storage.clear()
         self.total_updates += 1
         return loss

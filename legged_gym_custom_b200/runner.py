@@ -22,6 +22,11 @@ class OnPolicyRunner:
         self.device, self.env = torch.device(device), env
         pc, ac_ = self.policy_cfg, self.alg_cfg
         seed = int(train_cfg.get("seed", 1))
+        # networks are initialised from the SHARED seed (and broadcast from rank 0 below); exploration noise and the minibatch
+        # permutation are keyed per rank, so env e of every rank does not draw the same action noise
+        from .dist import shard_seed
+        rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        rank_seed = shard_seed(seed, rank)
         actor_critic = ActorCritic(num_proprio=env.num_proprio, num_privileged_obs=env.num_privileged_obs,
                                    num_critic_obs=env.num_critic_obs, num_estimated_obs=env.num_estimated_obs,
                                    num_scan_obs=env.num_scan_obs, num_actions=env.num_actions,
@@ -41,7 +46,7 @@ class OnPolicyRunner:
                        value_loss_coef=ac_["value_loss_coef"], entropy_coef=ac_["entropy_coef"], learning_rate=ac_["learning_rate"],
                        estimator_learning_rate=ac_["estimator_learning_rate"], max_grad_norm=ac_["max_grad_norm"],
                        use_clipped_value_loss=ac_["use_clipped_value_loss"], schedule=ac_["schedule"], desired_kl=ac_["desired_kl"],
-                       resume=self.cfg["resume"], device=self.device, seed=seed, process_group=process_group)
+                       resume=self.cfg["resume"], device=self.device, seed=rank_seed, process_group=process_group)
         if process_group is not None:      # replicas start from rank 0's weights; afterwards identical reduced gradients keep them in sync
             from .dist import broadcast_parameters
             broadcast_parameters([actor_critic.main, actor_critic.adapt, estimator.group], process_group)
@@ -75,6 +80,28 @@ class OnPolicyRunner:
         self.alg.set_device_counter(enabled)
         self.alg.use_graphs = bool(enabled)
         self._rollout_graphs, self._rollout_calls = {}, {}
+
+    def capture_graphs(self):
+        """Capture EVERY graph a training run replays -- both rollout graphs (adaptation_mode False / True) and every
+        ("ppo", i) / ("dagger", i) minibatch graph -- now, instead of lazily on the second use of each (the adaptation-mode
+        rollout would otherwise be captured at iteration `dagger_update_freq`, in the middle of a run).  Parameters, optimiser
+        state and the update counter are restored afterwards, so the learner starts from where it was; the env has advanced by
+        four rollouts (set-up steps, like the reference's own warm-up reset)."""
+        if not getattr(self, "use_graphs", False):
+            raise RuntimeError("capture_graphs: call enable_graphs() first")
+        alg = self.alg
+        groups = [alg.actor_critic.main, alg.actor_critic.adapt, alg.estimator.group]
+        saved = [(g.params.clone(), g.exp_avg.clone(), g.exp_avg_sq.clone(), g.state.clone()) for g in groups]
+        updates, perm_state = alg.total_updates, alg._perm_gen.get_state()
+        for mode in (True, False):
+            for _ in range(2):                      # 1st call eager (allocations, kernel attributes), 2nd captures + replays
+                self.rollout(mode)
+                alg.update_dagger() if mode else alg.update()
+        for g, (p, m, v, s) in zip(groups, saved):
+            g.params.copy_(p); g.exp_avg.copy_(m); g.exp_avg_sq.copy_(v); g.state.copy_(s)
+        alg.total_updates = updates
+        alg._perm_gen.set_state(perm_state)
+        torch.cuda.synchronize()
 
     def rollout(self, use_adaptation_mode):
         if not getattr(self, "use_graphs", False):

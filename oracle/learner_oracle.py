@@ -45,11 +45,83 @@ import numpy as np
 from . import philox
 
 
+# ---- numerics of the PRODUCTION kernels (precise=False): TF32 operands, fp32 accumulation ---------------------------
+# The reference trains with torch.set_float32_matmul_precision('high') (scripts/train.py:39): TF32 matmuls.  The product's
+# tcgen05 kernels (kind::tf32) consume the fp32 bits directly -- the tensor core ignores the low 13 mantissa bits
+# (truncation); its mma.sync kernels (layers narrower than 8) convert with cvt.rna (round to nearest, ties away); the 1- /
+# 3-wide heads' dgrad and the adaptation encoder's forward are plain fp32.  `numerics("tf32")` makes every Linear of this
+# file reproduce exactly that (operands rounded per kernel, fp32 accumulation), so the production path has a comparator of
+# its own precision; the default "fp32" is the reference's CPU arithmetic, bit for bit.
+import contextlib
+
+_NUMERICS = ["fp32"]
+
+
+@contextlib.contextmanager
+def numerics(mode):
+    assert mode in ("fp32", "tf32")
+    _NUMERICS.append(mode)
+    try:
+        yield
+    finally:
+        _NUMERICS.pop()
+
+
+def tf32_trunc(x):
+    """fp32 -> TF32 by dropping the low 13 mantissa bits (what tcgen05.mma kind::tf32 sees of an fp32 operand)"""
+    return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def tf32_rna(x):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero (sign-magnitude: add half an ulp to the magnitude, truncate)"""
+    return ((x.contiguous().view(torch.int32) + 4096) & -8192).view(torch.float32)
+
+
+_ROUND = {"trunc": tf32_trunc, "rna": tf32_rna, "fp32": lambda x: x}
+
+
+def production_gemm_modes(M, N, K):
+    """operand rounding of (forward, dgrad, wgrad) of a Linear [K -> N] on M rows, as legged_gym_custom_b200.networks.Kernels
+    dispatches it with precise=False: tcgen05 when N >= 8 and K >= 8 (wgrad: and M >= 32), else mma.sync; the dgrad of a
+    head with N <= 4 is an fp32 outer product"""
+    tc = N >= 8 and K >= 8
+    return ("trunc" if tc else "rna", "trunc" if tc else ("fp32" if N <= 4 else "rna"), "trunc" if (tc and M >= 32) else "rna")
+
+
+class _LinearTF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, fwd, dgrad, wgrad):
+        ctx.save_for_backward(x, w)
+        ctx.modes = (dgrad, wgrad)
+        y = _ROUND[fwd](x) @ _ROUND[fwd](w).t()
+        return y + b if b is not None else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dgrad, wgrad = ctx.modes
+        dy = dy.contiguous()
+        dx = _ROUND[dgrad](dy) @ _ROUND[dgrad](w)
+        dw = _ROUND[wgrad](dy).t() @ _ROUND[wgrad](x)
+        return dx, dw, dy.sum(0), None, None, None
+
+
+def linear(x, w, b, forward_mode=None):
+    """F.linear in the current numerics; `forward_mode` overrides the forward rounding (the adaptation encoder's fused
+    forward kernel is fp32 while its backward runs on the TF32 GEMM kernels)"""
+    if _NUMERICS[-1] == "fp32":
+        return F.linear(x, w, b)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    f, d, g = production_gemm_modes(x2.shape[0], w.shape[0], w.shape[1])
+    return _LinearTF32.apply(x2, w, b, forward_mode or f, d, g).reshape(*lead, w.shape[0])
+
+
 def mlp(sd, prefix, x, n_layers, final_act=False):
     """nn.Sequential(Linear, ELU, ..., Linear) with keys `<prefix>.<2i>.{weight,bias}`
     (actor_critic.py:84-108, support_networks.py:24-35, :70-80, :108-116)."""
     for i in range(n_layers):
-        x = F.linear(x, sd[f"{prefix}.{2 * i}.weight"], sd[f"{prefix}.{2 * i}.bias"])
+        x = linear(x, sd[f"{prefix}.{2 * i}.weight"], sd[f"{prefix}.{2 * i}.bias"])
         if i < n_layers - 1 or final_act:
             x = F.elu(x)
     return x
@@ -63,10 +135,27 @@ def adaptation_encoder(sd, obs, num_proprio=52, hist=10):
     """AdaptationEncoder.forward on obs[:, :-num_proprio] (actor_critic.py:174-180, support_networks.py:128-175)."""
     h = obs[:, :-num_proprio].reshape(-1, hist, num_proprio)
     p = "adaptation_encoder_."
+    if _NUMERICS[-1] == "tf32":
+        return _adaptation_encoder_tf32(sd, h)
     x = F.elu(F.linear(h, sd[p + "fc_encoder.0.weight"], sd[p + "fc_encoder.0.bias"])).permute(0, 2, 1)
     x = F.elu(F.conv1d(x, sd[p + "conv_layers.0.weight"], sd[p + "conv_layers.0.bias"], stride=2))
     x = F.elu(F.conv1d(x, sd[p + "conv_layers.2.weight"], sd[p + "conv_layers.2.bias"], stride=1))
     return F.elu(F.linear(x.flatten(1), sd[p + "fc_final.0.weight"], sd[p + "fc_final.0.bias"]))
+
+
+def _adaptation_encoder_tf32(sd, h):
+    """the same network with each Conv1d written as the GEMM over its windows that the product runs (networks.py): the fused
+    forward kernel is fp32, the backward (DAgger) goes through the TF32 GEMM kernels window by window"""
+    p = "adaptation_encoder_."
+    B = h.shape[0]
+    x = F.elu(linear(h, sd[p + "fc_encoder.0.weight"], sd[p + "fc_encoder.0.bias"], forward_mode="fp32"))        # [B, 10, 30]
+    w1, w2 = sd[p + "conv_layers.0.weight"], sd[p + "conv_layers.2.weight"]                                      # [20,30,4], [10,20,2]
+    win = torch.stack([x[:, 2 * t:2 * t + 4, :] for t in range(4)], 1)                                           # [B, 4, k=4, 30]
+    x = F.elu(linear(win.reshape(B, 4, 120), w1.permute(0, 2, 1).reshape(20, 120), sd[p + "conv_layers.0.bias"], forward_mode="fp32"))
+    win = torch.stack([x[:, t:t + 2, :] for t in range(3)], 1)                                                   # [B, 3, k=2, 20]
+    x = F.elu(linear(win.reshape(B, 3, 40), w2.permute(0, 2, 1).reshape(10, 40), sd[p + "conv_layers.2.bias"], forward_mode="fp32"))
+    # Flatten of [B, 10 channels, 3 steps] is channel-major: column c * 3 + t
+    return F.elu(linear(x.permute(0, 2, 1).reshape(B, 30), sd[p + "fc_final.0.weight"], sd[p + "fc_final.0.bias"], forward_mode="fp32"))
 
 
 def privileged_encoder(sd, priv):
@@ -166,10 +255,16 @@ def dagger_loss(sd, b):
     return (lat_p.detach() - lat_a).norm(p=2, dim=1).mean()
 
 
-def clip_and_adam(params, grads, state, lr, max_norm, betas=(0.9, 0.999), eps=1e-8):
-    """nn.utils.clip_grad_norm_ + torch.optim.Adam.step on lists of tensors; `state` = dict(step, m, v)."""
-    total = torch.sqrt(sum((g.detach() ** 2).sum() for g in grads))
+def clip_and_adam(params, grads, state, lr, max_norm, betas=(0.9, 0.999), eps=1e-8, extra_sumsq=None):
+    """nn.utils.clip_grad_norm_ + torch.optim.Adam.step on lists of tensors; `state` = dict(step, m, v).
+    `extra_sumsq`: squared norm of gradients the same clip_grad_norm_ call covers but this optimiser does not own
+    (ppo.py:274: the adaptation encoder's stale .grad).  -> (post-clip squared norm of `grads`, rescaled extra_sumsq)"""
+    own = sum((g.detach() ** 2).sum() for g in grads)
+    total = torch.sqrt(own if extra_sumsq is None else own + extra_sumsq)
     coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    state["total_norm"] = float(total)
+    state["post_clip_sumsq"] = own * coef * coef
+    state["extra_sumsq"] = None if extra_sumsq is None else extra_sumsq * coef * coef
     state["step"] += 1
     t = state["step"]
     bc1, bc2 = 1 - betas[0] ** t, 1 - betas[1] ** t
@@ -198,6 +293,9 @@ class LearnerOracle:
         self.opt_main, self.opt_adapt = mk(self.main_keys, self.sd), mk(self.adapt_keys, self.sd)
         self.est_keys = list(self.sd_est)
         self.opt_est = mk(self.est_keys, self.sd_est)
+        # squared norm of the adaptation encoder's stale .grad (left post-clip by the last update_dagger minibatch; the
+        # main optimiser's zero_grad() never clears it, and clip_grad_norm_(actor_critic.parameters()) covers + rescales it)
+        self.stale_adapt_sumsq = None
 
     def minibatch(self, b, reg_coef=0.0):
         out = ppo_losses(self.sd, self.sd_est, b, reg_coef=reg_coef, **self.loss_kw)
@@ -210,7 +308,9 @@ class LearnerOracle:
             mu = out["mu"].detach()
             self.lr, kl = adaptive_lr(self.lr, mu, mu * 0. + self.sd["std"].detach(), b["mu"], b["sigma"], self.desired_kl)
             self.kl_log.append((kl, self.lr))
-        clip_and_adam([self.sd[k] for k in self.main_keys], g, self.opt_main, self.lr, self.max_grad_norm)
+        clip_and_adam([self.sd[k] for k in self.main_keys], g, self.opt_main, self.lr, self.max_grad_norm,
+                      extra_sumsq=self.stale_adapt_sumsq)
+        self.stale_adapt_sumsq = self.opt_main["extra_sumsq"]
         return {k: float(v.detach()) for k, v in out.items() if v.dim() == 0}
 
     def dagger_minibatch(self, b):
@@ -218,4 +318,5 @@ class LearnerOracle:
         g = torch.autograd.grad(loss, [self.sd[k] for k in self.adapt_keys])
         self.last_grads = dict(zip(self.adapt_keys, g))
         clip_and_adam([self.sd[k] for k in self.adapt_keys], g, self.opt_adapt, self.lr, self.max_grad_norm)
-        return float(loss)
+        self.stale_adapt_sumsq = self.opt_adapt["post_clip_sumsq"]
+        return float(loss.detach())

@@ -76,6 +76,49 @@ def main():
         data["dagger/returned"] = np.array([ppo.update_dagger()], dtype=np.float64)
         for k, v in ppo.actor_critic.state_dict().items():
             data["dagger/ac/" + k] = v.numpy().copy()
+        # update_dagger THEN update on the same PPO object (what OnPolicyRunner.learn does: iteration 0 is a DAgger
+        # iteration): the adaptation encoder's stale post-clip .grad enters every later clip_grad_norm_ (ppo.py:274).
+        # Its own storage ("seq_storage/"): on-policy old log-probs / values and small advantages, so that the main
+        # gradient norm is of the order of max_grad_norm -- with the 1000x larger norms of the storage above the stale
+        # term would vanish in the total norm and the fixture would not pin it.
+        ppo = build(resume=True)
+        st2 = lu.random_storage(T, N, seed=12)
+        with torch.no_grad():
+            f = lambda t: t.flatten(0, 1)
+            ppo.actor_critic.update_distribution(f(st2["obs"]), f(st2["priv"]), f(st2["true_est"]), f(st2["scan"]), adaptation_mode=False)
+            g2 = torch.Generator().manual_seed(19)
+            mu = ppo.actor_critic.action_mean
+            st2["actions"] = (mu + 0.8 * torch.randn(mu.shape, generator=g2)).view(T, N, -1)
+            st2["old_logp"] = ppo.actor_critic.get_actions_log_prob(f(st2["actions"])).view(T, N, 1).clone()
+            st2["mu"] = mu.view(T, N, -1).clone()
+            st2["sigma"] = ppo.actor_critic.action_std.reshape(T, N, -1).clone()
+            st2["values"] = ppo.actor_critic.evaluate(f(st2["critic_obs"])).view(T, N, 1).clone()
+            st2["returns"] = st2["values"] + 0.3 * torch.randn(T, N, 1, generator=g2)
+            st2["adv"] = 1.0 * torch.randn(T, N, 1, generator=g2)
+        for k, v in st2.items():
+            data["seq_storage/" + k] = v.numpy()
+        fill(ppo, st2)
+        data["seq/dagger_returned"] = np.array([ppo.update_dagger()], dtype=np.float64)
+        norms = []
+        real_clip = torch.nn.utils.clip_grad_norm_
+        def spy(params, max_norm, *a, **k):
+            out = real_clip(params, max_norm, *a, **k)
+            norms.append(float(out))
+            return out
+        torch.nn.utils.clip_grad_norm_ = spy
+        import rsl_rl.algorithms.ppo as ppo_mod
+        ppo_mod.nn.utils.clip_grad_norm_ = spy
+        try:
+            data["seq/update_returned"] = np.array(ppo.update(), dtype=np.float64)
+        finally:
+            torch.nn.utils.clip_grad_norm_ = real_clip
+            ppo_mod.nn.utils.clip_grad_norm_ = real_clip
+        data["seq/clip_total_norms"] = np.array(norms, dtype=np.float64)      # estimator, main, estimator, main, ...
+        print("seq: total norms seen by clip_grad_norm_ (estimator / main alternating):", [round(n, 4) for n in norms])
+        for k, v in ppo.actor_critic.state_dict().items():
+            data["seq/ac/" + k] = v.numpy().copy()
+        for k, v in ppo.estimator.state_dict().items():
+            data["seq/est/" + k] = v.numpy().copy()
         # act statistics + GAE
         ppo = build(resume=True)
         b = lu.minibatch(st, torch.arange(N))

@@ -34,7 +34,7 @@ def _make_group(seed):
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     pg = bdist.init_process_group("gloo")
-    assert bdist.env_rank_info() == (rank, world, rank) and bdist.shard_seed(1234, rank) == 1234 + rank
+    assert bdist.env_rank_info() == (rank, world, rank) and bdist.shard_seed(1234, rank) == 1234 + 7919 * rank
     g = _make_group(seed=100 + rank)                     # different start on purpose
     bdist.broadcast_parameters([g], pg)                  # -> rank 0's parameters everywhere
     for step in range(3):

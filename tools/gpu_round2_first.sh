@@ -8,18 +8,18 @@
 tag=${1:-r4a}
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_smoke_$tag.log \
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_smoke_$tag.log \
   python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitize_smoke_$tag.out 2>&1
 echo "memcheck smoke rc=$?"
-compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_env_$tag.log \
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_env_$tag.log \
   python -m pytest tests/test_env_gpu.py -q -x -k "golden" > gpurun_out/sanitize_env_$tag.out 2>&1
 echo "memcheck env golden rc=$?"
-compute-sanitizer --tool racecheck --error-exitcode 1 --log-file gpurun_out/sanitize_racecheck_env_$tag.log \
+timeout 400 compute-sanitizer --tool racecheck --error-exitcode 1 --log-file gpurun_out/sanitize_racecheck_env_$tag.log \
   python -m pytest tests/test_env_gpu.py -q -x -k "golden and go2_parkour-go2-layout-baked-in" > gpurun_out/sanitize_race_$tag.out 2>&1
 echo "racecheck env rc=$?"
-compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_learner_$tag.log \
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 1 --log-file gpurun_out/sanitize_memcheck_learner_$tag.log \
   python -m pytest tests/test_learner_gpu.py -q -x -k "update_matches or dagger_matches or adaptive" > gpurun_out/sanitize_learner_$tag.out 2>&1
 echo "memcheck learner rc=$?"
-python tools/trace_update.py gpurun_out/minibatch_timeline_$tag.json > gpurun_out/minibatch_timeline_$tag.txt 2> gpurun_out/minibatch_timeline_$tag.err
-python bench.py > gpurun_out/bench_${tag}_1gpu.json 2> gpurun_out/bench_${tag}.err
+timeout 300 python tools/trace_update.py gpurun_out/minibatch_timeline_$tag.json > gpurun_out/minibatch_timeline_$tag.txt 2> gpurun_out/minibatch_timeline_$tag.err
+timeout 600 python bench.py > gpurun_out/bench_${tag}_1gpu.json 2> gpurun_out/bench_${tag}.err
 tail -c 600 gpurun_out/bench_${tag}_1gpu.json
