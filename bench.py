@@ -379,7 +379,14 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_arm(args, budget_s=20.0, steps=1, warmup=0)["cpu_baseline"]
+        # the unmodified reference (baseline/_ref) for 2 full iterations after 1 warm-up; the oracle port only if it is absent
+        small = argparse.Namespace(**{**vars(args), "steps": 2, "warmup": 1})
+        r = None
+        try:
+            r = reference_arm(small)
+        except Exception as e:
+            sys.stderr.write(f"cpu_baseline: unmodified reference failed ({type(e).__name__}: {e}); timing the oracle port\n")
+        cpu = (r or cpu_arm(args, budget_s=20.0, steps=1, warmup=0))["cpu_baseline"]
 
     if rank == 0:
         line = {"metric": "env-steps/s (env step + GAE + PPO update), go2_parkour, 4096 envs/GPU", "value": value, "unit": "env-steps/s",
@@ -482,17 +489,70 @@ def cpu_arm(args, budget_s, steps, warmup):
                              "split": {k: round(v, 4) for k, v in parts.items()}}}
 
 
+def reference_arm(args):
+    """The UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.sh) on the host cores: its own Go2Robot and
+    OnPolicyRunner.learn from its task registry (--sim_device=cpu --rl_device=cpu), PhysX replaced by the stub that replays
+    the same synthetic frames.  Every timed step is one FULL learning iteration (24 env steps with policy inference, GAE,
+    20 minibatches; every 20th a DAgger iteration) -- nothing is sampled down or extrapolated; if K iterations would not fit
+    the time budget fewer are timed and `sample` says how many."""
+    import contextlib
+    import io
+    from oracle import ref_runner as rr
+    if not rr.reference_available():
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t_setup = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        runner, env = rr.build_training_run(args.task, args.num_envs, seed=1)
+    t_setup = time.perf_counter() - t_setup
+    budget_s, times = 170.0, []
+    t_begin = time.perf_counter()
+    n_warm = min(args.warmup, 1)
+    for i in range(n_warm + args.steps):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):            # the reference prints a 40-line table per iteration
+            runner.learn(1, init_at_random_ep_len=(i == 0))
+        dt = time.perf_counter() - t0
+        if i >= n_warm:
+            times.append(dt)
+        if times and time.perf_counter() - t_begin + dt > budget_s:
+            break
+    it_time = float(np.mean(times))
+    value = T_STEPS * args.num_envs / it_time
+    sample = (f"the reference's own OnPolicyRunner.learn (unmodified, baseline/_ref) at {args.num_envs} envs in ONE process on {cores} host "
+              f"threads: {len(times)} full iterations timed of {args.steps} requested (after {n_warm} warm-up; ~{budget_s:.0f} s budget), each = 24 env "
+              "steps with policy inference + GAE + 20 minibatches of 24576 (no extrapolation); PhysX = stub replaying synthetic frames; "
+              f"set-up {t_setup:.1f} s not timed")
+    return {"value": value, "ms_per_step": it_time * 1e3, "timed": len(times),
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "iteration_s": [round(t, 3) for t in times]}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = max(1, args.steps + args.warmup)
-    r = cpu_arm(args, budget_s=max(2.0, 150.0 / total), steps=args.steps, warmup=min(args.warmup, 1))
+    r = None
+    if not args.ref_port:
+        try:
+            r = reference_arm(args)
+        except Exception as e:                                        # e.g. baseline/_ref missing a module: say so, fall back
+            sys.stderr.write(f"reference arm: unmodified reference failed ({type(e).__name__}: {e}); timing the oracle port instead\n")
+    if r is None:
+        total = max(1, args.steps + args.warmup)
+        r = cpu_arm(args, budget_s=max(2.0, 150.0 / total), steps=args.steps, warmup=min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        r["cpu_baseline"]["sample"] += f"; launched with {world} ranks: the CPU arm is ONE {args.num_envs}-env process on rank 0 (the other ranks exit)"
     line = {"impl": "reference", "metric": "env-steps/s (env step + GAE + PPO update), go2_parkour, 4096 envs/GPU", "value": r["value"],
-            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": r.get("timed", args.steps), "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.task}: rollout of {T_STEPS} env steps + GAE + PPO update, {args.num_envs} envs, CPU "
-                                   "(the reference's --sim_device=cpu --rl_device=cpu torch path, restated in oracle/)"},
+            "config": {"workload": f"{args.task}: rollout of {T_STEPS} env steps (policy inference + 4 PD substeps + post-physics) "
+                                   f"+ GAE + PPO update (5 epochs x 4 minibatches of {T_STEPS * args.num_envs // 4}), {args.num_envs} envs/GPU, "
+                                   "PhysX replaced by a ring of replayed synthetic frames",
+                       "num_envs_per_gpu": args.num_envs,
+                       "arm": "the reference's --sim_device=cpu --rl_device=cpu path on the host cores"},
             "cpu_baseline": r["cpu_baseline"],
             "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -509,6 +569,7 @@ def main():
     ap.add_argument("--resume", type=int, default=None, help="ROA schedule of a resumed policy (default: on for the finetune task)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-port", action="store_true", help="--impl reference: time the oracle port instead of baseline/_ref")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--pdl", action="store_true", help="launch the tcgen05 GEMMs with programmatic dependent launch (A/B; default off)")
     ap.add_argument("--side-sm-cap", type=int, default=None, help="SMs the low-priority side chains of the update may occupy (A/B; 0 = all)")

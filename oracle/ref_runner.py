@@ -20,8 +20,9 @@ import tempfile
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("B200GYM_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_INSTALLED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")      # baseline/install_ref.sh (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get("B200GYM_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/legged_gym") else _INSTALLED)
 
 
 def reference_available():
@@ -43,8 +44,9 @@ def make_args(task, num_envs, seed=1, max_iterations=1):
                               sim_device='cpu', use_gpu=False, subscenes=0, use_gpu_pipeline=False, num_threads=0)
 
 
-def build_env(task="go2_parkour", num_envs=32, seed=1, cfg_patch=None):
-    """-> (env, env_cfg, gym). The env is the reference's own Go2Robot instance."""
+def build_env(task="go2_parkour", num_envs=32, seed=1, cfg_patch=None, keyed_rng=True):
+    """-> (env, env_cfg, gym). The env is the reference's own Go2Robot instance.  `keyed_rng=False` leaves the reference's
+    own torch RNG draws in place (timing runs: nothing is wrapped)."""
     _setup_path()
     import isaacgym  # noqa: F401  (the stub)
     from isaacgym import gymapi
@@ -54,8 +56,41 @@ def build_env(task="go2_parkour", num_envs=32, seed=1, cfg_patch=None):
     if cfg_patch is not None:
         cfg_patch(env_cfg)
     env, env_cfg = task_registry.make_env(task, args, env_cfg)
-    install_keyed_rng(env)
+    if keyed_rng:
+        install_keyed_rng(env)
     return env, env_cfg, gymapi._GYM
+
+
+def build_training_run(task="go2_parkour", num_envs=4096, seed=1, ring=4, resume=None):
+    """The reference's own training set-up on CPU (scripts/train.py:33-44 with --sim_device=cpu --rl_device=cpu): its
+    Go2Robot from task_registry.make_env and its OnPolicyRunner from task_registry.make_alg_runner, nothing wrapped or
+    edited; PhysX is the stub replaying a ring of `ring` synthetic frame sets (the same generator bench.py's GPU arm
+    replays).  -> (runner, env); drive it with runner.learn(n)."""
+    env, _, gym = build_env(task, num_envs, seed, keyed_rng=False)
+    from legged_gym.envs import task_registry
+    from legged_gym_custom_b200 import synth
+    args = make_args(task, num_envs, seed)
+    if resume is not None:
+        _, train_cfg = task_registry.get_cfgs(task)
+        train_cfg.runner.resume = False            # no checkpoint ships with the reference: random-init weights either way
+    runner, _ = task_registry.make_alg_runner(env=env, name=task, args=args, log_root=temp_log_dir())
+    rng = np.random.default_rng(seed)
+    origins = env.env_origins.detach().cpu().numpy()
+    frames = [{k: torch.from_numpy(v) for k, v in synth.make_frames(num_envs, origins, rng).items()} for _ in range(ring)]
+    cur = {"frame": -1, "sub": 0}
+
+    def on_sim(g):                                  # gym.simulate, once per decimation substep
+        if cur["sub"] == 0:
+            cur["frame"] = (cur["frame"] + 1) % ring
+        g.dof.copy_(frames[cur["frame"]]["dof"][cur["sub"]])
+        cur["sub"] = (cur["sub"] + 1) % frames[0]["dof"].shape[0]
+
+    def on_root(g):                                 # gym.refresh_actor_root_state_tensor, top of post_physics_step
+        f = frames[max(cur["frame"], 0)]
+        g.root.copy_(f["root"]); g.contact.copy_(f["contact"]); g.rigid.copy_(f["rigid"])
+
+    gym.on_simulate, gym.on_refresh_root = on_sim, on_root
+    return runner, env
 
 
 def install_keyed_rng(env):
