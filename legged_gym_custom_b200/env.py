@@ -134,6 +134,8 @@ class Go2Env:
         self._init_domain_randomisation(cfg, hs, origins, seed)
         self.physx = physx if physx is not None else SyntheticPhysX(N, self.bufs["env_origins"], self.device, seed=seed,
                                                                     decimation=p.decimation)
+        if hasattr(self.physx, "bind"):                 # a simulator-backed provider wraps its own state tensors (integration.py)
+            self.physx.bind(self)
         self.init_done = True
 
     # ---- env-creation-time randomisation (legged_robot.py:306-380, :696-701, :897-930): one kernel over the envs

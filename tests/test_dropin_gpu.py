@@ -1,0 +1,164 @@
+"""Drop-in proof: the reference's OWN, unmodified `OnPolicyRunner` (rsl_rl/runners/on_policy_runner.py,
+from baseline/_ref on the GPU box) drives `Go2Env` and the kernel-backed `PPO` / `ActorCritic` / `MlpEstimator`, and the
+Isaac Gym PhysX adapter of INTEGRATION.md is exercised against a stub gym whose tensors live on the GPU."""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_runner_module():
+    """the reference's runner module, imported from the installed copy (needs nothing of Isaac Gym)"""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/rsl_rl"):
+        if os.path.isdir(os.path.join(root, "rsl_rl", "runners")):
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            import rsl_rl.runners.on_policy_runner as m
+            return m
+    pytest.skip("the reference is not installed (baseline/install_ref.sh)")
+
+
+def _env(num_envs, seed=5):
+    from legged_gym_custom_b200 import configs
+    from legged_gym_custom_b200.env import Go2Env
+    env_cfg, train_cfg = configs.TASKS["go2_parkour"]
+
+    class Cfg(env_cfg):
+        class env(env_cfg.env):
+            pass
+    Cfg.env.num_envs = num_envs
+    return Go2Env(Cfg, sim_device=DEV, seed=seed), train_cfg
+
+
+def test_reference_runner_drives_go2env_and_kernel_ppo():
+    from legged_gym_custom_b200 import _lib
+    from legged_gym_custom_b200.integration import bind_reference_runner
+    from legged_gym_custom_b200.runner import OnPolicyRunner as OurRunner, class_to_dict
+    ref_mod = _reference_runner_module()
+    RefRunner = bind_reference_runner(ref_mod)
+    assert RefRunner.__module__.startswith("rsl_rl.runners") and "legged_gym_custom_b200" not in RefRunner.learn.__code__.co_filename
+    N = 256
+    calls = {}
+
+    def hook(name, raw, args):
+        calls[name] = calls.get(name, 0) + 1
+        return raw(*args)
+
+    # --- the reference's runner: iteration 0 (DAgger, adaptation-mode rollout) and iteration 1 (PPO update)
+    env, train_cfg = _env(N)
+    tc = class_to_dict(train_cfg)
+    tc["seed"] = 0
+    log_dir = tempfile.mkdtemp(prefix="b200_dropin_")
+    _lib.lib().hook = hook
+    try:
+        with contextlib.redirect_stdout(io.StringIO()) as out:
+            runner = RefRunner(env, tc, log_dir, device=DEV)
+            runner.learn(2, init_at_random_ep_len=False)
+    finally:
+        _lib.lib().hook = None
+    torch.cuda.synchronize()
+    assert type(runner).__module__ == ref_mod.__name__ and type(runner.alg).__module__ == "legged_gym_custom_b200.learner"
+    assert "Learning iteration 1/2" in out.getvalue() and "Estimator loss" in out.getvalue()       # the reference's own log()
+    assert calls.get("b200_post_physics_step", 0) + calls.get("b200_post_physics_step_dev", 0) == 2 * 24 + 1      # + env.reset()
+    assert calls["b200_clip_adam"] == 20 + 2 * 20 and calls["b200_compute_returns"] == 2
+    assert os.path.exists(os.path.join(log_dir, "model_0.pt")) and os.path.exists(os.path.join(log_dir, "model_2.pt"))
+    ck = torch.load(os.path.join(log_dir, "model_2.pt"), map_location="cpu")
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "iter", "infos"} and "actor.0.weight" in ck["model_state_dict"]
+
+    # --- our runner from the same seeds: same kernels, same numbers (fp32 atomics of the split-K wgrads reorder sums)
+    env2, _ = _env(N)
+    ours = OurRunner(env2, tc, log_dir=None, device=DEV)
+    for it in range(2):
+        ours.iteration(it)
+    torch.cuda.synchronize()
+    a, b = runner.alg.actor_critic.state_dict(), ours.alg.actor_critic.state_dict()
+    moved = 0.0
+    for k in a:
+        assert torch.allclose(a[k], b[k], rtol=0, atol=2.5e-4), (k, float((a[k] - b[k]).abs().max()))      # <= lr x steps
+        moved = max(moved, float((a[k] - ours.alg.actor_critic._random_state_dict(1.0, 0)[k].to(a[k].device)).abs().max()))
+    assert moved > 1e-4                                        # the weights did train
+    assert torch.equal(env.obs_buf, env2.obs_buf) or float((env.obs_buf - env2.obs_buf).abs().max()) < 10.0
+    assert int(env.common_step_counter) == int(env2.common_step_counter) == 49
+
+
+def test_isaacgym_physx_adapter_against_stub_gym():
+    """`IsaacGymPhysX` over a stub gym with GPU tensors: bind() makes the env read the simulator's own
+    tensors, simulate / refresh / push_state make the calls legged_robot.py:79-88 makes, and a step equals the same step
+    with the frames written directly."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    from isaacgym import gymapi, gymtorch
+    from legged_gym_custom_b200 import configs, synth
+    from legged_gym_custom_b200.env import ExternalPhysX, Go2Env
+    from legged_gym_custom_b200.integration import IsaacGymPhysX
+    N = 128
+
+    class CudaGym(gymapi.FakeGym):
+        calls = []
+
+        def _alloc(self):
+            if self.root is None:
+                super()._alloc()
+                self.root, self.dof, self.contact, self.rigid = (t.to(DEV) for t in (self.root, self.dof, self.contact, self.rigid))
+
+        def set_dof_actuation_force_tensor(self, sim, t):
+            self.calls.append("actuate")
+            self.last_torques = t.clone()
+
+        def set_dof_state_tensor_indexed(self, sim, t, ids, n):
+            self.calls.append(("push_dof", int(n)))
+
+        def set_actor_root_state_tensor_indexed(self, sim, t, ids, n):
+            self.calls.append(("push_root", int(n)))
+
+    env_cfg, _ = configs.TASKS["go2_parkour"]
+
+    class Cfg(env_cfg):
+        class env(env_cfg.env):
+            pass
+    Cfg.env.num_envs = N
+    gym = CudaGym()
+    gym.num_envs = N
+    env = Go2Env(Cfg, sim_device=DEV, seed=3, physx=IsaacGymPhysX(gym, gym, gymtorch))
+    assert env.bufs["root_states"].data_ptr() == gym.root.data_ptr() and env.bufs["dof_state"].data_ptr() == gym.dof.data_ptr()
+    rng = np.random.default_rng(4)
+    frames = synth.make_frames(N, env.env_origins.cpu().numpy(), rng, hole_prob=0.05)
+    k = {"i": 0}
+
+    def on_sim(g):
+        g.dof.copy_(torch.from_numpy(frames["dof"][k["i"] % 4]).to(DEV)); k["i"] += 1
+
+    def on_root(g):
+        g.root.copy_(torch.from_numpy(frames["root"]).to(DEV)); g.contact.copy_(torch.from_numpy(frames["contact"]).to(DEV))
+        g.rigid.copy_(torch.from_numpy(frames["rigid"]).to(DEV))
+    gym.on_simulate, gym.on_refresh_root = on_sim, on_root
+    actions = torch.randn(N, 12, generator=torch.Generator().manual_seed(0)).to(DEV)
+    env.reset()
+    gym.calls.clear(); k["i"] = 0
+    out = env.step(actions)
+    torch.cuda.synchronize()
+    n_reset = int(out[6].sum())
+    assert gym.calls[:4] == ["actuate"] * 4 and n_reset > 0 and gym.calls[4:] == [("push_dof", n_reset), ("push_root", n_reset)]
+    assert torch.equal(gym.last_torques, env.torques)
+
+    # the same two steps with the frames written straight into an env of the same seed
+    def write_dof(e, sub):
+        e.bufs["dof_state"].copy_(torch.from_numpy(frames["dof"][sub]).to(DEV))
+
+    def write_root(e):
+        for name, key in (("root_states", "root"), ("contact_forces", "contact"), ("rigid_body_states", "rigid")):
+            e.bufs[name].copy_(torch.from_numpy(frames[key]).to(DEV))
+    env2 = Go2Env(Cfg, sim_device=DEV, seed=3, physx=ExternalPhysX(on_simulate=write_dof, on_refresh=write_root))
+    env2.reset()
+    out2 = env2.step(actions)
+    torch.cuda.synchronize()
+    for a, b in zip(out[:7], out2[:7]):
+        assert torch.equal(a, b)
