@@ -282,6 +282,20 @@ def test_tcgen05_operands_are_truncated_tf32():
     assert e_t <= 2e-5 and e_r >= 10 * e_t, (e_t, e_r)
 
 
+def test_mma_sync_heads_round_to_nearest():
+    """the other half of numerics('tf32'): layers narrower than 8 run on mma.sync with cvt.rna operands"""
+    lib = _lib.lib()
+    for (M, N, K) in ((512, 1, 128), (512, 3, 128)):
+        g = torch.Generator().manual_seed(3)
+        X, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+        Xd, Wd, Y = X.to(DEV), W.to(DEV), torch.zeros(M, 4, device=DEV)
+        _lib.check(lib.b200_linear_forward(Xd.data_ptr(), K, Wd.data_ptr(), K, None, Y.data_ptr(), 4, M, N, K, 0, 0, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        e_r = scale_err(Y[:, :N], (lo.tf32_rna(X).double() @ lo.tf32_rna(W).double().t()).float())
+        e_t = scale_err(Y[:, :N], (lo.tf32_trunc(X).double() @ lo.tf32_trunc(W).double().t()).float())
+        assert e_r <= 2e-5 and e_t >= 10 * e_r, (e_r, e_t)
+
+
 @pytest.mark.parametrize("dagger_first", [False, True], ids=["update", "dagger-then-update"])
 def test_production_path_update_on_reference_golden_storage(dagger_first):
     """PPO.update (and update_dagger -> update on the same object, the runner's order) through the PRODUCTION tcgen05 TF32
@@ -443,10 +457,13 @@ def test_adaptive_schedule_matches_oracle(near, graphs):
 def test_production_minibatch_of_24576_samples_matches_tf32_oracle(dagger):
     """ONE REAL minibatch (M = 24 576 = 24 steps x 4096 envs / 4, the benchmark's shape) through the production tcgen05 path
     against the oracle in numerics('tf32'): losses <= 1e-4; every gradient tensor <= 1e-3 in relative Frobenius distance
-    and <= 5e-3 of its rms in the worst element.  (Truncation to TF32 is discontinuous: an operand that differs by one fp32
-    ulp between two implementations -- accumulation order, __expf -- truncates to a different TF32 value with probability
-    2^-13, a 2^-10 step, and four layers of forward + backward compound that to ~3e-4 rms with 8-sigma tails over the
-    321 k elements of the widest tensor; measured 2.6e-4 / 2.2e-3.  The fp32 oracle is 10-30x farther away.)"""
+    (rms of the error over rms of the gradient) and <= 1e-2 of its rms in the WORST element.  Every single kernel matches its
+    emulation to fp32-accumulation distance (test_tcgen05_operands_are_truncated_tf32, test_mma_sync_heads_round_to_nearest:
+    1e-6 .. 1e-5); the chain cannot, because truncation to TF32 is discontinuous: an operand that differs by one fp32 ulp
+    between two implementations (accumulation order, __expf) truncates to a different TF32 value with probability 2^-13 -- a
+    2^-10 step -- and four layers of forward + backward compound that to ~3e-4 rms with heavy tails over the 321 k elements
+    of the widest tensor (measured: 2.6e-4 / 2.2e-3 at M = 24 576, 4.5e-3 worst element at M = 384).  The fp32 oracle is
+    10-30x farther away (test_tf32_numerics_mode bounds that distance at 3e-2)."""
     test_gradients_match_oracle_full_size(dagger, False, T=24, N=1024)
 
 
@@ -491,10 +508,10 @@ def test_gradients_match_oracle_full_size(dagger, precise, T=4, N=96):
         group.params = saved
         for k in keys:
             ref = orc.last_grads[k]
-            if T * N <= 1024:
+            if precise:
                 assert scale_err(gsd[k], ref) <= 1e-3, (k, scale_err(gsd[k], ref))
-            else:
-                assert fro_err(gsd[k], ref) <= 1e-3 and scale_err(gsd[k], ref) <= 5e-3, (k, fro_err(gsd[k], ref), scale_err(gsd[k], ref))
+            else:       # production: see test_production_minibatch_of_24576_samples_matches_tf32_oracle for why two measures
+                assert fro_err(gsd[k], ref) <= 1e-3 and scale_err(gsd[k], ref) <= 1e-2, (k, fro_err(gsd[k], ref), scale_err(gsd[k], ref))
 
 
 @pytest.mark.parametrize("precise", [True, False], ids=["3xTF32-vs-fp32-oracle", "production-tcgen05-vs-tf32-oracle"])
@@ -515,8 +532,9 @@ def test_act_and_storage_vs_oracle(precise):
         a = ppo.act(*(st[k][t].to(DEV) for k in ("obs", "priv", "critic_obs", "true_est", "scan")), adaptation_mode=mode)
         with lo.numerics("fp32" if precise else "tf32"):
             ra, rv, rlp, rmu, rsig = lo.ppo_act(sd, sd_est, st["obs"][t], st["priv"][t], st["critic_obs"][t], st["scan"][t], ppo.seed, t, mode)
-        assert scale_err(a, ra) <= 1e-4 and scale_err(ppo.storage.values[t], rv) <= 1e-4
-        assert scale_err(ppo.storage.actions_log_prob[t, :, 0], rlp) <= 1e-4 and scale_err(ppo.storage.mu[t], rmu) <= 1e-4
+        tol = (lambda x, y: scale_err(x, y) <= 1e-4) if precise else (lambda x, y: fro_err(x, y) <= 5e-4 and scale_err(x, y) <= 5e-3)
+        assert tol(a, ra) and tol(ppo.storage.values[t], rv), (scale_err(a, ra), scale_err(ppo.storage.values[t], rv))
+        assert tol(ppo.storage.actions_log_prob[t, :, 0], rlp) and tol(ppo.storage.mu[t], rmu)
         assert torch.equal(ppo.storage.observations[t].cpu(), st["obs"][t]) and torch.equal(ppo.storage.privileged_observations[t].cpu(), st["priv"][t])
         assert torch.equal(ppo.storage.critic_observations[t].cpu(), st["critic_obs"][t]) and torch.equal(ppo.storage.scan_observations[t].cpu(), st["scan"][t])
         ppo.process_env_step(rews[t].to(DEV), dones[t].to(DEV), {"time_outs": tmo[t].to(DEV)})

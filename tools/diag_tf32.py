@@ -58,3 +58,14 @@ for group, owner, keys in [(ac.main, ac, orc.main_keys), (est.group, est, orc.es
         for name, lo_, hi_ in (("obs", 0, 572), ("latent", 572, 592), ("scan", 592, 624), ("est", 624, 627)):
             d = (a[:, lo_:hi_] - r[:, lo_:hi_]).abs()
             print("  actor.0 cols", name, "max", float(d.max()), "rms err", float(d.pow(2).mean().sqrt()), "rms ref", float(r[:, lo_:hi_].pow(2).mean().sqrt()))
+
+# --- the mma.sync heads (N < 8): which rounding do they apply?
+for (M, N, K) in [(512, 1, 128), (512, 3, 128), (512, 4, 256)]:
+    g = torch.Generator().manual_seed(3)
+    X, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    Xd, Wd, Y = X.to(DEV), W.to(DEV), torch.zeros(M, 4, device=DEV)
+    _lib.check(lib.b200_linear_forward(Xd.data_ptr(), K, Wd.data_ptr(), K, None, Y.data_ptr(), 4, M, N, K, 0, 0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for name, r in (("rna", lo.tf32_rna), ("trunc", lo.tf32_trunc), ("fp32", lambda x: x)):
+        ref = (r(X).double() @ r(W).double().t()).float()
+        print("head fwd", (M, N, K), name, tg.scale_err(Y[:, :N], ref), tg.fro_err(Y[:, :N], ref))
