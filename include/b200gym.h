@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 #define B200_NUM_DOF 12          /* go2 family: {FL,FR,RL,RR}_{hip,thigh,calf}_joint */
 #define B200_NUM_BODIES 19       /* base, Head_upper, Head_lower, 4 x {hip,thigh,calf,foot} */
 #define B200_NUM_FEET 4          /* FL, FR, RL, RR (reference order, go2.py:295-298) */
@@ -161,7 +161,12 @@ typedef struct B200EnvParams {
   /* largest fp32 s with sqrt_rn(s) <= 1.0 / 0.1: "norm > t" is evaluated as "squared norm > s" (bit-identical masks,
    * no square root) for the termination (legged_robot.py:146) and collision (:1088) contact tests */
   float contact_thr2_term, contact_thr2_collision;
-  int32_t _pad0;
+  /* != 0: the step's observation outputs exist ONCE, as the row of critic_obs_buf -- [obs | priv | est | scan] is exactly
+   * what obs_buf, privileged_obs_buf, estimated_obs_buf and scan_obs_buf hold (go2.py:538-563 concatenates the same clipped
+   * values), so those four pointers are ignored and the caller exposes them as column slices of the critic rows.  Saves a
+   * quarter of the step's writes and lets the rows land directly in a rollout-storage slot (bufs->critic_obs_buf may point
+   * there).  The go2 layout then runs post_physics_tile_kernel (rows assembled in shared memory, bulk-copied out). */
+  int32_t alias_outputs;
   uint64_t seed;                       /* Philox key (oracle/philox.py, csrc/philox.cuh) */
   /* command curriculum (go2.py:80-107, :222-223; cfg.commands.curriculum, off in every shipped go2 cfg).  The reference
    * keeps the lin_vel_x range as Python floats and moves it with np.clip in double: so do we (B200EnvBuffers.command_ranges) */

@@ -55,12 +55,35 @@ class BufferSet:
         self.t["reset_buf"].fill_(True)                      # base_task.py:83
         self.set_command_range(p.cc_range0[0], p.cc_range0[1])
         self.struct = EnvBuffers()
+        if p.alias_outputs:
+            self._alias_views(self.t["critic_obs_buf"])
         self.refresh_pointers()
+
+    ALIASED = ("obs_buf", "privileged_obs_buf", "estimated_obs_buf", "scan_obs_buf")
+
+    def _alias_views(self, rows):
+        """alias_outputs: obs / priv / est / scan ARE column slices of the critic rows (go2.py:538-563 concatenates them)"""
+        p = self.p
+        obs = p.num_proprio * (p.history_len + 1)
+        c0, c1 = obs + p.num_priv, obs + p.num_priv + p.num_est
+        self.t["obs_buf"], self.t["privileged_obs_buf"] = rows[:, :obs], rows[:, obs:c0]
+        self.t["estimated_obs_buf"], self.t["scan_obs_buf"] = rows[:, c0:c1], rows[:, c1:]
+
+    def bind_output_rows(self, rows):
+        """alias_outputs only: the step's observation rows land in `rows` [N, critic width] from now on -- e.g. a slot of the
+        rollout storage, so that the env writes the learner's transition in place"""
+        assert self.p.alias_outputs, "bind_output_rows needs alias_outputs"
+        old = self.t["critic_obs_buf"]
+        assert rows.shape == old.shape and rows.dtype == old.dtype and rows.device == old.device and rows.is_contiguous()
+        self.t["critic_obs_buf"] = rows
+        self._alias_views(rows)
+        for name in ("critic_obs_buf",) + self.ALIASED:
+            setattr(self.struct, name, C.c_void_p(self.t[name].data_ptr()))
 
     def refresh_pointers(self):
         for name in BUFFER_FIELDS:
             t = self.t[name]
-            if t is not None:
+            if t is not None and not (self.p.alias_outputs and name in self.ALIASED):
                 assert t.is_contiguous(), name
             setattr(self.struct, name, None if t is None else C.c_void_p(t.data_ptr()))
 

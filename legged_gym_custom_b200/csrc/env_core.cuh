@@ -50,11 +50,15 @@ struct float3_ {
 };
 
 // ---- per-warp scratch -------------------------------------------------------------------
-struct alignas(16) EnvScratch {
+// The three bulk rows are sized by the instantiation: EnvScratch (below) holds any supported layout; the kernel that
+// assembles its output rows in a shared-memory tile (env_kernels.cu, post_physics_tile_kernel) keeps `cur` / `tail` there
+// and instantiates the struct with token-sized arrays.
+template <int CUR_CAP, int TAIL_CAP, int SCAN_CAP>
+struct alignas(16) EnvScratchT {
   // the new proprioceptive row (unclipped); the history rows never pass through shared memory (env_hist_*)
-  float cur[B200_MAX_PROPRIO];
-  float tail[32 + 4 + B200_MAX_SCAN];   // priv | est | scan  = critic tail (16 B aligned pieces for 29+3+132)
-  float heights[B200_MAX_SCAN];
+  float cur[CUR_CAP];
+  float tail[TAIL_CAP];                 // priv | est | scan  = critic tail (16 B aligned pieces for 29+3+132)
+  float heights[SCAN_CAP];
   // staged inputs
   float root[16];
   float dof[24];                 // interleaved pos, vel
@@ -91,6 +95,7 @@ struct alignas(16) EnvScratch {
   int32_t reset, time_out, root_dirty, dof_dirty;
   int64_t ep_len_out, level_out;
 };
+typedef EnvScratchT<B200_MAX_PROPRIO, 32 + 4 + B200_MAX_SCAN, B200_MAX_SCAN> EnvScratch;
 
 // lanes of a warp address consecutive EnvScratch objects (lane = env slot): an odd number of 16-byte units per object
 // puts 8 consecutive slots on 8 different bank groups
@@ -343,13 +348,15 @@ enum { DV_ACTION_RATE = 0, DV_DELTA_TORQUES, DV_DOF_ACC, DV_DQ2, DV_POS_LIMITS, 
 
 B200_HD float gait_phase(const B200EnvParams& P, int64_t ep) { return fmodf((float)ep * P.dt, P.period) / P.period; }
 
-B200_HD void env_item_body(const B200EnvParams& P, EnvScratch& S, int b) {
+template <class SC>
+B200_HD void env_item_body(const B200EnvParams& P, SC& S, int b) {
   const float* c = S.contact + b * 3;
   const float n2 = B200_FMA(c[2], c[2], B200_FMA(c[1], c[1], c[0] * c[0]));
   S.body_hit[b] = (n2 > P.contact_thr2_term ? 1 : 0) | (n2 > P.contact_thr2_collision ? 2 : 0);
 }
 
-B200_HD void env_item_dof(const B200EnvParams& P, const EnvTables& T, EnvScratch& S, int d) {
+template <class SC>
+B200_HD void env_item_dof(const B200EnvParams& P, const EnvTables& T, SC& S, int d) {
   const float pos = S.dof[2 * d], vel = S.dof[2 * d + 1];
   const float dq = pos - T.default_dof_pos[d];
   S.dofv[DV_ACTION_RATE][d] = sq(S.last_act[d] - S.act[d]);
@@ -367,7 +374,8 @@ B200_HD void env_item_dof(const B200EnvParams& P, const EnvTables& T, EnvScratch
 }
 
 // gait phase of one leg (go2.py:279-290), order fl, fr, bl, br
-B200_HD void env_item_leg(const B200EnvParams& P, EnvScratch& S, int f) {
+template <class SC>
+B200_HD void env_item_leg(const B200EnvParams& P, SC& S, int f) {
   const float ph = gait_phase(P, S.ep_len + 1);
   const float off = f == 0 ? P.fl_offset : (f == 1 ? P.fr_offset : (f == 2 ? P.bl_offset : P.br_offset));
   const float keep = norm3_fma(S.cmd[0], S.cmd[1], S.cmd[2]) < 0.2f ? 0.0f : 1.0f;
@@ -383,7 +391,8 @@ B200_HD void env_item_leg(const B200EnvParams& P, EnvScratch& S, int f) {
 
 // a = 0 roll, 1 pitch, 2 yaw (quaternion_to_euler, go2.py:11-31), 3 heading.  The heading item goes on with the command
 // update of _post_physics_step_callback (go2.py:390-410), which is the only consumer of the heading.
-B200_HD void env_item_angle(const B200EnvParams& P, EnvScratch& S, int a, uint32_t e, uint32_t step) {
+template <class SC>
+B200_HD void env_item_angle(const B200EnvParams& P, SC& S, int a, uint32_t e, uint32_t step) {
   const float x = S.root[3], y = S.root[4], z = S.root[5], w = S.root[6];
   if (a == 1) {                                           // pitch (go2.py:23-25)
     const float pitch = asinf(clampf(2.0f * (w * y - z * x), -1.0f, 1.0f));
@@ -417,7 +426,8 @@ B200_HD void env_item_angle(const B200EnvParams& P, EnvScratch& S, int a, uint32
 }
 
 // base-frame velocities and gravity (go2.py:357-360)
-B200_HD void env_item_velocities(EnvScratch& S) {
+template <class SC>
+B200_HD void env_item_velocities(SC& S) {
   const float* q = S.root + 3;
   const float3_ blv = quat_rotate_inverse(q, S.root[7], S.root[8], S.root[9]);
   const float3_ bav = quat_rotate_inverse(q, S.root[10], S.root[11], S.root[12]);
@@ -429,7 +439,8 @@ B200_HD void env_item_velocities(EnvScratch& S) {
 
 // update_feet_states (go2.py:266-328; leg order of contacts / feet: fl, fr, bl, br) and _push_robots
 // (legged_robot.py:535-540).  Stage 0 has already copied root -> root_out, so the push lands on the copy.
-B200_HD void env_item_feet_push(const B200EnvParams& P, EnvScratch& S, uint32_t e, int64_t step64) {
+template <class SC>
+B200_HD void env_item_feet_push(const B200EnvParams& P, SC& S, uint32_t e, int64_t step64) {
   for (int f = 0; f < 4; ++f) {
     const int cur = S.contact[P.feet[f] * 3 + 2] > 1.0f;
     const int filt = cur | (S.last_contacts[f] != 0);
@@ -449,7 +460,8 @@ B200_HD void env_item_feet_push(const B200EnvParams& P, EnvScratch& S, uint32_t 
 
 // check_termination (go2.py:186-204) and the jump flags of the NEXT step (go2.py:487-494, from this step's heights):
 // known before any reward is, which lets the history rows move while the rewards are computed
-B200_HD void env_item_flags(const B200EnvParams& P, EnvScratch& S) {
+template <class SC>
+B200_HD void env_item_flags(const B200EnvParams& P, SC& S) {
   int reset = 0;
   for (int i = 0; i < P.n_termination; ++i) {
     const float* c = S.contact + P.termination[i] * 3;
@@ -475,7 +487,8 @@ B200_HD void env_item_flags(const B200EnvParams& P, EnvScratch& S) {
 // item ids of one env: bodies | dofs | legs | angles | velocities | feet + push | flags
 enum { ITEM_BODY0 = 0, ITEM_DOF0 = ITEM_BODY0 + B200_NUM_BODIES, ITEM_LEG0 = ITEM_DOF0 + B200_NUM_DOF, ITEM_ANGLE0 = ITEM_LEG0 + 4,
        ITEM_VEL = ITEM_ANGLE0 + 4, ITEM_FEET, ITEM_FLAGS, ITEM_COUNT };
-B200_HD void env_item(const B200EnvParams& P, const EnvTables& T, EnvScratch& S, int item, uint32_t e, int64_t step64) {
+template <class SC>
+B200_HD void env_item(const B200EnvParams& P, const EnvTables& T, SC& S, int item, uint32_t e, int64_t step64) {
   if (item < ITEM_DOF0) env_item_body(P, S, item - ITEM_BODY0);
   else if (item < ITEM_LEG0) env_item_dof(P, T, S, item - ITEM_DOF0);
   else if (item < ITEM_ANGLE0) env_item_leg(P, S, item - ITEM_LEG0);
@@ -490,8 +503,8 @@ B200_HD void env_item(const B200EnvParams& P, const EnvTables& T, EnvScratch& S,
 // the staged inputs and the item-stage results and writes term[k] = value * (scale * dt), 0 for a disabled term; the two
 // stateful terms also publish their state (feet_air_time -> fat_out, heading_alignment -> cmd_out[3]).
 #define B200_TERM_PARTS 8
-template <bool FIXED>
-B200_HD void env_terms_part(const B200EnvParams& P, EnvScratch& S, int part) {
+template <bool FIXED, class SC>
+B200_HD void env_terms_part(const B200EnvParams& P, SC& S, int part) {
   const int num_scan = FIXED ? B200_GO2_SCAN_NX * B200_GO2_SCAN_NY : P.num_scan;
   const float* sc = P.reward_scales;
   const float* cmd = S.cmd_out;                         // after resampling / heading update, before a reset
@@ -677,8 +690,8 @@ B200_HD void env_terms_part(const B200EnvParams& P, EnvScratch& S, int part) {
 // episode_sums[tracking_lin_vel] over the envs that reset on this step BEFORE any of them resamples its command.  After
 // stage 0 and the item stage of env e: evaluate the part that holds the term, publish (sum so far + this step's term,
 // reset flag); nothing else leaves the scratch.
-template <bool FIXED>
-B200_HD void env_cc_probe(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, int e) {
+template <bool FIXED, class SC>
+B200_HD void env_cc_probe(const B200EnvParams& P, const B200EnvBuffers& B, SC& S, int e) {
   env_terms_part<FIXED>(P, S, B200_REW_tracking_lin_vel % B200_TERM_PARTS);
   B.cc_value[e] = S.sums[B200_REW_tracking_lin_vel] + S.term[B200_REW_tracking_lin_vel];
   B.cc_reset[e] = (uint8_t)S.early_reset;
@@ -687,7 +700,8 @@ B200_HD void env_cc_probe(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
 // ---- compute_reward's sum (alphabetical, legged_robot.py:216-237), the termination reward, and reset_idx on this env if
 // flagged (go2.py:375-376).  One thread per env, after every part of env_terms_part.
 // (needs EnvScratch::reset_draws when the env resets: env_reset_draw, blocks 0..6)
-B200_HD void env_finalize(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S) {
+template <class SC>
+B200_HD void env_finalize(const B200EnvParams& P, const B200EnvBuffers& B, SC& S) {
   const float* sc = P.reward_scales;
   const int reset = S.early_reset, time_out = S.early_time_out;
   float rew = 0.0f;
@@ -740,7 +754,8 @@ B200_HD void env_finalize(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
 //   [0:3) base_ang_vel * 0.25 | [3:5) roll, pitch | [5:8) commands * (2, 2, 0.25) | [8:20) (dof_pos - default) * 1
 //   [20:32) dof_vel * 0.05 | [32:44) actions | [44:52) sin, cos of the fr, fl, bl, br phases (go2.py:476-481)
 // (x - 0) * 1 is x bit for bit, so one formula serves every segment.  Entry i of every table: env_tables_fill(P, T, i).
-#define B200_SOFF(field) ((int)(offsetof(EnvScratch, field) / sizeof(float)))
+#define B200_SOFF(field) ((int)(offsetof(SC, field) / sizeof(float)))
+template <class SC = EnvScratch>
 B200_HD void env_tables_fill(const B200EnvParams& P, EnvTables& T, int i) {
   if (i < B200_NUM_DOF) {
     T.default_dof_pos[i] = P.default_dof_pos[i];
@@ -768,7 +783,8 @@ B200_HD void env_tables_fill(const B200EnvParams& P, EnvTables& T, int i) {
   T.cur_scl[i] = scl;
   T.noise[i] = i < B200_PROPRIO ? P.noise_vec[i] : 0.0f;
 }
-B200_HD float cur_obs_element(const B200EnvParams& P, const EnvTables& T, const EnvScratch& S, float u, int i) {
+template <class SC>
+B200_HD float cur_obs_element(const B200EnvParams& P, const EnvTables& T, const SC& S, float u, int i) {
   float v = (reinterpret_cast<const float*>(&S)[T.cur_idx[i]] - T.cur_off[i]) * T.cur_scl[i];
   if (P.add_noise) v += (2.0f * u - 1.0f) * T.noise[i];
   return v;
@@ -815,9 +831,9 @@ B200_HD bool env_layout_is_go2(const B200EnvParams& P) {
          P.num_scan == B200_GO2_SCAN_NX * B200_GO2_SCAN_NY;
 }
 
-template <bool FIXED>
-B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvScratch& S, const float* pt_x, const float* pt_y,
-                          int e, int lane_lo, int lane_hi) {
+template <bool FIXED, class SC>
+B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, SC& S, const float* pt_x, const float* pt_y,
+                          int e, int lane_lo, int lane_hi, float* tail_dst = nullptr) {
   B200_ENV_DIMS;
 
   // ---- stage 0: stage the env's small rows into scratch (coalesced: consecutive lanes, consecutive floats).
@@ -879,7 +895,7 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, EnvSc
     S.sums[lane] = r_s0;
     if (lane + 32 < B200_NUM_REWARD_TERMS) S.sums[lane + 32] = r_s1;
     if (lane < 3) S.origin[lane] = S.origin_out[lane] = r_org;
-    if (lane < NPRIV) S.tail[lane] = clampf(r_priv, -P.clip_obs, P.clip_obs);
+    if (lane < NPRIV) (tail_dst ? tail_dst : S.tail)[lane] = clampf(r_priv, -P.clip_obs, P.clip_obs);
     if (lane == 0) {
       S.ep_len = r_ep;
       S.jump_flag = r_jf;
@@ -956,13 +972,13 @@ B200_HD void env_hist_store(const B200EnvParams& P, const B200EnvBuffers& B, int
   B200_ENV_DIMS;
   f4_ o = clamp4(v, P.clip_obs);
   if (reset) o.x = o.y = o.z = o.w = 0.0f;
-  reinterpret_cast<f4_*>(B.obs_buf + (int64_t)e * OBS)[i] = o;
+  if (!P.alias_outputs) reinterpret_cast<f4_*>(B.obs_buf + (int64_t)e * OBS)[i] = o;
   reinterpret_cast<f4_*>(B.critic_obs_buf + (int64_t)e * CRIT)[i] = o;
   if (!refill && i >= NP4) reinterpret_cast<f4_*>(B.obs_history_buf + (int64_t)e * HN)[i - NP4] = v;
 }
 
-template <bool FIXED>
-B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, const EnvTables& T, EnvScratch& S, int e, int64_t step64, int lane_lo,
+template <bool FIXED, class SC>
+B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, const EnvTables& T, SC& S, int e, int64_t step64, int lane_lo,
                            int lane_hi) {
   B200_ENV_DIMS;
 
@@ -1000,7 +1016,7 @@ B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, cons
     if (lane < NP4) {                                     // obs / critic end with clip(cur); history's newest slot is cur
       const f4_ v = cur4[lane];
       const f4_ o = clamp4(v, c);
-      obs4[HN4 + lane] = o;
+      if (!P.alias_outputs) obs4[HN4 + lane] = o;
       crit4[HN4 + lane] = o;
       if (!refill) hist4[HN4 - NP4 + lane] = v;
     }
@@ -1012,11 +1028,13 @@ B200_HD void env_warp_post(const B200EnvParams& P, const B200EnvBuffers& B, cons
     const f4_* s4 = reinterpret_cast<const f4_*>(S.tail + PE);
     const f4_* h4 = reinterpret_cast<const f4_*>(S.heights);
     for (int i = lane; i < NS4; i += 32) {
-      reinterpret_cast<f4_*>(B.scan_obs_buf + (int64_t)e * NS)[i] = s4[i];
+      if (!P.alias_outputs) reinterpret_cast<f4_*>(B.scan_obs_buf + (int64_t)e * NS)[i] = s4[i];
       reinterpret_cast<f4_*>(B.measured_heights + (int64_t)e * NS)[i] = h4[i];
     }
-    if (lane < NPRIV) B.privileged_obs_buf[(int64_t)e * NPRIV + lane] = S.tail[lane];
-    else B.estimated_obs_buf[(int64_t)e * NEST + (lane - NPRIV)] = S.tail[lane];
+    if (!P.alias_outputs) {
+      if (lane < NPRIV) B.privileged_obs_buf[(int64_t)e * NPRIV + lane] = S.tail[lane];
+      else B.estimated_obs_buf[(int64_t)e * NEST + (lane - NPRIV)] = S.tail[lane];
+    }
     // persistent state (go2.py:380-384 and the in-place updates of reset_idx)
     if (lane < 12) {
       B.last_actions[(int64_t)e * 12 + lane] = S.act[lane];

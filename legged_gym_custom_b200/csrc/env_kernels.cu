@@ -12,6 +12,7 @@
 // (constant bank, no extra copy per launch).
 #include <stdarg.h>
 
+#include "bulk_copy.cuh"
 #include "common.cuh"
 #include "env_core.cuh"
 
@@ -148,6 +149,211 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
 
   // ---- C
   if (live) env_warp_post<FIXED>(P, B, T, scratch[warp], e, step, lane, lane + 1);
+  B200_TRACE(5)
+#undef B200_TRACE
+}
+
+// ---- post_physics_tile_kernel: the go2 layout with `alias_outputs` (the observation outputs exist once, as rows of
+// critic_obs_buf = [history 520 | cur 52 | priv 29 | est 3 | scan 132]).  Same pieces, same phases and barriers as
+// post_physics_kernel; what changes is how the rows move:
+//   * every env's output row is assembled in a shared-memory TILE [8][736] and leaves with ONE bulk copy (cp.async.bulk,
+//     2944 B) issued by its warp -- no per-lane 16-byte stores, no second copy of the 572 observation values;
+//   * the history rows never touch registers: a bulk copy at kernel entry drops env's [10 x 52] history at the head of its
+//     tile row (it arrives under phases A / E), the shifted history goes back to global memory as a bulk copy of
+//     tile[52:520] as soon as the termination flags are known (B1), and the new proprioceptive row is written behind it
+//     (tile[520:572]) -- so tile[0:572] IS the unclipped observation; one in-place clip pass turns it into the output;
+//   * the reward sum / reset of the 8 envs (one warp, B2) overlaps the cur / tail rows of the envs that do not reset.
+typedef EnvScratchT<4, 4, B200_GO2_SCAN_NX * B200_GO2_SCAN_NY> TileScratch;      // cur / tail live in the tile
+static_assert((sizeof(TileScratch) / 16) % 2 == 1, "TileScratch stride would bank-conflict the per-env lanes");
+constexpr int kTileHist = B200_GO2_HISTORY * B200_PROPRIO;                       // 520
+constexpr int kTileObs = kTileHist + B200_PROPRIO;                               // 572
+constexpr int kTileRow = kTileObs + 32 + B200_GO2_SCAN_NX * B200_GO2_SCAN_NY;     // 736
+constexpr size_t kTileSmem = (size_t)kEnvsPerCta * (kTileRow * sizeof(float) + sizeof(TileScratch));
+static_assert((kTileRow * sizeof(float)) % 16 == 0 && (kTileHist * sizeof(float)) % 16 == 0, "rows move as 16-byte multiples");
+
+// cur (unclipped, go2.py:506-519) and the critic tail's est / scan parts of env `e` into its tile row; one warp
+__device__ __forceinline__ void tile_cur_tail(const B200EnvParams& P, const EnvTables& T, const TileScratch& S, float* row, int e,
+                                              int64_t step64, int lane) {
+  constexpr int NP = B200_PROPRIO, NS = B200_GO2_SCAN_NX * B200_GO2_SCAN_NY, NPRIV = 29;
+  const float c = P.clip_obs;
+  Philox4 r;
+  if (P.add_noise) r = keyed_block(P.seed, SITE_OBS_NOISE, (uint32_t)step64, (uint32_t)e, (uint32_t)(lane & 15));
+#pragma unroll
+  for (int i = lane; i < NP; i += 32) {
+    float u = 0.0f;
+    if (P.add_noise) {
+      const uint32_t w = (uint32_t)(i >> 4);
+      u = u32_to_uniform(w == 0 ? r.v[0] : (w == 1 ? r.v[1] : (w == 2 ? r.v[2] : r.v[3])));
+    }
+    row[kTileHist + i] = cur_obs_element(P, T, S, u, i);
+  }
+  if (lane >= NPRIV) row[kTileObs + lane] = clampf(S.blv[lane - NPRIV] * P.obs_lin_vel, -c, c);      // priv part: stage 0
+#pragma unroll
+  for (int j = lane; j < NS; j += 32) row[kTileObs + 32 + j] = clampf((S.root_out[2] - 0.3f) - S.heights[j], -1.0f, 1.0f);
+}
+
+__global__ void __launch_bounds__(kEnvsPerCta * 32, 4)
+post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
+                         const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace) {
+  extern __shared__ __align__(128) uint8_t tile_smem_raw[];
+  float* tile = reinterpret_cast<float*>(tile_smem_raw);
+  TileScratch* scratch = reinterpret_cast<TileScratch*>(tile_smem_raw + (size_t)kEnvsPerCta * kTileRow * sizeof(float));
+  __shared__ float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
+  __shared__ EnvTables T;
+  __shared__ __align__(8) uint64_t hist_bar;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int e0 = blockIdx.x * kEnvsPerCta;
+  const int e = e0 + warp;
+  const bool live = e < P.num_envs;
+  const int n_live = min(kEnvsPerCta, P.num_envs - e0);
+  constexpr int NP = B200_PROPRIO, NP4 = NP / 4, HN4 = kTileHist / 4, OBS4 = kTileObs / 4, NS4 = B200_GO2_SCAN_NX * B200_GO2_SCAN_NY / 4;
+  if (t == 0) {      // the history rows start towards shared memory before anything else happens
+    bulk::mbar_init(&hist_bar, 1);
+    bulk::mbar_expect_tx(&hist_bar, (uint32_t)(n_live * kTileHist * sizeof(float)));
+    for (int slot = 0; slot < n_live; ++slot)
+      bulk::load(tile + slot * kTileRow, B.obs_history_buf + (int64_t)(e0 + slot) * kTileHist, kTileHist * sizeof(float), &hist_bar);
+  }
+  if (t < P.num_scan) scan_point(P, t, &pt_x[t], &pt_y[t]);
+  if (t >= 64 && t < 64 + B200_MAX_PROPRIO) env_tables_fill<TileScratch>(P, T, t - 64);
+  __syncthreads();
+  if (step_dev) step = *step_dev;
+#define B200_TRACE(slot)                                                                          \
+  if (trace && t == 0) {                                                                          \
+    unsigned long long t_;                                                                        \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+    trace[(size_t)blockIdx.x * 8 + (slot)] = t_;                                                  \
+  }
+  B200_TRACE(0)
+  float* row = tile + warp * kTileRow;
+
+  // ---- A: small rows -> scratch (the privileged statics straight into the tile's tail), height scan
+  if (live) env_warp_pre<true>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1, row + kTileObs);
+  B200_TRACE(1)
+  __syncthreads();
+
+  // ---- E: items, packed type by type (as post_physics_kernel)
+  {
+    constexpr int kBodies = kEnvsPerCta * B200_NUM_BODIES, kDofs = kEnvsPerCta * B200_NUM_DOF;
+    if (t < kBodies) {
+      const int slot = t / B200_NUM_BODIES;
+      if (slot < n_live) env_item_body(P, scratch[slot], t - slot * B200_NUM_BODIES);
+    } else if (t < kBodies + kDofs) {
+      const int slot = (t - kBodies) / B200_NUM_DOF;
+      if (slot < n_live) env_item_dof(P, T, scratch[slot], (t - kBodies) - slot * B200_NUM_DOF);
+    } else if (t - (kBodies + kDofs) < n_live) {
+      env_item_flags(P, scratch[t - (kBodies + kDofs)]);
+    }
+    const int slot4 = lane >> 2;
+    if (warp == 0) {
+      if (slot4 < n_live) env_item_leg(P, scratch[slot4], lane & 3);
+    } else if (warp == 1) {
+      if (slot4 < n_live) env_item_angle(P, scratch[slot4], lane & 3, (uint32_t)(e0 + slot4), (uint32_t)step);
+    } else if (warp == 2) {
+      if (lane < n_live) env_item_velocities(scratch[lane]);
+    } else if (warp == 3) {
+      if (lane < n_live) env_item_feet_push(P, scratch[lane], (uint32_t)(e0 + lane), step);
+    }
+  }
+  B200_TRACE(2)
+  __syncthreads();
+
+  // ---- B1: reward terms (warp = part, lane = env slot); the Philox blocks of a reset; lane 16 of warp w sends env w's
+  //      shifted history home (in place in global memory: the source is the shared-memory copy, which has fully arrived)
+  if (lane < n_live) env_terms_part<true>(P, scratch[lane], warp);
+  if (live && scratch[warp].early_reset && lane >= 8 && lane < 8 + B200_RESET_BLOCKS)
+    env_reset_draw(P, scratch[warp].reset_draws, (uint32_t)e, (uint32_t)step, lane - 8);
+  const bool shift = live && !scratch[warp].early_refill;
+  if (lane == 16 && shift) {
+    bulk::mbar_wait(&hist_bar, 0);
+    bulk::store(B.obs_history_buf + (int64_t)e * kTileHist, row + NP, (kTileHist - NP) * sizeof(float));
+    bulk::commit();
+  }
+  B200_TRACE(3)
+  __syncthreads();
+
+  // ---- B2: warp 0 = reward sum, termination reward, reset of the 8 envs; the other warps meanwhile write the cur / tail
+  //      rows of their envs unless the env resets (finalize rewrites what those rows read only for a resetting env)
+  if (warp == 0) {
+    if (lane < n_live) env_finalize(P, B, scratch[lane]);
+  } else if (live && !scratch[warp].early_reset) {
+    tile_cur_tail(P, T, scratch[warp], row, e, step, lane);
+  }
+  B200_TRACE(4)
+  __syncthreads();
+
+  // ---- C: remaining cur / tail rows, clip in place, write-back
+  if (!live) return;
+  TileScratch& S = scratch[warp];
+  if (warp == 0 || S.early_reset) tile_cur_tail(P, T, S, row, e, step, lane);
+  bulk::mbar_wait(&hist_bar, 0);                        // every reader of the tile observes the arrival itself
+  if (lane == 16 && shift) bulk::wait_read();           // the shift store has read tile[52:520]: the row may now change
+  __syncwarp();
+  {
+    const float c = P.clip_obs;
+    const bool reset = S.reset != 0, refill = S.ep_len_out <= 1;      // refill == S.early_refill (go2.py:570-574)
+    f4_* row4 = reinterpret_cast<f4_*>(row);
+    f4_* hist4 = reinterpret_cast<f4_*>(B.obs_history_buf + (int64_t)e * kTileHist);
+#pragma unroll
+    for (int i = lane; i < OBS4; i += 32) {
+      const f4_ v = row4[i];
+      if (i >= HN4) {                                   // the new row: history's newest slot, or all of them after a reset
+        if (!refill) hist4[i - NP4] = v;
+        else
+#pragma unroll
+          for (int k = 0; k < B200_GO2_HISTORY; ++k) hist4[k * NP4 + (i - HN4)] = v;
+      }
+      f4_ o = clamp4(v, c);
+      if (reset && i < HN4) o.x = o.y = o.z = o.w = 0.0f;      // obs_history_buf[env_ids] = 0 before the observation (go2.py:238)
+      row4[i] = o;
+    }
+    bulk::fence_smem_writes();
+    __syncwarp();
+    if (lane == 0) {
+      bulk::store(B.critic_obs_buf + (int64_t)e * kTileRow, row, kTileRow * sizeof(float));
+      bulk::commit();
+    }
+    const f4_* h4 = reinterpret_cast<const f4_*>(S.heights);
+    for (int i = lane; i < NS4; i += 32) reinterpret_cast<f4_*>(B.measured_heights + (int64_t)e * (NS4 * 4))[i] = h4[i];
+    // persistent state (go2.py:380-384 and the in-place updates of reset_idx) -- as env_warp_post
+    if (lane < 12) {
+      B.last_actions[(int64_t)e * 12 + lane] = S.act[lane];
+      B.last_dof_vel[(int64_t)e * 12 + lane] = S.dof_out[2 * lane + 1];
+      B.last_torques[(int64_t)e * 12 + lane] = S.tq[lane];
+    }
+    if (lane < 6) B.last_root_vel[(int64_t)e * 6 + lane] = S.root_out[7 + lane];
+    if (lane < 3) {
+      B.last_base_lin_vel[(int64_t)e * 3 + lane] = S.blv[lane];
+      B.base_lin_vel[(int64_t)e * 3 + lane] = S.blv[lane];
+      B.base_ang_vel[(int64_t)e * 3 + lane] = S.bav[lane];
+      B.projected_gravity[(int64_t)e * 3 + lane] = S.pg[lane];
+      B.rpy[(int64_t)e * 3 + lane] = S.rpy[lane];
+      B.env_origins[(int64_t)e * 3 + lane] = S.origin_out[lane];
+    }
+    if (lane < 5) B.phases[(int64_t)e * 5 + lane] = S.phases[lane];
+    if (lane < 4) {
+      B.commands[(int64_t)e * 4 + lane] = S.cmd_out[lane];
+      B.last_contact_heights[(int64_t)e * 4 + lane] = S.lch_out[lane];
+      B.feet_air_time[(int64_t)e * 4 + lane] = S.fat_out[lane];
+      B.last_contacts[(int64_t)e * 4 + lane] = (uint8_t)S.contact_cur[lane];
+      B.foot_contacts[(int64_t)e * 4 + lane] = (uint8_t)S.contact_filt[lane];
+    }
+    if (S.root_dirty && lane < 13) B.root_states[(int64_t)e * 13 + lane] = S.root_out[lane];
+    if (S.dof_dirty && lane < 24) B.dof_state[(int64_t)e * 24 + lane] = S.dof_out[lane];
+    for (int k = lane; k < B200_NUM_REWARD_TERMS; k += 32) {
+      const float total = S.sums[k] + S.term[k];
+      B.episode_sums[(int64_t)e * B200_NUM_REWARD_TERMS + k] = S.reset ? 0.0f : total;
+      if (S.reset) B.reset_episode_sums[(int64_t)e * B200_NUM_REWARD_TERMS + k] = total;
+    }
+    if (lane == 0) {
+      B.episode_length_buf[e] = S.ep_len_out;
+      B.terrain_levels[e] = S.level_out;
+      B.jump_flags[e] = S.jump_flag_out;
+      B.rew_buf[e] = S.rew;
+      B.reset_buf[e] = (uint8_t)S.reset;
+      B.time_out_buf[e] = (uint8_t)S.time_out;
+      bulk::wait_read();                                // the row store has read shared memory: the CTA may retire
+    }
+  }
   B200_TRACE(5)
 #undef B200_TRACE
 }
@@ -292,6 +498,7 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
                  "b200_env_create: height field extent must stay below 2^23 m");
   B200_CHECK_ARG(p->resample_interval > 0 && p->push_interval > 0, "b200_env_create: intervals must be > 0");
   B200_CHECK_ARG(!p->command_curriculum || p->max_episode_length >= 2, "b200_env_create: command curriculum needs max_episode_length >= 2");
+  B200_CHECK_ARG(p->alias_outputs == 0 || p->alias_outputs == 1, "b200_env_create: alias_outputs must be 0 or 1");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess) {
@@ -335,6 +542,12 @@ int b200_env_set_prefetch(B200Env* env, int on) {
 static int post_physics_attr() {
   static bool done = false;
   if (!done) {
+    cudaError_t et = cudaFuncSetAttribute(post_physics_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    if (et == cudaSuccess) et = cudaFuncSetAttribute(post_physics_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (et != cudaSuccess) {
+      b200_set_error("post_physics_tile_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(et));
+      return (int)et;
+    }
     for (int fixed = 0; fixed < 2; ++fixed) {
       cudaError_t e = cudaFuncSetAttribute(fixed ? post_physics_kernel<true> : post_physics_kernel<false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEnvsPerCta * sizeof(EnvScratch)));
@@ -353,7 +566,9 @@ static void launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, 
                                 int dry = 0) {
   const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
   const size_t smem = kEnvsPerCta * sizeof(EnvScratch);
-  if (env_layout_is_go2(env->p) && !env->force_generic_layout)
+  if (env->p.alias_outputs && env_layout_is_go2(env->p) && !env->force_generic_layout && !dry && !bufs->height_index)
+    post_physics_tile_kernel<<<ctas, kEnvsPerCta * 32, kTileSmem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace);
+  else if (env_layout_is_go2(env->p) && !env->force_generic_layout)
     post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, dry ? nullptr : env->phase_trace, env->prefetch_history, dry);
   else
     post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, dry ? nullptr : env->phase_trace,

@@ -86,7 +86,8 @@ def _buffer_property(name):
 
 class Go2Env:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, physx=None,
-                 seed=None, index_div_mode=0, height_samples=None, terrain_origins=None, record_height_index=False):
+                 seed=None, index_div_mode=0, height_samples=None, terrain_origins=None, record_height_index=False,
+                 alias_outputs=True):
         if not torch.cuda.is_available():
             raise RuntimeError("Go2Env needs a CUDA device: the hot path has no CPU fallback")
         self.lib = _lib.lib()
@@ -105,8 +106,11 @@ class Go2Env:
                                      "beyond the parkour layouts is out of scope, SURVEY.md §8(f1))")
                 height_samples, terrain_origins = terrain_mod.make_parkour_terrain(cfg.terrain)
             hs, origins = np.asarray(height_samples, dtype=np.int16), np.asarray(terrain_origins, dtype=np.float32)
+        # alias_outputs (default): obs / privileged / estimated / scan observations are column slices of the critic rows
+        # (identical values, go2.py:538-563) -- strided views instead of four more buffers; `bind_output_rows` lets a
+        # runner point the rows at its rollout-storage slot.  Pass False for separate contiguous buffers.
         self.params = p = env_params_from_cfg(cfg, num_envs=N, seed=seed, index_div_mode=index_div_mode,
-                                              hs_shape=None if hs is None else hs.shape)
+                                              hs_shape=None if hs is None else hs.shape, alias_outputs=alias_outputs)
         self.bufs = BufferSet(p, self.device, record_height_index=record_height_index)
         self._handle = C.c_void_p()
         _lib.check(self.lib.b200_env_create(C.byref(p), self.device.index or 0, C.byref(self._handle)))
@@ -178,6 +182,14 @@ class Go2Env:
     def set_device_counter(self, enabled=True):
         self.step_counter_dev.fill_(self.common_step_counter)
         self.use_device_counter = bool(enabled)
+
+    @property
+    def supports_output_binding(self):
+        return bool(self.params.alias_outputs)
+
+    def bind_output_rows(self, rows):
+        """the next step() writes its observation rows [N, num_critic_obs] into `rows` (alias_outputs only)"""
+        self.bufs.bind_output_rows(rows)
 
     def step5(self, actions):
         """upstream rsl_rl VecEnv 5-tuple (rsl_rl/env/vec_env.py:28): obs, privileged_obs, rew, done, info."""

@@ -38,7 +38,7 @@ class RolloutStorage:
             self.actions_log_prob = self.action_mean = self.action_sigma = None
 
     def __init__(self, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, critic_obs_shape,
-                 estimated_obs_shape, scan_obs_shape, actions_shape, device="cuda:0"):
+                 estimated_obs_shape, scan_obs_shape, actions_shape, device="cuda:0", alias_critic_rows=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("RolloutStorage lives on the GPU: the hot path has no CPU fallback")
@@ -50,11 +50,30 @@ class RolloutStorage:
         self.d_obs, self.d_priv, self.d_crit = obs_shape[0], privileged_obs_shape[0], critic_obs_shape[0]
         self.d_est, self.d_scan, self.d_act = estimated_obs_shape[0], scan_obs_shape[0], actions_shape[0]
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=self.device)
-        self.observations = z(T, N, self.d_obs)
-        self._priv = z(T, N, ceil4(self.d_priv))
-        self.critic_observations = z(T, N, self.d_crit)
-        self._est = z(T, N, ceil4(self.d_est))
-        self.scan_observations = z(T, N, self.d_scan)
+        # alias_critic_rows: a critic row IS [obs | priv | est | scan] (go2.py:538-563), so the four observation tensors are
+        # column slices of `critic_observations` instead of four more tensors -- and an env that writes its rows straight
+        # into slot t + 1 (Go2Env.bind_output_rows) leaves nothing to copy.  One extra slot holds the observation AFTER the
+        # last transition (the bootstrap value's input and the next rollout's first row).
+        self.alias_critic_rows = bool(alias_critic_rows)
+        if self.alias_critic_rows:
+            if self.d_crit != self.d_obs + self.d_priv + self.d_est + self.d_scan:
+                raise ValueError("alias_critic_rows: critic width must be obs + priv + est + scan")
+            self.rows = z(T + 1, N, self.d_crit)
+            c0, c1, c2 = self.d_obs, self.d_obs + self.d_priv, self.d_obs + self.d_priv + self.d_est
+            self.critic_observations = self.rows[:T]
+            self.observations, self._priv = self.rows[:T, :, :c0], self.rows[:T, :, c0:c1]
+            self._est, self.scan_observations = self.rows[:T, :, c1:c2], self.rows[:T, :, c2:]
+        else:
+            self.rows = None
+            self.observations = z(T, N, self.d_obs)
+            self._priv = z(T, N, ceil4(self.d_priv))           # 29 / 3 wide tensors are kept 32 / 4 wide (16-byte rows)
+            self.critic_observations = z(T, N, self.d_crit)
+            self._est = z(T, N, ceil4(self.d_est))
+            self.scan_observations = z(T, N, self.d_scan)
+        # row strides (floats) and copy widths of the five observation tensors
+        self.ld_obs, self.ld_priv, self.ld_crit = self.observations.stride(1), self._priv.stride(1), self.critic_observations.stride(1)
+        self.ld_est, self.ld_scan = self._est.stride(1), self.scan_observations.stride(1)
+        self.w_priv, self.w_est = self._priv.shape[2], self._est.shape[2]
         self.rewards, self.values, self.returns, self.advantages, self.actions_log_prob = (z(T, N, 1) for _ in range(5))
         self.actions, self.mu, self.sigma = z(T, N, self.d_act), z(T, N, self.d_act), z(T, N, self.d_act)
         self.dones = z(T, N, 1, dt=torch.uint8)
@@ -75,9 +94,9 @@ class RolloutStorage:
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         t = self.step
+        self.critic_observations[t].copy_(transition.critic_observations)
         self.observations[t].copy_(transition.observations)
         self._priv[t, :, :self.d_priv].copy_(transition.privileged_observations)
-        self.critic_observations[t].copy_(transition.critic_observations)
         self._est[t, :, :self.d_est].copy_(transition.true_estimated_observations)
         self.scan_observations[t].copy_(transition.scan_observations)
         self.actions[t].copy_(transition.actions)
@@ -217,9 +236,9 @@ class PPO:
 
     # ---- storage ------------------------------------------------------------------------------------
     def init_storage(self, num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
-                     estimated_obs_shape, scan_obs_shape, action_shape):
+                     estimated_obs_shape, scan_obs_shape, action_shape, alias_critic_rows=False):
         self.storage = s = RolloutStorage(num_envs, num_transitions_per_env, total_obs_shape, privileged_obs_shape, critic_obs_shape,
-                                          estimated_obs_shape, scan_obs_shape, action_shape, self.device)
+                                          estimated_obs_shape, scan_obs_shape, action_shape, self.device, alias_critic_rows)
         ac = self.actor_critic
         T, N = num_transitions_per_env, num_envs
         self.batch = T * N
@@ -264,8 +283,11 @@ class PPO:
         t, N, ws = s.step, s.num_envs, self.roll_ws
         ld = ac.ld_actor_in
         x = ws.get("actor_in", N, ld)
-        obs, privileged_obs, critic_obs = obs.contiguous(), privileged_obs.contiguous(), critic_obs.contiguous()
-        true_estimated_obs, scan_obs = true_estimated_obs.contiguous(), scan_obs.contiguous()
+        obs, privileged_obs, critic_obs = _rows16(obs), _rows16(privileged_obs, need16=False), _rows16(critic_obs)
+        true_estimated_obs, scan_obs = _rows16(true_estimated_obs, need16=False), _rows16(scan_obs)
+        # `in_place`: the env wrote this step's rows straight into storage slot t (Go2Env.bind_output_rows on an aliased
+        # storage): obs / priv / est / scan are column slices of that row and there is nothing to copy
+        in_place = s.alias_critic_rows and critic_obs.data_ptr() == s.critic_observations[t].data_ptr()
         # estimated obs -> actor input (the rollout acts on the ESTIMATE, ppo.py:134-137); the estimator, the latent
         # encoder, the scan encoder and the critic are independent until the actor's first layer.  Estimator -> actor is the
         # critical path (high-priority stream); the critic's value is not needed before process_env_step, so with
@@ -277,35 +299,41 @@ class PPO:
         # obs buffer in place, [obs -> actor input, priv -> storage] precede the latent encoder, the rest precedes the critic.
         s_hi, s_scan, s_lat, s_crit = self._fork(4)
         with self._on(s_hi):
-            est.fwd(ws, _p(obs), s.d_obs, _p(x, ac.col_est), ld, N)
+            est.fwd(ws, _p(obs), obs.stride(0), _p(x, ac.col_est), ld, N)
         with self._on(s_lat):
-            self._copy_segments([
-                (_p(obs), s.d_obs, _p(x), ld, s.d_obs),
-                (_p(privileged_obs), s.d_priv, _p(s._priv[t]), s._priv.shape[2], s.d_priv),
-            ], N)
+            segs = [(_p(obs), obs.stride(0), _p(x), ld, s.d_obs)]
+            if s.alias_critic_rows and not in_place:      # the row = critic_obs (assumed [obs | priv | est | scan], as the env builds it)
+                segs.append((_p(critic_obs), critic_obs.stride(0), _p(s.critic_observations[t]), s.ld_crit, s.d_crit))
+            elif not s.alias_critic_rows:
+                segs.append((_p(privileged_obs), privileged_obs.stride(0), _p(s._priv[t]), s.ld_priv, s.d_priv))
+            self._copy_segments(segs, N)
             if adaptation_mode:
                 ac.fwd_adapt(ws, _p(x), ld, _p(x, ac.col_latent), ld, N)
             else:
-                ac.fwd_priv(ws, _p(s._priv[t]), s._priv.shape[2], _p(x, ac.col_latent), ld, N)
+                ac.fwd_priv(ws, _p(s._priv[t]), s.ld_priv, _p(x, ac.col_latent), ld, N)
         with self._on(s_scan):
-            ac.fwd_scan(ws, _p(scan_obs), s.d_scan, _p(x, ac.col_scan), ld, N)
+            ac.fwd_scan(ws, _p(scan_obs), scan_obs.stride(0), _p(x, ac.col_scan), ld, N)
         mu = ws.get("mu", N, s.d_act)
         with self._on(s_hi):
             self._join([s_lat, s_scan])
             self._fork_onto([s_crit])                     # the critic's big first layer must not take the SMs before this point
             ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
         with self._on(s_crit):
-            self._copy_segments([
-                (_p(obs), s.d_obs, _p(s.observations[t]), s.d_obs, s.d_obs),
-                (_p(critic_obs), s.d_crit, _p(s.critic_observations[t]), s.d_crit, s.d_crit),
-                (_p(true_estimated_obs), s.d_est, _p(s._est[t]), s._est.shape[2], s.d_est),
-                (_p(scan_obs), s.d_scan, _p(s.scan_observations[t]), s.d_scan, s.d_scan),
-            ], N)
+            if s.alias_critic_rows:
+                if not in_place and s_lat is not None:    # the row copy above rides on the latent stream
+                    self._join_onto(s_crit, [s_lat])
+            else:
+                self._copy_segments([
+                    (_p(obs), obs.stride(0), _p(s.observations[t]), s.ld_obs, s.d_obs),
+                    (_p(critic_obs), critic_obs.stride(0), _p(s.critic_observations[t]), s.ld_crit, s.d_crit),
+                    (_p(true_estimated_obs), true_estimated_obs.stride(0), _p(s._est[t]), s.ld_est, s.d_est),
+                    (_p(scan_obs), scan_obs.stride(0), _p(s.scan_observations[t]), s.ld_scan, s.d_scan),
+                ], N)
             copied = None
-            if s_crit is not None:                        # the env's buffers may be overwritten (env.step) once THIS has run,
+            if s_crit is not None and not in_place:       # the env's buffers may be overwritten (env.step) once THIS has run,
                 copied = torch.cuda.Event()               # even if the critic chain itself is still in flight
                 copied.record()
-            ac.fwd_critic(ws, _p(s.critic_observations[t]), s.d_crit, _p(s.values[t]), 1, N)
+            ac.fwd_critic(ws, _p(s.critic_observations[t]), s.ld_crit, _p(s.values[t]), 1, N)
         self._join([s_hi])
         if copied is not None:
             torch.cuda.current_stream().wait_event(copied)
@@ -363,8 +391,8 @@ class PPO:
     def compute_returns(self, last_critic_obs):
         """ppo.py:174-179."""
         s, ac = self.storage, self.actor_critic
-        x = last_critic_obs.contiguous()
-        ac.fwd_critic(self.roll_ws, _p(x), s.d_crit, _p(self.last_values), 1, s.num_envs)
+        x = _rows16(last_critic_obs)
+        ac.fwd_critic(self.roll_ws, _p(x), x.stride(0), _p(self.last_values), 1, s.num_envs)
         s.compute_returns(self.last_values, self.gamma, self.lam)
 
     # ---- update ---------------------------------------------------------------------------------------
@@ -373,12 +401,12 @@ class PPO:
         s, ac, B = self.storage, self.actor_critic, self.batch
         st = _lib.stream_ptr
         g = lambda src, sld, dst, dld, w: _lib.check(self.lib.b200_gather_rows(src, sld, _p_i64(indices), dst, dld, w, B, st()))
-        g(_p(s.observations), s.d_obs, _p(self.p_actor_in), ac.ld_actor_in, s.d_obs)
-        g(_p(s._est), s._est.shape[2], _p(self.p_actor_in, ac.col_est), ac.ld_actor_in, s._est.shape[2])   # actor sees the TRUE value (ppo.py:199)
-        g(_p(s._est), s._est.shape[2], _p(self.p_est), self.p_est.shape[1], s._est.shape[2])
-        g(_p(s._priv), s._priv.shape[2], _p(self.p_priv), self.p_priv.shape[1], s._priv.shape[2])
-        g(_p(s.critic_observations), s.d_crit, _p(self.p_crit), s.d_crit, s.d_crit)
-        g(_p(s.scan_observations), s.d_scan, _p(self.p_scan), s.d_scan, s.d_scan)
+        g(_p(s.observations), s.ld_obs, _p(self.p_actor_in), ac.ld_actor_in, s.d_obs)
+        g(_p(s._est), s.ld_est, _p(self.p_actor_in, ac.col_est), ac.ld_actor_in, s.w_est)   # actor sees the TRUE value (ppo.py:199)
+        g(_p(s._est), s.ld_est, _p(self.p_est), self.p_est.shape[1], s.w_est)
+        g(_p(s._priv), s.ld_priv, _p(self.p_priv), self.p_priv.shape[1], s.w_priv)
+        g(_p(s.critic_observations), s.ld_crit, _p(self.p_crit), s.d_crit, s.d_crit)
+        g(_p(s.scan_observations), s.ld_scan, _p(self.p_scan), s.d_scan, s.d_scan)
         g(_p(s.actions), s.d_act, _p(self.p_act), s.d_act, s.d_act)
         for src, dst in ((s.values, self.p_val), (s.returns, self.p_ret), (s.actions_log_prob, self.p_logp), (s.advantages, self.p_adv)):
             g(_p(src), 1, _p(dst), 1, 1)
@@ -545,6 +573,14 @@ class PPO:
                     self.lib.b200_tc_set_sm_cap(0)
         return ctx()
 
+    def _join_onto(self, stream, streams):
+        """make `stream` wait for everything queued on `streams` so far"""
+        for s in streams:
+            if s is not None and stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                stream.wait_event(ev)
+
     def _join(self, streams):
         for s in streams:
             if s is not None:
@@ -636,3 +672,12 @@ class PPO:
 
 def _p_i64(t):
     return C.c_void_p(t.data_ptr())
+
+
+def _rows16(t, need16=True):
+    """a [rows, cols] fp32 CUDA tensor the kernels can read in place: unit column stride and (need16: it feeds a TMA / 16-byte
+    vector path) a 16-byte aligned base and row pitch -- column slices of a wider row qualify; anything else is copied"""
+    ok = t.dim() == 2 and t.dtype == torch.float32 and t.is_cuda and (t.shape[1] == 1 or t.stride(1) == 1)
+    if ok and need16:
+        ok = t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0
+    return t if ok else t.to(torch.float32).contiguous()

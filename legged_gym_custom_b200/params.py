@@ -16,7 +16,7 @@ NUM_BODIES = 19
 NUM_FEET = 4
 MAX_SCAN_AXIS = 24
 MAX_PROPRIO = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # go2.urdf with collapse_fixed_joints (Head_*/foot joints are dont_collapse) -- SURVEY.md §8(c)
 BODY_NAMES = ["base", "Head_upper", "Head_lower"] + [
@@ -70,7 +70,7 @@ class EnvParams(C.Structure):
         ("feet", i32 * NUM_FEET), ("calves", i32 * NUM_FEET), ("n_penalised", i32), ("penalised", i32 * NUM_BODIES),
         ("n_termination", i32), ("termination", i32 * NUM_BODIES),
         ("hip_joints", i32 * 4), ("thigh_joints", i32 * 4), ("calf_joints", i32 * 4),
-        ("contact_thr2_term", f32), ("contact_thr2_collision", f32), ("_pad0", i32),
+        ("contact_thr2_term", f32), ("contact_thr2_collision", f32), ("alias_outputs", i32),
         ("seed", C.c_uint64),
         ("cc_vel_increment", C.c_double), ("cc_max_forward_vel", C.c_double), ("cc_max_reverse_vel", C.c_double),
         ("cc_range0", C.c_double * 2),
@@ -152,12 +152,14 @@ def _names_containing(keys, names):
     return out
 
 
-def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shape=None):
+def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shape=None, alias_outputs=False):
     """Pack a reference-style env cfg (class namespace or instance) into EnvParams.
 
-    `hs_shape` = (rows, cols) of height_samples for heightfield/trimesh terrains.
+    `hs_shape` = (rows, cols) of height_samples for heightfield/trimesh terrains.  `alias_outputs`: the observation outputs
+    exist once, as rows of critic_obs_buf (include/b200gym.h).
     """
     p = EnvParams()
+    p.alias_outputs = int(bool(alias_outputs))
     env, ter, cmd, ctl, dr = cfg.env, cfg.terrain, cfg.commands, cfg.control, cfg.domain_rand
     rew, norm, noise = cfg.rewards, cfg.normalization, cfg.noise
     p.abi_version = ABI_VERSION

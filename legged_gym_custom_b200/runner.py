@@ -53,12 +53,17 @@ class OnPolicyRunner:
         self.alg.defer_critic_join = True      # every act() of this runner is followed by process_env_step()
         self.dagger_update_freq = ac_["dagger_update_freq"]
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
+        # an env that can write its observation rows anywhere (Go2Env with alias_outputs) writes them straight into the
+        # rollout storage: step t's output is slot t + 1, the transition of the NEXT act() -- no observation copies at all
+        self.in_place_rows = bool(getattr(env, "supports_output_binding", False))
         self.alg.init_storage(num_envs=env.num_envs, num_transitions_per_env=self.num_steps_per_env, total_obs_shape=[env.num_obs],
                               privileged_obs_shape=[env.num_privileged_obs], critic_obs_shape=[env.num_critic_obs],
                               estimated_obs_shape=[env.num_estimated_obs], scan_obs_shape=[env.num_scan_obs],
-                              action_shape=[env.num_actions])
+                              action_shape=[env.num_actions], alias_critic_rows=self.in_place_rows)
         self.log_dir, self.writer = log_dir, None
         self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0, 0
+        if self.in_place_rows:                     # the reset's observation is "the row after the last transition"
+            self.env.bind_output_rows(self.alg.storage.rows[self.num_steps_per_env])
         self.env.reset()
         N = env.num_envs
         self._cur_rew, self._cur_len = torch.zeros(N, device=self.device), torch.zeros(N, device=self.device)
@@ -131,10 +136,16 @@ class OnPolicyRunner:
     # ---- one iteration = rollout + GAE + update (on_policy_runner.py:144-194) -----------------------------
     def _rollout_eager(self, use_adaptation_mode):
         env, alg = self.env, self.alg
+        if self.in_place_rows:                     # the last row of the previous rollout is the first of this one
+            rows = alg.storage.rows
+            rows[0].copy_(rows[self.num_steps_per_env])
+            env.bind_output_rows(rows[0])
         obs, priv, crit = env.get_observations(), env.get_privileged_observations(), env.get_critic_observations()
         est, scan = env.get_estimated_observations(), env.get_scan_observations()
-        for _ in range(self.num_steps_per_env):
+        for t in range(self.num_steps_per_env):
             actions = alg.act(obs, priv, crit, est, scan, adaptation_mode=use_adaptation_mode)
+            if self.in_place_rows:
+                env.bind_output_rows(rows[t + 1])
             obs, priv, crit, est, scan, rewards, dones, infos = env.step(actions)
             alg.process_env_step(rewards, dones, infos)
             if self.log_dir is not None:

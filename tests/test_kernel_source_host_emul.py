@@ -17,11 +17,12 @@ def lib():
     return emul.load()
 
 
-@pytest.mark.parametrize("force_generic", [0, 1], ids=["go2-layout-baked-in", "layout-generic"])
+@pytest.mark.parametrize("force_generic,alias", [(0, 0), (1, 0), (0, 1)], ids=["go2-layout-baked-in", "layout-generic", "aliased-output-rows"])
 @pytest.mark.parametrize("task", gu.TASKS + gu.CC_SCENARIOS)
-def test_kernel_source_matches_reference(lib, task, force_generic):
+def test_kernel_source_matches_reference(lib, task, force_generic, alias):
     g = gu.load(task)
     p = gu.params_for(task, g)
+    p.alias_outputs = alias            # obs / priv / est / scan are column slices of the critic rows, written once
     bufs = BufferSet(p, "cpu", record_height_index=True)
     bufs.load_statics(gu.statics_for(task, g))
     st = gu.init_state(g, p)
