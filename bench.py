@@ -436,7 +436,7 @@ def run_b200(args):
                 "config": {"workload": f"{args.task}: rollout of {T_STEPS} env steps (policy inference + 4 PD substeps + post-physics) "
                                        f"+ GAE + PPO update (5 epochs x 4 minibatches of {T_STEPS * N // 4}), {N} envs/GPU, "
                                        "PhysX replaced by a ring of replayed synthetic frames",
-                           "num_envs_per_gpu": N, "parallelism": f"dp{world} (envs sharded, flat-gradient NCCL all-reduce)",
+                           "num_envs_per_gpu": N, "parallelism": f"dp{world} (envs sharded; optimiser step: {runner.alg.dist_mode})",
                            "l2": "working set per iteration (~1.3 GB of rollout storage + permuted slabs) exceeds the 126 MB L2",
                            "timed_iterations": f"it {first}..{first + K - 1} (every 20th is a DAgger iteration with the adaptation-mode rollout, as in the "
                                                "reference's loop; all CUDA graphs are captured during set-up, before it 0)",

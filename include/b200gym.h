@@ -448,6 +448,38 @@ int b200_adaptive_lr(double* acc, int64_t count, double desired_kl, double* adam
  * [6] (out) post-clip squared norm of `grads` -- what update_dagger hands to the main optimiser's [7]. */
 int b200_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double* state,
                    float grad_scale, float max_norm, float beta1, float beta2, float eps, void* stream);
+
+/* The data-parallel form of the same step (section 8 row e): gradient exchange + clip_grad_norm_ + Adam as
+ * ONE kernel per optimiser step over NVLink / NVSwitch peer memory -- replaces all_reduce(grads) + b200_clip_adam on every
+ * rank.  `grads`, `params` and the sync area are SYMMETRIC allocations (one per rank, every rank's mapped into every rank:
+ * `*_peer[p]` = rank p's buffer as seen from here, own rank included; host arrays of `world` device pointers); `*_mc` are
+ * their NVSwitch multicast addresses or NULL (then the kernel loops over the peers).  Rank r owns shard r of the flat
+ * buffers: it reduces that shard of all ranks' gradients (multimem.ld_reduce: the switch adds), contributes the shard's sum
+ * of squares to the global norm (W doubles exchanged through the sync area, summed in rank order), applies clip + Adam to
+ * its shard only -- `exp_avg` / `exp_avg_sq` are maintained for the own shard only -- and broadcasts the updated parameters
+ * (multimem.st); the shard of every rank's `grads` is left zeroed.  Start / end barriers between the ranks are inside the
+ * kernel (flags in the sync area: 4 * world uint64, zero-initialised once).  `local`: 8 uint32 of zero-initialised device
+ * scratch (barrier epoch, grid counters, partial sum); `gsum`: ceil(n / 4 / world) * 4 floats of scratch.  `state` as for
+ * b200_clip_adam (the gradient is the MEAN over ranks, i.e. grad_scale = 1 / world).  Every rank must launch the call the
+ * same number of times, in the same order per sync area. */
+typedef struct B200DistAdam {
+  float* grads;
+  float* params;
+  float* const* grads_peer;                 /* host [world] */
+  float* const* params_peer;                /* host [world] */
+  unsigned long long* const* sync_peer;     /* host [world] */
+  float* grads_mc;
+  float* params_mc;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* gsum;
+  double* state;
+  unsigned int* local;
+  int64_t n;
+  int32_t world, rank;
+  float max_norm, beta1, beta2, eps;
+} B200DistAdam;
+int b200_dist_adam(const B200DistAdam* args /* host */, void* stream);
 /* AdaptationEncoder.forward (support_networks.py:128-175) fused into one fp32 kernel.  X [M, >=520] = observation rows
  * whose first 10*52 columns are the proprio history.  Weights in the kernel layouts of networks.py: W1 [30][52],
  * W2 [20][4*32] (tap*32 + channel), W3 [10][2*20], W4 [20][3*12] (step*12 + channel).  proj/c1/c2: optional

@@ -53,6 +53,7 @@ SYMBOLS = {
     "b200_l2_rows_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200_elu_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p]),
+    "b200_dist_adam": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_kl_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200_adaptive_lr": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
     "b200_adaptation_forward": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]),
@@ -64,6 +65,15 @@ SYMBOLS = {
 class CopySeg(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("src_ld", C.c_int32), ("dst_ld", C.c_int32),
                 ("_pad", C.c_int32)]
+
+
+class DistAdamArgs(C.Structure):
+    """B200DistAdam (include/b200gym.h)"""
+    _fields_ = [("grads", C.c_void_p), ("params", C.c_void_p), ("grads_peer", C.POINTER(C.c_void_p)), ("params_peer", C.POINTER(C.c_void_p)),
+                ("sync_peer", C.POINTER(C.c_void_p)), ("grads_mc", C.c_void_p), ("params_mc", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("gsum", C.c_void_p), ("state", C.c_void_p), ("local", C.c_void_p), ("n", C.c_int64),
+                ("world", C.c_int32), ("rank", C.c_int32), ("max_norm", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float)]
 
 
 class PpoLossArgs(C.Structure):

@@ -23,6 +23,7 @@ UNITS = [
     ("learner_kernels.cu", []),
     ("linear_kernels.cu", []),
     ("mlp_tcgen05.cu", []),
+    ("dist_adam.cu", []),
 ]
 
 

@@ -152,8 +152,11 @@ class _AdamFacade:
 
     def state_dict(self):
         g = self.group
-        return {"flat_exp_avg": g.exp_avg.clone(), "flat_exp_avg_sq": g.exp_avg_sq.clone(), "adam_state": g.state.clone(),
-                "param_groups": self.param_groups}
+        if getattr(g, "dist", None) is not None:          # sharded moments: collect every rank's shard over the peer mappings
+            m, v = g.dist.full_moments()
+        else:
+            m, v = g.exp_avg.clone(), g.exp_avg_sq.clone()
+        return {"flat_exp_avg": m, "flat_exp_avg_sq": v, "adam_state": g.state.clone(), "param_groups": self.param_groups}
 
     def load_state_dict(self, sd):
         g = self.group
@@ -201,6 +204,10 @@ class PPO:
         self.act_counter = 0
         self.process_group = process_group            # torch.distributed group for the gradient all-reduce, or None
         self.world_size = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        # data-parallel optimiser steps: ONE kernel does gradient exchange + clip + Adam + parameter all-gather over peer memory
+        # (csrc/dist_adam.cu); NCCL all-reduce + the local kernels only where symmetric memory cannot be set up
+        from .dist import enable_fused_dist_adam
+        self.dist_mode = enable_fused_dist_adam([ac.main, ac.adapt, estimator.group], process_group, max_grad_norm)
         self._perm_gen = torch.Generator(device=self.device).manual_seed(seed + 12345)
         self.act_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.use_device_counter = False
@@ -425,6 +432,9 @@ class PPO:
         allreduce_flat_grads([group], self.process_group)
 
     def _adam(self, group):
+        if getattr(group, "dist", None) is not None:      # exchange + clip + Adam + all-gather in one kernel
+            group.dist.step()
+            return
         self._allreduce(group)
         _lib.check(self.lib.b200_clip_adam(_p(group.params), _p(group.grads), _p(group.exp_avg), _p(group.exp_avg_sq), group.n,
                                            C.c_void_p(group.state.data_ptr()), 1.0 / self.world_size, self.max_grad_norm, 0.9, 0.999, 1e-8,
