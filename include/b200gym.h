@@ -369,6 +369,10 @@ int b200_tc_set_pdl(int on);
  * device; 0 = no cap.  The learner caps the low-priority side-stream chains (critic, estimator) so that their one-wave
  * persistent kernels leave SMs to the small kernels of the critical path.  Host-side state, read at launch time. */
 int b200_tc_set_sm_cap(int sms);
+/* 2: forward / dgrad launches run TWO persistent CTAs per SM on tiles <= 128 columns wide (2 x 256 TMEM columns, half the
+ * operand ring each), so that one CTA's epilogue overlaps the other's main loop; 1 (default): one CTA per SM, tiles up to
+ * 256 wide, CTA pairs for the large forward problems.  Host-side state, read at launch time (A/B switch). */
+int b200_tc_set_ctas_per_sm(int n);
 /* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
  * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */
 int b200_tc_linear_supported(int M, int N, int K);

@@ -185,20 +185,23 @@ struct TcArgs {
 // A-operand smem per stage: K-major  [BM rows][32]         = 16 KB
 //                           MN-major 4 chunks x [32 k][32]  = 16 KB   (chunk = 32 fp32 of the M dimension)
 // B-operand smem per stage: K-major  [BN rows][32]; MN-major (BN/32) chunks x [32 k][32]      = BN * 128 B
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int CPS = 1>
 struct TileCfg {
   static constexpr int BNH = PAIR ? BN / 2 : BN;                  // rows of B this CTA stages
   static constexpr int BMT = PAIR ? 2 * BM : BM;                  // rows of the output tile (pair: 256)
   static constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BNH * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   // shared-memory budget of the operand ring: what is left of 227 KB after the epilogue's staging tiles (36 KB), the
   // dgrad's column-sum buffer (<= 8 KB) and the barriers
-  static constexpr int STAGES_ = (int)((176u * 1024u) / STAGE_BYTES) < 8 ? (int)((176u * 1024u) / STAGE_BYTES) : 8;
+  // (CPS = 2: two CTAs share the SM -- one's epilogue runs under the other's main loop -- with half the ring each)
+  static constexpr uint32_t RING_BYTES = CPS == 2 ? 70u * 1024u : 176u * 1024u;
+  static constexpr int STAGES_ = (int)(RING_BYTES / STAGE_BYTES) < 8 ? (int)(RING_BYTES / STAGE_BYTES) : 8;
+  static_assert(STAGES_ >= 2, "operand ring needs at least two stages");
 };
 
-template <int MODE, int BN, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int MODE, int BN, bool PAIR, int CPS = 1>
+__global__ void __launch_bounds__(NUM_THREADS, CPS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
-  using Cfg = TileCfg<BN, PAIR>;
+  using Cfg = TileCfg<BN, PAIR, CPS>;
   constexpr bool A_MN = (MODE == TN), B_MN = (MODE != NT);
   constexpr int BNH = Cfg::BNH, BMT = Cfg::BMT, STAGES = Cfg::STAGES_;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -366,7 +369,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ax_next[it] = v4;
         }
       };
-      if (ci_lo < ci_hi) load_aux(ci_lo);
+      if (CPS == 1 && ci_lo < ci_hi) load_aux(ci_lo);      // (CPS = 2: the partner CTA hides the latency; no prefetch registers)
       mbar_wait(tmem_full + acc, acc_ph);
       tc_fence_after();
       const bool want_colsum = (MODE == NN) && g.dbias != nullptr;
@@ -377,9 +380,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int col0 = n0 + c;
         float ay[32];
         if (MODE == NN && g.aux != nullptr) {
+          if (CPS == 2) load_aux(ci);
 #pragma unroll
           for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(stg + (it * 4 + sr) * STG_PITCH + sc) = ax_next[it];
-          if (ci + 1 < ci_hi) load_aux(ci + 1);
+          if (CPS == 1 && ci + 1 < ci_hi) load_aux(ci + 1);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -562,17 +566,20 @@ int avail_sms() {
   return (g_sm_cap > 0 && g_sm_cap < n) ? g_sm_cap : n;
 }
 
+int g_cps = 1;            // b200_tc_set_ctas_per_sm: 2 = forward / dgrad tiles <= 128 wide run two CTAs per SM (A/B)
 int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
 
-template <int MODE, int BN, bool PAIR = false>
+template <int MODE, int BN, bool PAIR = false, int CPS = 1>
 int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int splits, cudaStream_t st, const char* name) {
-  using Cfg = TileCfg<BN, PAIR>;
+  using Cfg = TileCfg<BN, PAIR, CPS>;
+  static_assert(CPS == 1 || (!PAIR && 2 * BN <= 256), "two CTAs per SM: 2 x 256 TMEM columns, no CTA pairs");
   constexpr int smem = Cfg::STAGES_ * (int)Cfg::STAGE_BYTES + 256 + (MODE == NN ? 2 * 4 * BN * 4 : 0) + 8 * 32 * 36 * 4 + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration does not fit shared memory");
-  auto kern = tc_gemm_kernel<MODE, BN, PAIR>;
+  auto kern = tc_gemm_kernel<MODE, BN, PAIR, CPS>;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && CPS == 2) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
       b200_set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
       return (int)e;
@@ -589,7 +596,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
     gt.trace = g_trace + 2 * (size_t)i;
   }
   const int tiles = ((g.M + Cfg::BMT - 1) / Cfg::BMT) * ((g.N + BN - 1) / BN);
-  int workers = (PAIR ? avail_sms() / 2 : avail_sms()) / (splits > 1 ? splits : 1);
+  int workers = (PAIR ? avail_sms() / 2 : avail_sms() * CPS) / (splits > 1 ? splits : 1);
   workers = workers < 1 ? 1 : workers;
   workers = tiles < workers ? tiles : workers;
   cudaLaunchConfig_t cfg = {};
@@ -692,6 +699,11 @@ int b200_tc_set_sm_cap(int sms) {
   return 0;
 }
 
+int b200_tc_set_ctas_per_sm(int n) {
+  g_cps = n == 2 ? 2 : 1;
+  return 0;
+}
+
 int b200_tc_set_pair_mode(int on) {
   g_pair_mode = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 forward only (default), 2 forward + dgrad
   return 0;
@@ -705,8 +717,9 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
   B200_CHECK_ARG(X && W && Y && M > 0 && N > 0 && K > 0, "b200_tc_linear_forward: bad argument");
   B200_CHECK_ARG(b200_tc_linear_supported(M, N, K), "b200_tc_linear_forward: needs N >= 8 and K >= 8 (N=%d K=%d)", N, K);
   B200_CHECK_ARG(ldx % 4 == 0 && ldw % 4 == 0 && aligned16(X) && aligned16(W), "b200_tc_linear_forward: operands need 16-byte rows");
-  const int pbn = pick_pair_bn(M, N);
-  const int bn = pbn ? pbn : pick_bn(M, N);
+  const int pbn = g_cps == 2 ? 0 : pick_pair_bn(M, N);
+  int bn = pbn ? pbn : pick_bn(M, N);
+  if (g_cps == 2 && bn > 128) bn = 128;
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, X, M, K, ldx, BM, 0)) return rc;
   if (int rc = make_tmap(&tb, W, N, K, ldw, pbn ? bn / 2 : bn, 0)) return rc;   // pair: each CTA stages half of the B rows
@@ -719,6 +732,11 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
     case 64: return launch_tc<NT, 64, true>(ta, tb, g, 1, st, "tc_forward_pair<64>");
     default: break;
   }
+  if (g_cps == 2) switch (bn) {
+      case 128: return launch_tc<NT, 128, false, 2>(ta, tb, g, 1, st, "tc_forward<128,2/SM>");
+      case 64: return launch_tc<NT, 64, false, 2>(ta, tb, g, 1, st, "tc_forward<64,2/SM>");
+      default: return launch_tc<NT, 32, false, 2>(ta, tb, g, 1, st, "tc_forward<32,2/SM>");
+    }
   switch (bn) {
     case 256: return launch_tc<NT, 256>(ta, tb, g, 1, st, "tc_forward<256>");
     case 128: return launch_tc<NT, 128>(ta, tb, g, 1, st, "tc_forward<128>");
@@ -739,8 +757,9 @@ int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw
   B200_CHECK_ARG(dY && W && dX && M > 0 && N > 0 && K > 0, "b200_tc_linear_dgrad: bad argument");
   B200_CHECK_ARG(!(dbias_prev && accumulate), "b200_tc_linear_dgrad_bias: the fused bias gradient needs accumulate = 0");
   B200_CHECK_ARG(lddy % 4 == 0 && ldw % 4 == 0 && aligned16(dY) && aligned16(W), "b200_tc_linear_dgrad: operands need 16-byte rows");
-  const int pbn = g_pair_mode == 2 ? pick_pair_bn(M, K) : 0;   // measured: pairs do not pay for the dgrads (epilogue-bound); 2 = force
-  const int bn = pbn ? pbn : pick_bn(M, K);
+  const int pbn = (g_pair_mode == 2 && g_cps != 2) ? pick_pair_bn(M, K) : 0;   // measured: pairs do not pay for the dgrads (epilogue-bound); 2 = force
+  int bn = pbn ? pbn : pick_bn(M, K);
+  if (g_cps == 2 && bn > 128) bn = 128;
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, dY, M, N, lddy, BM, 0)) return rc;          // A K-major: [M rows][N reduction]
   if (int rc = make_tmap(&tb, W, N, K, ldw, BK, 1)) return rc;            // B MN-major: box [32 n][32 k]
@@ -753,6 +772,11 @@ int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw
     case 64: return launch_tc<NN, 64, true>(ta, tb, g, 1, st, "tc_dgrad_pair<64>");
     default: break;
   }
+  if (g_cps == 2) switch (bn) {
+      case 128: return launch_tc<NN, 128, false, 2>(ta, tb, g, 1, st, "tc_dgrad<128,2/SM>");
+      case 64: return launch_tc<NN, 64, false, 2>(ta, tb, g, 1, st, "tc_dgrad<64,2/SM>");
+      default: return launch_tc<NN, 32, false, 2>(ta, tb, g, 1, st, "tc_dgrad<32,2/SM>");
+    }
   switch (bn) {
     case 256: return launch_tc<NN, 256>(ta, tb, g, 1, st, "tc_dgrad<256>");
     case 128: return launch_tc<NN, 128>(ta, tb, g, 1, st, "tc_dgrad<128>");

@@ -10,6 +10,8 @@ from legged_gym_custom_b200 import _lib  # noqa: E402
 lib = _lib.lib()
 if os.environ.get("B200_PAIR") is not None:
     lib.b200_tc_set_pair_mode(int(os.environ["B200_PAIR"]))
+if os.environ.get("B200_CPS") is not None:
+    lib.b200_tc_set_ctas_per_sm(int(os.environ["B200_CPS"]))
 DEV = "cuda:0"
 ld = lambda k: (k + 3) // 4 * 4
 p = lambda t: t.data_ptr()
