@@ -109,7 +109,7 @@ class Profile:
     def hook(self, name, raw, args):
         from legged_gym_custom_b200 import _lib
         if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version",
-                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_tc_set_sm_cap", "b200_tc_set_ctas_per_sm", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
+                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_tc_set_sm_cap", "b200_tc_set_ctas_per_sm", "b200_tc_set_stream_sm_cap", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
             return raw(*args)
         self.count += _lib.LAUNCHES.get(name, 1)
         self.by_entry[name] = self.by_entry.get(name, 0) + _lib.LAUNCHES.get(name, 1)
@@ -181,8 +181,6 @@ def build_runner(args, rank, world, device, host_physx=False):
         runner.alg.side_sm_cap = args.side_sm_cap
     if args.offload_wgrads is not None:
         runner.alg.offload_wgrads = bool(args.offload_wgrads)
-    if args.side_sm_cap_forward is not None:
-        runner.alg.side_sm_cap_forward = args.side_sm_cap_forward
     env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
     if not args.no_graphs:
         runner.enable_graphs()
@@ -616,7 +614,6 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--pdl", action="store_true", help="launch the tcgen05 GEMMs with programmatic dependent launch (A/B; default off)")
     ap.add_argument("--side-sm-cap", type=int, default=None, help="SMs the low-priority side chains of the update may occupy (A/B; 0 = all)")
-    ap.add_argument("--side-sm-cap-forward", type=int, default=None, help="the same for the side chains' forward GEMMs only (default: = --side-sm-cap)")
     ap.add_argument("--offload-wgrads", type=int, default=None, help="actor / encoder weight-gradient GEMMs on their own low-priority stream (A/B)")
     ap.add_argument("--ctas-per-sm", type=int, default=None, help="tcgen05 forward / dgrad: 2 = two persistent CTAs per SM on <= 128-wide tiles (A/B)")
     ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")

@@ -369,9 +369,13 @@ int b200_tc_set_pdl(int on);
  * device; 0 = no cap.  The learner caps the low-priority side-stream chains (critic, estimator) so that their one-wave
  * persistent kernels leave SMs to the small kernels of the critical path.  Host-side state, read at launch time. */
 int b200_tc_set_sm_cap(int sms);
+/* The same cap as a property of ONE stream: every GEMM launched to `stream` from now on is sized for `sms` SMs (0 removes
+ * the cap).  What the learner uses (set once per side stream): no process-wide state to toggle around launches. */
+int b200_tc_set_stream_sm_cap(void* stream, int sms);
 /* 2: forward / dgrad launches run TWO persistent CTAs per SM on tiles <= 128 columns wide (2 x 256 TMEM columns, half the
- * operand ring each), so that one CTA's epilogue overlaps the other's main loop; 1 (default): one CTA per SM, tiles up to
- * 256 wide, CTA pairs for the large forward problems.  Host-side state, read at launch time (A/B switch). */
+ * operand ring each), so that one CTA's epilogue overlaps the other's main loop; 1: one CTA per SM, tiles up to 256 wide,
+ * CTA pairs for the large forward problems; 0 (default): by shape -- outputs up to 256 columns wide take 2, wider ones 1.
+ * Host-side state, read at launch time (A/B switch). */
 int b200_tc_set_ctas_per_sm(int n);
 /* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
  * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */

@@ -560,13 +560,26 @@ int g_trace_cap = 0, g_trace_next = 0;
 // instead of all of them.  A persistent one-wave kernel holds every SM until it ends, so a LOW-priority big GEMM starves the
 // small kernels of the critical path no matter what the stream priorities say (priorities only order PENDING CTAs): the
 // learner caps the side-stream chains and leaves the rest of the machine to the critical path.
+// The cap is a property of the STREAM a launch goes to (b200_tc_set_stream_sm_cap, set once when the learner creates its
+// low-priority side streams): no process-wide switch to toggle around blocks of launches, nothing to restore after an
+// exception.  b200_tc_set_sm_cap (process-wide) remains for A/B tools.
 int g_sm_cap = 0;
-int avail_sms() {
+struct StreamCap { cudaStream_t stream; int cap; };
+StreamCap g_stream_caps[16];
+int g_num_stream_caps = 0;
+int avail_sms(cudaStream_t st) {
   const int n = num_sms();
-  return (g_sm_cap > 0 && g_sm_cap < n) ? g_sm_cap : n;
+  int cap = g_sm_cap;
+  for (int i = 0; i < g_num_stream_caps; ++i)
+    if (g_stream_caps[i].stream == st) cap = g_stream_caps[i].cap;
+  return (cap > 0 && cap < n) ? cap : n;
 }
 
-int g_cps = 1;            // b200_tc_set_ctas_per_sm: 2 = forward / dgrad tiles <= 128 wide run two CTAs per SM (A/B)
+// b200_tc_set_ctas_per_sm: 0 (default) = by shape: outputs up to 256 columns wide run two CTAs per SM on <= 128-wide tiles
+// (measured on B200, M = 24576: forward 256 x 512 26.1 -> 23.3 us, 128 x 256 14.8 -> 12.8 us), wider ones one CTA per SM on
+// 256-wide tiles / CTA pairs (512 x 627: 43.5 us against 62.9 us with two CTAs); 1 / 2 force either (A/B runs)
+int g_cps = 0;
+int cps_for(int cols) { return g_cps == 0 ? (cols <= 256 ? 2 : 1) : g_cps; }
 int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
 
 template <int MODE, int BN, bool PAIR = false, int CPS = 1>
@@ -596,7 +609,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
     gt.trace = g_trace + 2 * (size_t)i;
   }
   const int tiles = ((g.M + Cfg::BMT - 1) / Cfg::BMT) * ((g.N + BN - 1) / BN);
-  int workers = (PAIR ? avail_sms() / 2 : avail_sms() * CPS) / (splits > 1 ? splits : 1);
+  int workers = (PAIR ? avail_sms(st) / 2 : avail_sms(st) * CPS) / (splits > 1 ? splits : 1);
   workers = workers < 1 ? 1 : workers;
   workers = tiles < workers ? tiles : workers;
   cudaLaunchConfig_t cfg = {};
@@ -699,8 +712,20 @@ int b200_tc_set_sm_cap(int sms) {
   return 0;
 }
 
+int b200_tc_set_stream_sm_cap(void* stream, int sms) {
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < g_num_stream_caps; ++i)
+    if (g_stream_caps[i].stream == st) {
+      g_stream_caps[i].cap = sms > 0 ? sms : 0;
+      return 0;
+    }
+  B200_CHECK_ARG(g_num_stream_caps < 16, "b200_tc_set_stream_sm_cap: more than 16 capped streams");
+  g_stream_caps[g_num_stream_caps++] = StreamCap{st, sms > 0 ? sms : 0};
+  return 0;
+}
+
 int b200_tc_set_ctas_per_sm(int n) {
-  g_cps = n == 2 ? 2 : 1;
+  g_cps = (n == 1 || n == 2) ? n : 0;
   return 0;
 }
 
@@ -717,9 +742,10 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
   B200_CHECK_ARG(X && W && Y && M > 0 && N > 0 && K > 0, "b200_tc_linear_forward: bad argument");
   B200_CHECK_ARG(b200_tc_linear_supported(M, N, K), "b200_tc_linear_forward: needs N >= 8 and K >= 8 (N=%d K=%d)", N, K);
   B200_CHECK_ARG(ldx % 4 == 0 && ldw % 4 == 0 && aligned16(X) && aligned16(W), "b200_tc_linear_forward: operands need 16-byte rows");
-  const int pbn = g_cps == 2 ? 0 : pick_pair_bn(M, N);
+  const int cps = cps_for(N);
+  const int pbn = cps == 2 ? 0 : pick_pair_bn(M, N);
   int bn = pbn ? pbn : pick_bn(M, N);
-  if (g_cps == 2 && bn > 128) bn = 128;
+  if (cps == 2 && bn > 128) bn = 128;
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, X, M, K, ldx, BM, 0)) return rc;
   if (int rc = make_tmap(&tb, W, N, K, ldw, pbn ? bn / 2 : bn, 0)) return rc;   // pair: each CTA stages half of the B rows
@@ -732,7 +758,7 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
     case 64: return launch_tc<NT, 64, true>(ta, tb, g, 1, st, "tc_forward_pair<64>");
     default: break;
   }
-  if (g_cps == 2) switch (bn) {
+  if (cps == 2) switch (bn) {
       case 128: return launch_tc<NT, 128, false, 2>(ta, tb, g, 1, st, "tc_forward<128,2/SM>");
       case 64: return launch_tc<NT, 64, false, 2>(ta, tb, g, 1, st, "tc_forward<64,2/SM>");
       default: return launch_tc<NT, 32, false, 2>(ta, tb, g, 1, st, "tc_forward<32,2/SM>");
@@ -757,9 +783,10 @@ int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw
   B200_CHECK_ARG(dY && W && dX && M > 0 && N > 0 && K > 0, "b200_tc_linear_dgrad: bad argument");
   B200_CHECK_ARG(!(dbias_prev && accumulate), "b200_tc_linear_dgrad_bias: the fused bias gradient needs accumulate = 0");
   B200_CHECK_ARG(lddy % 4 == 0 && ldw % 4 == 0 && aligned16(dY) && aligned16(W), "b200_tc_linear_dgrad: operands need 16-byte rows");
-  const int pbn = (g_pair_mode == 2 && g_cps != 2) ? pick_pair_bn(M, K) : 0;   // measured: pairs do not pay for the dgrads (epilogue-bound); 2 = force
+  const int cps = cps_for(K);
+  const int pbn = (g_pair_mode == 2 && cps != 2) ? pick_pair_bn(M, K) : 0;   // measured: pairs do not pay for the dgrads (epilogue-bound); 2 = force
   int bn = pbn ? pbn : pick_bn(M, K);
-  if (g_cps == 2 && bn > 128) bn = 128;
+  if (cps == 2 && bn > 128) bn = 128;
   CUtensorMap ta, tb;
   if (int rc = make_tmap(&ta, dY, M, N, lddy, BM, 0)) return rc;          // A K-major: [M rows][N reduction]
   if (int rc = make_tmap(&tb, W, N, K, ldw, BK, 1)) return rc;            // B MN-major: box [32 n][32 k]
@@ -772,7 +799,7 @@ int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw
     case 64: return launch_tc<NN, 64, true>(ta, tb, g, 1, st, "tc_dgrad_pair<64>");
     default: break;
   }
-  if (g_cps == 2) switch (bn) {
+  if (cps == 2) switch (bn) {
       case 128: return launch_tc<NN, 128, false, 2>(ta, tb, g, 1, st, "tc_dgrad<128,2/SM>");
       case 64: return launch_tc<NN, 64, false, 2>(ta, tb, g, 1, st, "tc_dgrad<64,2/SM>");
       default: return launch_tc<NN, 32, false, 2>(ta, tb, g, 1, st, "tc_dgrad<32,2/SM>");
@@ -798,7 +825,7 @@ int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, flo
   TcArgs g{};
   g.C = dW; g.ldc = ldw; g.M = N; g.N = K; g.K = M;
   const int tiles = ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
-  int splits = avail_sms() / (tiles < 1 ? 1 : tiles);
+  int splits = avail_sms((cudaStream_t)stream) / (tiles < 1 ? 1 : tiles);
   const int max_splits = (M + 8 * BK - 1) / (8 * BK);
   splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
   int per = (M + splits - 1) / splits;

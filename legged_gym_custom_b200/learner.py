@@ -218,7 +218,7 @@ class PPO:
         # path whatever the stream priorities are (b200_tc_set_sm_cap).  Measured on B200 (148 SMs), update of 20 minibatches:
         # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt)
         self.side_sm_cap = 116
-        self.side_sm_cap_forward = None      # cap of the side chains' FORWARD GEMMs; None = the same as side_sm_cap
+        self._stream_caps = {}               # cuda stream -> cap registered with the library
         # weight-gradient GEMMs of the actor / encoder chains on a fifth (low-priority, capped) stream: the dgrad chain that
         # the encoders' backward waits for no longer queues behind them
         self.offload_wgrads = False
@@ -566,22 +566,13 @@ class PPO:
         return run
 
     def _capped(self, stream, forward=False):
-        """`_on(stream)` for a LOW-priority chain of the update: its GEMM launches are sized for `side_sm_cap` SMs"""
-        import contextlib
-
-        @contextlib.contextmanager
-        def ctx():
-            cap = self.side_sm_cap_forward if (forward and self.side_sm_cap_forward is not None) else self.side_sm_cap
-            cap = cap if (self.use_streams and stream is not None) else 0
-            if cap:
-                self.lib.b200_tc_set_sm_cap(int(cap))
-            try:
-                with self._on(stream):
-                    yield
-            finally:
-                if cap:
-                    self.lib.b200_tc_set_sm_cap(0)
-        return ctx()
+        """`_on(stream)` for a LOW-priority chain of the update.  Its GEMM launches are sized for `side_sm_cap` SMs: the cap is
+        a property of the stream inside the library (b200_tc_set_stream_sm_cap), (re)registered here whenever it changed."""
+        cap = self.side_sm_cap if (self.use_streams and stream is not None) else 0
+        if stream is not None and self._stream_caps.get(stream.cuda_stream) != cap:
+            _lib.check(self.lib.b200_tc_set_stream_sm_cap(C.c_void_p(stream.cuda_stream), int(cap or 0)))
+            self._stream_caps[stream.cuda_stream] = cap
+        return self._on(stream)
 
     def _join_onto(self, stream, streams):
         """make `stream` wait for everything queued on `streams` so far"""

@@ -177,6 +177,30 @@ def test_tcgen05_pair_pdl_switches_and_launch_trace():
         lib.b200_tc_set_pdl(0)
     for Y in outs[1:]:
         assert torch.equal(Y, outs[0])
+    # one / two persistent CTAs per SM (b200_tc_set_ctas_per_sm) and a per-stream SM cap (b200_tc_set_stream_sm_cap) change the
+    # schedule of the tiles, not what a tile computes
+    M2, N2, K2 = 24576, 256, 512
+    X2, W2 = torch.randn(M2, K2, generator=g).to(DEV), (torch.randn(N2, K2, generator=g) / K2 ** 0.5).to(DEV)
+    dY2, Yp2 = torch.randn(M2, N2, generator=g).to(DEV), torch.randn(M2, K2, generator=g).to(DEV)
+    side = torch.cuda.Stream()
+    res = []
+    try:
+        for cps, cap in ((1, 0), (2, 0), (0, 0), (0, 100)):
+            lib.b200_tc_set_ctas_per_sm(cps)
+            _lib.check(lib.b200_tc_set_stream_sm_cap(C.c_void_p(side.cuda_stream), cap))
+            Y2, dX2 = torch.zeros(M2, N2, device=DEV), torch.zeros(M2, K2, device=DEV)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(side):
+                sp = _lib.stream_ptr()
+                _lib.check(lib.b200_tc_linear_forward(p(X2), K2, p(W2), K2, p(bd), p(Y2), N2, M2, N2, K2, 1, sp))
+                _lib.check(lib.b200_tc_linear_dgrad(p(dY2), N2, p(W2), K2, p(Yp2), K2, p(dX2), K2, M2, N2, K2, 0, sp))
+            torch.cuda.synchronize()
+            res.append((Y2, dX2))
+    finally:
+        lib.b200_tc_set_ctas_per_sm(0)
+        lib.b200_tc_set_stream_sm_cap(C.c_void_p(side.cuda_stream), 0)
+    for Y2, dX2 in res[1:]:
+        assert torch.equal(Y2, res[0][0]) and torch.equal(dX2, res[0][1])
     dev = torch.zeros(4, 2, dtype=torch.int64, device=DEV)
     dev[:, 0] = torch.iinfo(torch.int64).max
     meta = np.zeros((4, 4), dtype=np.int64)
