@@ -1141,7 +1141,17 @@ B200_HD void env_init_one(const B200EnvParams& P, const B200EnvBuffers& B, const
   }
   if (I.num_init_levels > 0) {                           // _get_env_origins with a height field (legged_robot.py:904-917)
     const int64_t level = (int64_t)(keyed_u32(P.seed, SITE_INIT_LEVEL, 0, ue, 0) % (uint32_t)I.num_init_levels);
-    const int64_t type = (int64_t)floorf((float)e / (float)((double)P.num_envs / (double)I.terrain_cols));
+    // torch.div(arange(N), N / num_cols, rounding_mode='floor') in fp32 (legged_robot.py:909): torch's floor division is
+    // fmod-based -- (a - fmod(a, b)) / b, then floor with a half-ulp guard -- NOT floor(a / b): at an exact multiple of the
+    // rounded-up fp32 divisor (env 1024 of 4096 with 20 columns: 1024 / 204.8000031) a / b rounds UP to 5.0 while the
+    // reference assigns column 4.  Pinned to the reference's own terrain_types (tests/test_env_init.py).
+    const float a_ = (float)e, b_ = (float)((double)P.num_envs / (double)I.terrain_cols);
+    const float mod_ = fmodf(a_, b_);
+    float div_ = (a_ - mod_) / b_;
+    if (mod_ != 0.0f && ((b_ < 0.0f) != (mod_ < 0.0f))) div_ -= 1.0f;
+    float fl_ = floorf(div_);
+    if (div_ - fl_ > 0.5f) fl_ += 1.0f;
+    const int64_t type = (int64_t)fl_;
     B.terrain_levels[e] = level;
     const_cast<int64_t*>(B.terrain_types)[e] = type;
     const float* o = B.terrain_origins + (level * I.terrain_cols + type) * 3;

@@ -1,8 +1,9 @@
 """`OnPolicyRunner`: drop-in for rsl_rl/runners/on_policy_runner.py (same constructor, `learn`, `save`,
 `load`, `get_inference_policy`), driving `Go2Env` and the kernel-backed `PPO`.
 
-Differences that are deliberate: episode statistics are accumulated on the
-device and read once per iteration instead of `.cpu().numpy()` every env step, and checkpoints additionally
+Differences that are deliberate: the finished episodes of a rollout are collected on the
+device and read back once per iteration instead of `.cpu().numpy()` every env step -- `rewbuffer` / `lenbuffer` still hold
+the last 100 finished EPISODES in the reference's order (on_policy_runner.py:163-169) -- and checkpoints additionally
 carry the estimator, the auxiliary optimisers and `total_updates` (the reference silently drops them); the
 reference's keys ('model_state_dict', 'optimizer_state_dict', 'iter', 'infos') are unchanged.
 """
@@ -67,7 +68,11 @@ class OnPolicyRunner:
         self.env.reset()
         N = env.num_envs
         self._cur_rew, self._cur_len = torch.zeros(N, device=self.device), torch.zeros(N, device=self.device)
-        self._ep_stats = torch.zeros(3, device=self.device)      # finished episodes: sum reward, sum length, count
+        # finished episodes of one rollout, [T, N] with NaN where no episode ended: read back ONCE per iteration and appended
+        # to the 100-episode buffers in the reference's order (step-major, env-minor; on_policy_runner.py:163-169)
+        T = self.num_steps_per_env
+        self._fin_rew = torch.full((T, N), float("nan"), device=self.device)
+        self._fin_len = torch.full((T, N), float("nan"), device=self.device)
         self.rewbuffer, self.lenbuffer = deque(maxlen=100), deque(maxlen=100)
         self.last_losses = {}
 
@@ -148,13 +153,15 @@ class OnPolicyRunner:
                 env.bind_output_rows(rows[t + 1])
             obs, priv, crit, est, scan, rewards, dones, infos = env.step(actions)
             alg.process_env_step(rewards, dones, infos)
-            if self.log_dir is not None:
+            if self.log_dir is not None:               # book keeping of on_policy_runner.py:160-169, without its per-step read-back
                 self._cur_rew += rewards
                 self._cur_len += 1
-                d = dones.float()
-                self._ep_stats += torch.stack(((self._cur_rew * d).sum(), (self._cur_len * d).sum(), d.sum()))
-                self._cur_rew *= 1 - d
-                self._cur_len *= 1 - d
+                done = dones.bool()
+                nan = torch.full_like(self._cur_rew, float("nan"))
+                self._fin_rew[t] = torch.where(done, self._cur_rew, nan)
+                self._fin_len[t] = torch.where(done, self._cur_len, nan)
+                self._cur_rew.masked_fill_(done, 0.0)
+                self._cur_len.masked_fill_(done, 0.0)
         alg.compute_returns(crit)
 
     def iteration(self, it):
@@ -193,11 +200,10 @@ class OnPolicyRunner:
             self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
 
     def log(self, it, losses, dt):
-        srew, slen, cnt = self._ep_stats.tolist()
-        self._ep_stats.zero_()
-        if cnt > 0:
-            self.rewbuffer.append(srew / cnt)
-            self.lenbuffer.append(slen / cnt)
+        fin = torch.stack((self._fin_rew, self._fin_len)).cpu()      # the one read-back of the iteration's episode statistics
+        ended = ~torch.isnan(fin[0])
+        self.rewbuffer.extend(fin[0][ended].tolist())              # row-major = step-major, env-minor: the reference's order
+        self.lenbuffer.extend(fin[1][ended].tolist())
         fps = int(self.num_steps_per_env * self.env.num_envs / dt)
         if self.writer is not None:
             for k, v in losses.items():

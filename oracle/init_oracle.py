@@ -41,7 +41,15 @@ def init_randomisation(seed, num_envs, ip, terrain_origins=None):
     out["kp_kd_multipliers"] = np.stack([kpkd[:, :12], kpkd[:, 12:]]).astype(f32)
     if ip.num_init_levels > 0:
         levels = (px.keyed_u32(seed, SITE_INIT_LEVEL, 0, env, [0])[:, 0] % np.uint32(ip.num_init_levels)).astype(np.int64)
-        types = np.floor(env.astype(f32) / f32(N / ip.terrain_cols)).astype(np.int64)
+        # torch.div(arange(N), N / num_cols, rounding_mode='floor') (legged_robot.py:909) is fmod-based floor division in fp32
+        # (ATen div_floor_floating): (a - fmod(a, b)) / b, floored with a half-ulp guard -- not floor(a / b)
+        a, b = env.astype(f32), f32(N / ip.terrain_cols)
+        mod = np.fmod(a, b).astype(f32)
+        div = ((a - mod).astype(f32) / b).astype(f32)
+        div = np.where((mod != 0) & ((b < 0) != (mod < 0)), div - f32(1), div).astype(f32)
+        fl = np.floor(div).astype(f32)
+        fl = np.where(div - fl > f32(0.5), fl + f32(1), fl)
+        types = fl.astype(np.int64)
         out["terrain_levels"], out["terrain_types"] = levels, types
         out["env_origins"] = np.asarray(terrain_origins, f32)[levels, types]
     else:
