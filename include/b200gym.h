@@ -285,6 +285,27 @@ int b200_env_set_phase_trace(B200Env* env, unsigned long long* trace);
  * L2-resident between steps. */
 int b200_env_set_prefetch(B200Env* env, int on);
 
+/* Terrain construction on the device (init-time).
+ * b200_parkour_field: the parkour height field of Terrain.parkour_curriculum / parkour_selected_terrain (terrain.py:103-131,
+ * terrain_utils.py:318-399) -- `field` int16 [rows, cols] = tile_rows x tile_cols tiles of length_px x width_px cells inside a
+ * border; tile (i, j) is described by tiles[i * tile_cols + j] (device array): start platform, up to 16 obstacles in the
+ * reference's drawing order (rows [row_lo, row_hi) get `height` except columns < zero_below or >= zero_from, which get 0),
+ * side walls of `pad` cells at `border_height`.  The host builds the tables with the reference's rounding / slice semantics.
+ * b200_heightfield_to_trimesh: convert_heightfield_to_trimesh (terrain_utils.py:401-465) -- vertices float [rows * cols, 3],
+ * triangles uint32 [2 * (rows - 1) * (cols - 1), 3], with the slope-threshold correction when use_slope_threshold != 0. */
+#define B200_MAX_TILE_OBSTACLES 16
+typedef struct B200ParkourTile {
+  int32_t platform_rows, num_obstacles, pad;
+  int16_t platform_height, border_height;
+  int32_t row_lo[B200_MAX_TILE_OBSTACLES], row_hi[B200_MAX_TILE_OBSTACLES];
+  int32_t zero_below[B200_MAX_TILE_OBSTACLES], zero_from[B200_MAX_TILE_OBSTACLES];
+  int16_t height[B200_MAX_TILE_OBSTACLES];
+} B200ParkourTile;
+int b200_parkour_field(int16_t* field, int rows, int cols, int border, int length_px, int width_px, int tile_rows, int tile_cols,
+                       const B200ParkourTile* tiles /* device */, void* stream);
+int b200_heightfield_to_trimesh(const int16_t* height_field, int rows, int cols, double horizontal_scale, double vertical_scale,
+                                int use_slope_threshold, double slope_threshold, float* vertices, uint32_t* triangles, void* stream);
+
 /* Replaces LeggedRobot.step's action clip (legged_robot.py:74-75) + _compute_torques
  * (legged_robot.py:440-478).  `actions_in` [N,12] raw policy actions; when `clip_and_store`
  * != 0 they are clipped to +-clip_actions and stored into bufs->actions (first substep of an

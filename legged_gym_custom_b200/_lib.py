@@ -56,6 +56,9 @@ SYMBOLS = {
     "b200_elu_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p]),
     "b200_dist_adam": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_parkour_field": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
+    "b200_heightfield_to_trimesh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
     "b200_kl_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200_adaptive_lr": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
     "b200_adaptation_forward": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]),
@@ -67,6 +70,13 @@ SYMBOLS = {
 class CopySeg(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("src_ld", C.c_int32), ("dst_ld", C.c_int32),
                 ("_pad", C.c_int32)]
+
+
+class ParkourTile(C.Structure):
+    """B200ParkourTile (include/b200gym.h)"""
+    _fields_ = [("platform_rows", C.c_int32), ("num_obstacles", C.c_int32), ("pad", C.c_int32), ("platform_height", C.c_int16),
+                ("border_height", C.c_int16), ("row_lo", C.c_int32 * 16), ("row_hi", C.c_int32 * 16), ("zero_below", C.c_int32 * 16),
+                ("zero_from", C.c_int32 * 16), ("height", C.c_int16 * 16)]
 
 
 class DistAdamArgs(C.Structure):

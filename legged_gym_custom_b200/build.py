@@ -24,6 +24,7 @@ UNITS = [
     ("linear_kernels.cu", []),
     ("mlp_tcgen05.cu", []),
     ("dist_adam.cu", []),
+    ("terrain_kernels.cu", ["-fmad=false"]),
 ]
 
 

@@ -100,12 +100,13 @@ class Go2Env:
 
         hs = origins = None
         if cfg.terrain.mesh_type in ("heightfield", "trimesh"):
-            if height_samples is None:
-                if not getattr(cfg.terrain, "parkour", False):
-                    raise ValueError("non-parkour terrains: pass height_samples / terrain_origins (terrain generation "
-                                     "beyond the parkour layouts is out of scope, SURVEY.md §8(f1))")
-                height_samples, terrain_origins = terrain_mod.make_parkour_terrain(cfg.terrain)
-            hs, origins = np.asarray(height_samples, dtype=np.int16), np.asarray(terrain_origins, dtype=np.float32)
+            if height_samples is None:      # the layout the reference's Terrain would build: parkour, or the default curriculum
+                if getattr(cfg.terrain, "parkour", False):          # built on the device (csrc/terrain_kernels.cu)
+                    height_samples, terrain_origins = terrain_mod.make_parkour_terrain_gpu(cfg.terrain, self.device)
+                else:
+                    height_samples, terrain_origins = terrain_mod.make_terrain(cfg.terrain, seed)
+            hs = height_samples if isinstance(height_samples, torch.Tensor) else np.asarray(height_samples, dtype=np.int16)
+            origins = np.asarray(terrain_origins, dtype=np.float32)
         # alias_outputs (default): obs / privileged / estimated / scan observations are column slices of the critic rows
         # (identical values, go2.py:538-563) -- strided views instead of four more buffers; `bind_output_rows` lets a
         # runner point the rows at its rollout-storage slot.  Pass False for separate contiguous buffers.
@@ -147,7 +148,7 @@ class Go2Env:
     def _init_domain_randomisation(self, cfg, hs, origins, seed):
         b = self.bufs
         if hs is not None:
-            b["height_samples"].copy_(torch.from_numpy(hs))
+            b["height_samples"].copy_(hs if isinstance(hs, torch.Tensor) else torch.from_numpy(hs))
             b["terrain_origins"].copy_(torch.from_numpy(origins))
         self.init_params = init_params_from_cfg(cfg, self.num_envs, hs is not None)
         _lib.check(self.lib.b200_env_init_randomisation(self._handle, C.byref(b.struct), C.byref(self.init_params), _lib.stream_ptr()))

@@ -192,15 +192,19 @@ def test_go2env_api_smoke():
 
 
 def test_go2_rough_terrain_matches_oracle():
-    """BASELINE config 2: the `go2` task on a rough trimesh terrain with terrain curriculum and height measurements
-    (Go2Cfg + terrain.mesh_type='trimesh', curriculum=True; 10 x 20 tiles of 8 m -> height_samples [1300, 2100]).
-    The rough height field is synthetic (terrain generation beyond the parkour layouts is out of scope); base_height,
-    scan observations, curriculum levels and the bit-exact height indices are all exercised."""
+    """BASELINE config 2: the `go2` task on the reference's DEFAULT terrain curriculum (legged_robot_config.py:20-53:
+    trimesh, 10 x 20 tiles of 8 m, proportions [0.1, 0.1, 0.35, 0.25, 0.2]: smooth / rough slopes, stairs down / up,
+    discrete obstacles) at 4096 envs, built by legged_gym_custom_b200.terrain.make_curriculum_terrain (deterministic tiles
+    pinned to the reference's Terrain, tests/test_terrain_curriculum.py) -> height_samples [1300, 2100].  base_height, scan
+    observations, curriculum levels and the bit-exact height indices are all exercised."""
+    from legged_gym_custom_b200 import terrain as terrain_mod
+
     class RoughCfg(configs.Go2Cfg):
         class terrain(configs.Go2Cfg.terrain):
-            mesh_type, curriculum, measure_heights = "trimesh", True, True
+            mesh_type, curriculum, measure_heights, parkour = "trimesh", True, True, False
             num_rows, num_cols, terrain_length, terrain_width = 10, 20, 8., 8.
             max_init_terrain_level = 5
+            terrain_proportions = [0.1, 0.1, 0.35, 0.25, 0.2, 0.0, 0.0]
 
         class rewards(configs.Go2Cfg.rewards):
             class scales(configs.Go2Cfg.rewards.scales):
@@ -208,14 +212,9 @@ def test_go2_rough_terrain_matches_oracle():
                 stumble_feet = -1.0
                 feet_air_time = 1.0
     rng = np.random.default_rng(11)
-    rows, cols = 10 * 80 + 500, 20 * 80 + 500
-    hs = np.zeros((rows, cols), dtype=np.int16)
-    hs[250:-250, 250:-250] = (rng.integers(-12, 13, (rows - 500, cols - 500))).astype(np.int16)     # +-6 cm roughness
-    hs[400:420, :] = 60                                                                              # a 30 cm step across
-    origins = np.zeros((10, 20, 3), dtype=np.float32)
-    origins[..., 0] = (np.arange(10)[:, None] + 0.5) * 8.0
-    origins[..., 1] = (np.arange(20)[None, :] + 0.5) * 8.0
-    N = 2048
+    hs, origins = terrain_mod.make_terrain(RoughCfg.terrain, seed=21)
+    assert hs.shape == (10 * 80 + 500, 20 * 80 + 500) and hs.min() < -20 and hs.max() > 60
+    N = 4096
     p = env_params_from_cfg(RoughCfg, num_envs=N, seed=21, hs_shape=hs.shape)
     assert p.has_height_samples and p.curriculum and not p.parkour and p.reward_scales[gu.REWARD_INDEX["base_height"]] != 0
     statics = su.random_statics(p, rng, hs, origins)
