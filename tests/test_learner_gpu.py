@@ -204,7 +204,6 @@ def test_tcgen05_pair_pdl_switches_and_launch_trace():
     dev = torch.zeros(4, 2, dtype=torch.int64, device=DEV)
     dev[:, 0] = torch.iinfo(torch.int64).max
     meta = np.zeros((4, 4), dtype=np.int64)
-    import ctypes as C
     lib.b200_tc_set_trace(C.c_void_p(dev.data_ptr()), meta.ctypes.data_as(C.c_void_p), 4)
     try:
         for _ in range(2):
