@@ -288,12 +288,12 @@ int b200_env_set_prefetch(B200Env* env, int on);
 /* Terrain construction on the device (init-time).
  * b200_parkour_field: the parkour height field of Terrain.parkour_curriculum / parkour_selected_terrain (terrain.py:103-131,
  * terrain_utils.py:318-399) -- `field` int16 [rows, cols] = tile_rows x tile_cols tiles of length_px x width_px cells inside a
- * border; tile (i, j) is described by tiles[i * tile_cols + j] (device array): start platform, up to 16 obstacles in the
+ * border; tile (i, j) is described by tiles[i * tile_cols + j] (device array): start platform, up to 32 obstacles in the
  * reference's drawing order (rows [row_lo, row_hi) get `height` except columns < zero_below or >= zero_from, which get 0),
  * side walls of `pad` cells at `border_height`.  The host builds the tables with the reference's rounding / slice semantics.
  * b200_heightfield_to_trimesh: convert_heightfield_to_trimesh (terrain_utils.py:401-465) -- vertices float [rows * cols, 3],
  * triangles uint32 [2 * (rows - 1) * (cols - 1), 3], with the slope-threshold correction when use_slope_threshold != 0. */
-#define B200_MAX_TILE_OBSTACLES 16
+#define B200_MAX_TILE_OBSTACLES 32
 typedef struct B200ParkourTile {
   int32_t platform_rows, num_obstacles, pad;
   int16_t platform_height, border_height;

@@ -75,8 +75,8 @@ class CopySeg(C.Structure):
 class ParkourTile(C.Structure):
     """B200ParkourTile (include/b200gym.h)"""
     _fields_ = [("platform_rows", C.c_int32), ("num_obstacles", C.c_int32), ("pad", C.c_int32), ("platform_height", C.c_int16),
-                ("border_height", C.c_int16), ("row_lo", C.c_int32 * 16), ("row_hi", C.c_int32 * 16), ("zero_below", C.c_int32 * 16),
-                ("zero_from", C.c_int32 * 16), ("height", C.c_int16 * 16)]
+                ("border_height", C.c_int16), ("row_lo", C.c_int32 * 32), ("row_hi", C.c_int32 * 32), ("zero_below", C.c_int32 * 32),
+                ("zero_from", C.c_int32 * 32), ("height", C.c_int16 * 32)]
 
 
 class DistAdamArgs(C.Structure):

@@ -20,6 +20,8 @@
 // (cute/atom/mma_traits_sm100.hpp canonical layouts; instruction descriptor bits as cute::UMMA::InstrDescriptor).
 #include <cuda.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace {
@@ -564,14 +566,12 @@ int g_trace_cap = 0, g_trace_next = 0;
 // low-priority side streams): no process-wide switch to toggle around blocks of launches, nothing to restore after an
 // exception.  b200_tc_set_sm_cap (process-wide) remains for A/B tools.
 int g_sm_cap = 0;
-struct StreamCap { cudaStream_t stream; int cap; };
-StreamCap g_stream_caps[16];
-int g_num_stream_caps = 0;
+std::unordered_map<cudaStream_t, int> g_stream_caps;
 int avail_sms(cudaStream_t st) {
   const int n = num_sms();
   int cap = g_sm_cap;
-  for (int i = 0; i < g_num_stream_caps; ++i)
-    if (g_stream_caps[i].stream == st) cap = g_stream_caps[i].cap;
+  auto it = g_stream_caps.find(st);
+  if (it != g_stream_caps.end()) cap = it->second;
   return (cap > 0 && cap < n) ? cap : n;
 }
 
@@ -714,13 +714,8 @@ int b200_tc_set_sm_cap(int sms) {
 
 int b200_tc_set_stream_sm_cap(void* stream, int sms) {
   cudaStream_t st = (cudaStream_t)stream;
-  for (int i = 0; i < g_num_stream_caps; ++i)
-    if (g_stream_caps[i].stream == st) {
-      g_stream_caps[i].cap = sms > 0 ? sms : 0;
-      return 0;
-    }
-  B200_CHECK_ARG(g_num_stream_caps < 16, "b200_tc_set_stream_sm_cap: more than 16 capped streams");
-  g_stream_caps[g_num_stream_caps++] = StreamCap{st, sms > 0 ? sms : 0};
+  if (sms > 0) g_stream_caps[st] = sms;
+  else g_stream_caps.erase(st);
   return 0;
 }
 

@@ -218,7 +218,6 @@ class PPO:
         # path whatever the stream priorities are (b200_tc_set_sm_cap).  Measured on B200 (148 SMs), update of 20 minibatches:
         # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt)
         self.side_sm_cap = 116
-        self._stream_caps = {}               # cuda stream -> cap registered with the library
         # weight-gradient GEMMs of the actor / encoder chains on a fifth (low-priority, capped) stream: the dgrad chain that
         # the encoders' backward waits for no longer queues behind them
         self.offload_wgrads = False
@@ -531,9 +530,12 @@ class PPO:
         encoder (rollout), critic"""
         if not self.use_streams:
             return [None] * n
-        if not hasattr(self, "_side"):
-            lo, hi = 0, -1
-            self._side = [torch.cuda.Stream(device=self.device, priority=p) for p in (hi, hi, lo, lo, lo)]
+        if not hasattr(self, "_side"):        # one pool per device for the whole process, however many PPO objects exist
+            key = torch.device(self.device).index or 0
+            if key not in _SIDE_STREAMS:
+                lo, hi = 0, -1
+                _SIDE_STREAMS[key] = [torch.cuda.Stream(device=self.device, priority=p) for p in (hi, hi, lo, lo, lo)]
+            self._side = _SIDE_STREAMS[key]
         self._fork_onto(self._side[:n])
         return self._side[:n]
 
@@ -569,9 +571,9 @@ class PPO:
         """`_on(stream)` for a LOW-priority chain of the update.  Its GEMM launches are sized for `side_sm_cap` SMs: the cap is
         a property of the stream inside the library (b200_tc_set_stream_sm_cap), (re)registered here whenever it changed."""
         cap = self.side_sm_cap if (self.use_streams and stream is not None) else 0
-        if stream is not None and self._stream_caps.get(stream.cuda_stream) != cap:
+        if stream is not None and _REGISTERED_CAPS.get(stream.cuda_stream) != cap:
             _lib.check(self.lib.b200_tc_set_stream_sm_cap(C.c_void_p(stream.cuda_stream), int(cap or 0)))
-            self._stream_caps[stream.cuda_stream] = cap
+            _REGISTERED_CAPS[stream.cuda_stream] = cap
         return self._on(stream)
 
     def _join_onto(self, stream, streams):
@@ -673,6 +675,10 @@ class PPO:
 
 def _p_i64(t):
     return C.c_void_p(t.data_ptr())
+
+
+_SIDE_STREAMS = {}      # device index -> [critical, scan, estimator / latent, critic, wgrad offload] streams
+_REGISTERED_CAPS = {}   # cuda stream -> SM cap registered with the library (b200_tc_set_stream_sm_cap)
 
 
 def _rows16(t, need16=True):

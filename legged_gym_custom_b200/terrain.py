@@ -261,8 +261,8 @@ def _tile_table(length_px, width_px, h_scale, v_scale, start_platform_length, st
     t.platform_rows = min(length_px, max(0, round(start_platform_length / h_scale)))
     t.platform_height = round(start_platform_height / v_scale)
     mid, half_gap = width_px // 2, round(half_valid_width / h_scale)
-    if len(x_positions) > 16:
-        raise ValueError("more than 16 obstacles per tile")
+    if len(x_positions) > 32:
+        raise ValueError("more than 32 obstacles per tile")
     t.num_obstacles = len(x_positions)
     for k, (x, y, length, height) in enumerate(zip(x_positions, y_positions, obstacle_lengths, obstacle_heights)):
         cx, cy = round(x / h_scale), mid + round(y / h_scale)
