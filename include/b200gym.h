@@ -398,6 +398,9 @@ int b200_tc_set_stream_sm_cap(void* stream, int sms);
  * CTA pairs for the large forward problems; 0 (default): by shape -- outputs up to 256 columns wide take 2, wider ones 1.
  * Host-side state, read at launch time (A/B switch). */
 int b200_tc_set_ctas_per_sm(int n);
+/* != 0 (default): the dgrad kernels move their epilogue tiles by TMA (stored activation in, dX out, 128-byte-swizzled 32 x 32
+ * boxes) wherever the operands allow it; 0: the staging-tile epilogue everywhere (A/B switch). */
+int b200_tc_set_tma_epilogue(int on);
 /* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
  * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */
 int b200_tc_linear_supported(int M, int N, int K);

@@ -63,6 +63,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// shared -> global tile store (bulk async-group of the issuing thread); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -187,7 +197,11 @@ struct TcArgs {
 // A-operand smem per stage: K-major  [BM rows][32]         = 16 KB
 //                           MN-major 4 chunks x [32 k][32]  = 16 KB   (chunk = 32 fp32 of the M dimension)
 // B-operand smem per stage: K-major  [BN rows][32]; MN-major (BN/32) chunks x [32 k][32]      = BN * 128 B
-template <int BN, bool PAIR, int CPS = 1>
+// EPI (dgrad only): the epilogue moves its tiles by TMA -- the stored activation (for elu') arrives in shared memory as
+// 128-byte-swizzled 32 x 32 boxes on per-warp mbarriers, the result leaves as the same kind of box (cp.async.bulk.tensor
+// store): no per-lane global loads / stores, no staging round trip.  Costs 12 KB of shared memory per epilogue warp.
+constexpr uint32_t kEpiBytesPerWarp = 3 * 4096;      // aux double buffer + one output tile
+template <int BN, bool PAIR, int CPS = 1, bool EPI = false>
 struct TileCfg {
   static constexpr int BNH = PAIR ? BN / 2 : BN;                  // rows of B this CTA stages
   static constexpr int BMT = PAIR ? 2 * BM : BM;                  // rows of the output tile (pair: 256)
@@ -195,15 +209,17 @@ struct TileCfg {
   // shared-memory budget of the operand ring: what is left of 227 KB after the epilogue's staging tiles (36 KB), the
   // dgrad's column-sum buffer (<= 8 KB) and the barriers
   // (CPS = 2: two CTAs share the SM -- one's epilogue runs under the other's main loop -- with half the ring each)
-  static constexpr uint32_t RING_BYTES = CPS == 2 ? 70u * 1024u : 176u * 1024u;
+  static constexpr uint32_t RING_BYTES = CPS == 2 ? 70u * 1024u : (EPI ? 116u * 1024u : 176u * 1024u);
   static constexpr int STAGES_ = (int)(RING_BYTES / STAGE_BYTES) < 8 ? (int)(RING_BYTES / STAGE_BYTES) : 8;
   static_assert(STAGES_ >= 2, "operand ring needs at least two stages");
 };
 
-template <int MODE, int BN, bool PAIR, int CPS = 1>
+template <int MODE, int BN, bool PAIR, int CPS = 1, bool EPI = false>
 __global__ void __launch_bounds__(NUM_THREADS, CPS)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
-  using Cfg = TileCfg<BN, PAIR, CPS>;
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g,
+               const __grid_constant__ CUtensorMap tmap_aux, const __grid_constant__ CUtensorMap tmap_out) {
+  using Cfg = TileCfg<BN, PAIR, CPS, EPI>;
+  static_assert(!EPI || (MODE == NN && CPS == 1), "the TMA epilogue exists for the dgrad, one CTA (or CTA pair) per SM");
   constexpr bool A_MN = (MODE == TN), B_MN = (MODE != NT);
   constexpr int BNH = Cfg::BNH, BMT = Cfg::BMT, STAGES = Cfg::STAGES_;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -219,9 +235,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // NN + dbias: [2 tiles][4 quarters][BN]
+  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 256);   // EPI: [8 epilogue warps][2]
+  float* red = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512);   // NN + dbias: [2 tiles][4 quarters][BN]
   constexpr int STG_PITCH = 36;                                                // floats per staged row (32 + 4 pad)
   float* stage = red + (MODE == NN ? 2 * 4 * BN : 0);                          // [8 epilogue warps][32 rows][STG_PITCH]
+  // EPI: [8 epilogue warps][aux 0 | aux 1 | out], 1024-byte aligned (128-byte swizzle atoms) -- takes the staging tiles' place
+  uint8_t* epi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage) + 1023) & ~(uintptr_t)1023);
 
   // Programmatic dependent launch: let the NEXT kernel of the stream start launching now (its CTAs land on each SM as ours
   // leave and run their prologue there); our own reads / writes of global memory wait below until the PREVIOUS kernel of
@@ -252,6 +271,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + a, 1);
       mbar_init(tmem_empty + a, PAIR ? 16 : 8);      // one arrive per epilogue warp (pair: of both CTAs, on the leader)
+    }
+    if (EPI) {
+      prefetch_tmap(&tmap_aux);
+      prefetch_tmap(&tmap_out);
+      for (int a = 0; a < 16; ++a) mbar_init(aux_bar + a, 1);
     }
     fence_barrier_init();
   }
@@ -338,6 +362,88 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // instruction.  The dgrad's elu' input travels the other way (coalesced load -> staging -> row per lane).
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
+    if constexpr (EPI) {
+      // ---- TMA epilogue (dgrad): per 32 x 32 chunk -- aux box (prefetched one chunk ahead) -> row per lane from the swizzled
+      // tile, x accumulator row from TMEM, x elu', -> swizzled output tile -> one TMA store; column sums from the output tile.
+      // Box element (r, c) of a SWIZZLE_128B tile lives at r * 128 + ((c / 4) ^ (r & 7)) * 16 + (c % 4) * 4.
+      uint8_t* ebuf = epi + (size_t)(warp - 2) * kEpiBytesPerWarp;
+      uint8_t* obuf = ebuf + 2 * 4096;
+      uint64_t* abar = aux_bar + (warp - 2) * 2;
+      const bool has_aux = g.aux != nullptr;
+      uint32_t q = 0;                                          // chunks this warp has consumed: buffer q & 1, parity (q >> 1) & 1
+      uint32_t local_tile = 0;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_tile) {
+        const uint32_t acc = local_tile & 1, acc_ph = (local_tile >> 1) & 1;
+        const int m0 = (tile / n_tiles) * BMT + (int)rank * BM, n0 = (tile % n_tiles) * BN;      // pair: this CTA's 128 rows
+        const int row0 = m0 + quarter * 32;
+        const int ci_lo = half * CH_PER_HALF, ci_hi = min(CHUNKS, (half + 1) * CH_PER_HALF);
+        auto issue_aux = [&](int ci, uint32_t qq) {
+          if (has_aux && lane == 0) {
+            mbar_expect_tx(abar + (qq & 1), 4096);
+            tma_load_2d(ebuf + (qq & 1) * 4096, &tmap_aux, abar + (qq & 1), n0 + ci * 32, row0);
+          }
+        };
+        if (ci_lo < ci_hi) issue_aux(ci_lo, q);                 // before the accumulator is even complete
+        mbar_wait(tmem_full + acc, acc_ph);
+        tc_fence_after();
+        const bool want_colsum = g.dbias != nullptr;
+        float* red_tile = red + (local_tile & 1) * 4 * BN + quarter * BN;
+#pragma unroll 1
+        for (int ci = ci_lo; ci < ci_hi; ++ci, ++q) {
+          const int c = ci * 32;
+          if (ci + 1 < ci_hi) issue_aux(ci + 1, q + 1);         // the other buffer: its last reader was chunk q - 1
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
+          if (has_aux) {
+            mbar_wait(abar + (q & 1), (q >> 1) & 1);
+            const uint8_t* arow = ebuf + (q & 1) * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 y4 = *reinterpret_cast<const float4*>(arow + (((uint32_t)j ^ sw) << 4));
+              v[4 * j] *= (y4.x > 0.0f ? 1.0f : y4.x + 1.0f);      // elu'(y) from the stored y (zero-filled rows / columns: x 1)
+              v[4 * j + 1] *= (y4.y > 0.0f ? 1.0f : y4.y + 1.0f);
+              v[4 * j + 2] *= (y4.z > 0.0f ? 1.0f : y4.z + 1.0f);
+              v[4 * j + 3] *= (y4.w > 0.0f ? 1.0f : y4.w + 1.0f);
+            }
+          }
+          if (lane == 0) bulk_wait_read0();                     // the previous chunk's store has read the output tile
+          __syncwarp();
+          uint8_t* orow = obuf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(orow + (((uint32_t)j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && n0 + c < g.N && row0 < g.M) {
+            tma_store_2d(&tmap_out, obuf, n0 + c, row0);
+            bulk_commit();
+          }
+          if (want_colsum) {                                    // column `lane` of the tile (rows past M carry zeros)
+            float cs = 0.0f;
+            const uint32_t cchunk = (uint32_t)lane >> 2, cw = ((uint32_t)lane & 3) << 2;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) cs += *reinterpret_cast<const float*>(obuf + r * 128 + ((cchunk ^ (uint32_t)(r & 7)) << 4) + cw);
+            red_tile[c + lane] = cs;
+          }
+        }
+        if (want_colsum) {
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          const int tcol = (int)threadIdx.x - 64;
+          if (tcol < BN && n0 + tcol < g.N) {
+            const float* r = red + (local_tile & 1) * 4 * BN + tcol;
+            atomicAdd(g.dbias + n0 + tcol, (r[0] + r[BN]) + (r[2 * BN] + r[3 * BN]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(tmem_empty + acc);
+          else mbar_arrive(tmem_empty + acc);
+        }
+      }
+      if (lane == 0) bulk_wait_all();                           // every store of this warp is complete before the CTA retires
+    } else {
     float* stg = stage + (warp - 2) * (32 * STG_PITCH);
     const int sr = lane >> 3, sc = (lane & 7) * 4;            // staging coordinates of this lane in the "8 lanes per row" view
     uint32_t local_tile = 0;
@@ -488,6 +594,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         else mbar_arrive(tmem_empty + acc);
       }
     }
+    }      // !EPI
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all();          // nobody leaves while its partner can still signal its barriers / read its smem
@@ -580,15 +687,18 @@ int avail_sms(cudaStream_t st) {
 // 256-wide tiles / CTA pairs (512 x 627: 43.5 us against 62.9 us with two CTAs); 1 / 2 force either (A/B runs)
 int g_cps = 0;
 int cps_for(int cols) { return g_cps == 0 ? (cols <= 256 ? 2 : 1) : g_cps; }
+int g_tma_epi = 1;        // b200_tc_set_tma_epilogue: dgrad tiles >= 64 wide move their epilogue tiles by TMA (0: legacy staging path)
 int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
 
-template <int MODE, int BN, bool PAIR = false, int CPS = 1>
-int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int splits, cudaStream_t st, const char* name) {
-  using Cfg = TileCfg<BN, PAIR, CPS>;
+template <int MODE, int BN, bool PAIR = false, int CPS = 1, bool EPI = false>
+int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int splits, cudaStream_t st, const char* name,
+              const CUtensorMap* taux = nullptr, const CUtensorMap* tout = nullptr) {
+  using Cfg = TileCfg<BN, PAIR, CPS, EPI>;
   static_assert(CPS == 1 || (!PAIR && 2 * BN <= 256), "two CTAs per SM: 2 x 256 TMEM columns, no CTA pairs");
-  constexpr int smem = Cfg::STAGES_ * (int)Cfg::STAGE_BYTES + 256 + (MODE == NN ? 2 * 4 * BN * 4 : 0) + 8 * 32 * 36 * 4 + 1024;
+  constexpr int smem = Cfg::STAGES_ * (int)Cfg::STAGE_BYTES + 512 + (MODE == NN ? 2 * 4 * BN * 4 : 0) +
+                       (EPI ? 8 * (int)kEpiBytesPerWarp + 1024 : 8 * 32 * 36 * 4) + 1024;
   static_assert(smem <= 227 * 1024, "tile configuration does not fit shared memory");
-  auto kern = tc_gemm_kernel<MODE, BN, PAIR, CPS>;
+  auto kern = tc_gemm_kernel<MODE, BN, PAIR, CPS, EPI>;
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -633,7 +743,7 @@ int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, gt);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, gt, taux ? *taux : ta, tout ? *tout : ta);
   if (e != cudaSuccess) {
     b200_set_error("%s: cudaLaunchKernelEx: %s", name, cudaGetErrorString(e));
     return (int)e;
@@ -724,6 +834,11 @@ int b200_tc_set_ctas_per_sm(int n) {
   return 0;
 }
 
+int b200_tc_set_tma_epilogue(int on) {
+  g_tma_epi = on ? 1 : 0;
+  return 0;
+}
+
 int b200_tc_set_pair_mode(int on) {
   g_pair_mode = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 forward only (default), 2 forward + dgrad
   return 0;
@@ -788,6 +903,31 @@ int b200_tc_linear_dgrad_bias(const float* dY, int lddy, const float* W, int ldw
   TcArgs g{};
   g.C = dX; g.aux = Yprev; g.ldc = lddx; g.ldaux = ldyp; g.M = M; g.N = K; g.K = N; g.accumulate = accumulate; g.dbias = dbias_prev;
   cudaStream_t st = (cudaStream_t)stream;
+  // TMA epilogue: whole 32 x 32 boxes of the stored activation in, of dX out (needs 16-byte rows on both, no accumulate).
+  // Measured on B200 at M = 24576 (with the fused bias gradient): 256 -> 512: 40.8 -> 33.2 us, 128 -> 256: 16.9 -> 14.9 us; not
+  // for long reductions (N = 512: the epilogue buffers cost ring stages, 59.7 -> 64.7 us) and not for small M (two more
+  // tensor maps to encode per launch).
+  if (g_tma_epi && !accumulate && K >= 64 && N <= 256 && M >= 2048 && lddx % 4 == 0 && aligned16(dX) &&
+      (!Yprev || (ldyp % 4 == 0 && aligned16(Yprev)))) {
+    CUtensorMap taux, tout;
+    if (int rc = make_tmap(&tout, dX, M, K, lddx, 32, 0)) return rc;
+    if (Yprev) {
+      if (int rc = make_tmap(&taux, Yprev, M, K, ldyp, 32, 0)) return rc;
+    } else {
+      taux = tout;
+    }
+    // CTA pairs (each CTA stages half of W) measured no better with this epilogue either (256 -> 512: 33.3 us both ways,
+    // 128 -> 256: 14.8 -> 17.0 us): only when forced (pair mode 2, A/B runs)
+    const int epbn = g_pair_mode == 2 ? pick_pair_bn(M, K) : 0;
+    if (epbn == 256) return launch_tc<NN, 256, true, 1, true>(ta, tb, g, 1, st, "tc_dgrad_tma_pair<256>", &taux, &tout);
+    if (epbn == 128) return launch_tc<NN, 128, true, 1, true>(ta, tb, g, 1, st, "tc_dgrad_tma_pair<128>", &taux, &tout);
+    const int ebn = pick_bn(M, K) >= 128 ? pick_bn(M, K) : 64;
+    switch (ebn) {
+      case 256: return launch_tc<NN, 256, false, 1, true>(ta, tb, g, 1, st, "tc_dgrad_tma<256>", &taux, &tout);
+      case 128: return launch_tc<NN, 128, false, 1, true>(ta, tb, g, 1, st, "tc_dgrad_tma<128>", &taux, &tout);
+      default: return launch_tc<NN, 64, false, 1, true>(ta, tb, g, 1, st, "tc_dgrad_tma<64>", &taux, &tout);
+    }
+  }
   switch (pbn) {
     case 256: return launch_tc<NN, 256, true>(ta, tb, g, 1, st, "tc_dgrad_pair<256>");
     case 128: return launch_tc<NN, 128, true>(ta, tb, g, 1, st, "tc_dgrad_pair<128>");

@@ -185,8 +185,9 @@ def test_tcgen05_pair_pdl_switches_and_launch_trace():
     side = torch.cuda.Stream()
     res = []
     try:
-        for cps, cap in ((1, 0), (2, 0), (0, 0), (0, 100)):
+        for cps, cap, epi in ((1, 0, 1), (2, 0, 1), (0, 0, 1), (0, 100, 1), (0, 0, 0), (2, 0, 0)):
             lib.b200_tc_set_ctas_per_sm(cps)
+            lib.b200_tc_set_tma_epilogue(epi)
             _lib.check(lib.b200_tc_set_stream_sm_cap(C.c_void_p(side.cuda_stream), cap))
             Y2, dX2 = torch.zeros(M2, N2, device=DEV), torch.zeros(M2, K2, device=DEV)
             torch.cuda.synchronize()
@@ -198,6 +199,7 @@ def test_tcgen05_pair_pdl_switches_and_launch_trace():
             res.append((Y2, dX2))
     finally:
         lib.b200_tc_set_ctas_per_sm(0)
+        lib.b200_tc_set_tma_epilogue(1)
         lib.b200_tc_set_stream_sm_cap(C.c_void_p(side.cuda_stream), 0)
     for Y2, dX2 in res[1:]:
         assert torch.equal(Y2, res[0][0]) and torch.equal(dX2, res[0][1])

@@ -12,6 +12,8 @@ if os.environ.get("B200_PAIR") is not None:
     lib.b200_tc_set_pair_mode(int(os.environ["B200_PAIR"]))
 if os.environ.get("B200_CPS") is not None:
     lib.b200_tc_set_ctas_per_sm(int(os.environ["B200_CPS"]))
+if os.environ.get("B200_TMA_EPI") is not None:
+    lib.b200_tc_set_tma_epilogue(int(os.environ["B200_TMA_EPI"]))
 DEV = "cuda:0"
 ld = lambda k: (k + 3) // 4 * 4
 p = lambda t: t.data_ptr()
