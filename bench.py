@@ -109,7 +109,7 @@ class Profile:
     def hook(self, name, raw, args):
         from legged_gym_custom_b200 import _lib
         if name in ("b200_last_error", "b200_gae_scratch_bytes", "b200_env_create", "b200_env_destroy", "b200_abi_version",
-                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_tc_set_sm_cap", "b200_tc_set_ctas_per_sm", "b200_tc_set_stream_sm_cap", "b200_tc_set_tma_epilogue", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
+                    "b200_tc_set_pair_mode", "b200_tc_set_pdl", "b200_tc_set_sm_cap", "b200_tc_set_ctas_per_sm", "b200_tc_set_stream_sm_cap", "b200_tc_set_tma_epilogue", "b200_tc_set_wgrad_pairs", "b200_env_set_phase_trace", "b200_env_force_generic_layout", "b200_env_set_prefetch", "b200_tc_linear_supported"):
             return raw(*args)
         self.count += _lib.LAUNCHES.get(name, 1)
         self.by_entry[name] = self.by_entry.get(name, 0) + _lib.LAUNCHES.get(name, 1)
@@ -229,6 +229,8 @@ def run_b200(args):
         _lib.lib().b200_tc_set_pdl(1)
     if args.ctas_per_sm is not None:
         _lib.lib().b200_tc_set_ctas_per_sm(args.ctas_per_sm)
+    if args.wgrad_pairs is not None:
+        _lib.lib().b200_tc_set_wgrad_pairs(args.wgrad_pairs)
     if args.tma_epilogue is not None:
         _lib.lib().b200_tc_set_tma_epilogue(args.tma_epilogue)
     prof = Profile(args.num_envs)
@@ -619,6 +621,7 @@ def main():
     ap.add_argument("--offload-wgrads", type=int, default=None, help="actor / encoder weight-gradient GEMMs on their own low-priority stream (A/B)")
     ap.add_argument("--ctas-per-sm", type=int, default=None, help="tcgen05 forward / dgrad: 2 = two persistent CTAs per SM on <= 128-wide tiles (A/B)")
     ap.add_argument("--tma-epilogue", type=int, default=None, help="dgrad epilogue tiles by TMA (1, default) or through the staging tiles (0) (A/B)")
+    ap.add_argument("--wgrad-pairs", type=int, default=None, help="weight gradients on CTA pairs (A/B)")
     ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":

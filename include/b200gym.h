@@ -401,6 +401,9 @@ int b200_tc_set_ctas_per_sm(int n);
 /* != 0 (default): the dgrad kernels move their epilogue tiles by TMA (stored activation in, dX out, 128-byte-swizzled 32 x 32
  * boxes) wherever the operands allow it; 0: the staging-tile epilogue everywhere (A/B switch). */
 int b200_tc_set_tma_epilogue(int on);
+/* != 0: weight gradients with >= 256 output rows run on CTA pairs (cta_group::2, 256-row UMMA: X is staged once per pair);
+ * (default); 0: single CTAs (A/B switch).  Measured on B200, M = 24576: 512 x 627 49.7 -> 43.9 us, 512 x 736 45.4 -> 37.9 us. */
+int b200_tc_set_wgrad_pairs(int on);
 /* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
  * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */
 int b200_tc_linear_supported(int M, int N, int K);

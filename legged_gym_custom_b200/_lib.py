@@ -37,6 +37,7 @@ SYMBOLS = {
     "b200_tc_set_sm_cap": (C.c_int, [C.c_int]),
     "b200_tc_set_ctas_per_sm": (C.c_int, [C.c_int]),
     "b200_tc_set_tma_epilogue": (C.c_int, [C.c_int]),
+    "b200_tc_set_wgrad_pairs": (C.c_int, [C.c_int]),
     "b200_tc_set_stream_sm_cap": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_tc_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "b200_tc_linear_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),

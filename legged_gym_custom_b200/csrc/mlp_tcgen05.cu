@@ -687,6 +687,7 @@ int avail_sms(cudaStream_t st) {
 // 256-wide tiles / CTA pairs (512 x 627: 43.5 us against 62.9 us with two CTAs); 1 / 2 force either (A/B runs)
 int g_cps = 0;
 int cps_for(int cols) { return g_cps == 0 ? (cols <= 256 ? 2 : 1) : g_cps; }
+int g_wgrad_pairs = 1;    // b200_tc_set_wgrad_pairs: weight gradients with >= 256 output rows on CTA pairs (256-row UMMA, X staged once per pair)
 int g_tma_epi = 1;        // b200_tc_set_tma_epilogue: dgrad tiles >= 64 wide move their epilogue tiles by TMA (0: legacy staging path)
 int g_pdl = 0;            // b200_tc_set_pdl: programmatic dependent launch of the tcgen05 GEMMs (measured: no gain)
 
@@ -834,6 +835,11 @@ int b200_tc_set_ctas_per_sm(int n) {
   return 0;
 }
 
+int b200_tc_set_wgrad_pairs(int on) {
+  g_wgrad_pairs = on ? 1 : 0;
+  return 0;
+}
+
 int b200_tc_set_tma_epilogue(int on) {
   g_tma_epi = on ? 1 : 0;
   return 0;
@@ -959,8 +965,9 @@ int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, flo
   if (int rc = make_tmap(&tb, X, M, K, ldx, BK, 1)) return rc;            // B MN-major: box [32 m][32 k]
   TcArgs g{};
   g.C = dW; g.ldc = ldw; g.M = N; g.N = K; g.K = M;
-  const int tiles = ((N + BM - 1) / BM) * ((K + bn - 1) / bn);
-  int splits = avail_sms((cudaStream_t)stream) / (tiles < 1 ? 1 : tiles);
+  const bool pair = g_wgrad_pairs && N >= 2 * BM && bn >= 64;
+  const int tiles = ((N + (pair ? 2 : 1) * BM - 1) / ((pair ? 2 : 1) * BM)) * ((K + bn - 1) / bn);
+  int splits = (avail_sms((cudaStream_t)stream) / (pair ? 2 : 1)) / (tiles < 1 ? 1 : tiles);
   const int max_splits = (M + 8 * BK - 1) / (8 * BK);
   splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
   int per = (M + splits - 1) / splits;
@@ -968,6 +975,11 @@ int b200_tc_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, flo
   g.k_per_split = per;
   splits = (M + per - 1) / per;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pair) switch (bn) {
+      case 256: return launch_tc<TN, 256, true>(ta, tb, g, splits, st, "tc_wgrad_pair<256>");
+      case 128: return launch_tc<TN, 128, true>(ta, tb, g, splits, st, "tc_wgrad_pair<128>");
+      default: return launch_tc<TN, 64, true>(ta, tb, g, splits, st, "tc_wgrad_pair<64>");
+    }
   switch (bn) {
     case 256: return launch_tc<TN, 256>(ta, tb, g, splits, st, "tc_wgrad<256>");
     case 128: return launch_tc<TN, 128>(ta, tb, g, splits, st, "tc_wgrad<128>");

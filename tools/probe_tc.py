@@ -14,6 +14,8 @@ if os.environ.get("B200_CPS") is not None:
     lib.b200_tc_set_ctas_per_sm(int(os.environ["B200_CPS"]))
 if os.environ.get("B200_TMA_EPI") is not None:
     lib.b200_tc_set_tma_epilogue(int(os.environ["B200_TMA_EPI"]))
+if os.environ.get("B200_WGRAD_PAIRS") is not None:
+    lib.b200_tc_set_wgrad_pairs(int(os.environ["B200_WGRAD_PAIRS"]))
 DEV = "cuda:0"
 ld = lambda k: (k + 3) // 4 * 4
 p = lambda t: t.data_ptr()

@@ -19,9 +19,9 @@ for n in sizes:
     k = d["kernels"].get("b200_post_physics_step_dev") or d["kernels"].get("b200_post_physics_step") or {}
     re_ = d.get("roofline_env") or {}
     rows.append({"num_envs": n, "env_steps_per_s": d["value"], "ms_per_iteration": d["ms_per_step"], "split": d["split"],
-                 "post_physics": {"l2_flushed_us": re_.get("avg_us"), "frac_of_hbm_peak_l2_flushed": re_.get("frac"),
-                                  "device_span_us": (re_.get("device_span") or {}).get("us"),
-                                  "frac_of_hbm_peak_device_span": (re_.get("device_span") or {}).get("frac")},
+                 "post_physics": {"kernel": re_.get("kernel"), "inputs_larger_than_l2_us": re_.get("avg_us"), "frac_of_hbm_peak": re_.get("frac"),
+                                  "l2_resident_graph": re_.get("l2_resident_graph"), "l2_flushed_single_launch": re_.get("l2_flushed_single_launch"),
+                                  "device_span": re_.get("device_span")},
                  "roofline": d["roofline"]})
     print(json.dumps(rows[-1]), flush=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "sweep_envs.json"), "w"), indent=1)
