@@ -169,7 +169,7 @@ def build_runner(args, rank, world, device, host_physx=False):
         class env(env_cfg.env):
             num_envs = args.num_envs
     pg = torch.distributed.group.WORLD if world > 1 else None
-    env = Go2Env(Cfg, sim_device=str(device), seed=1234 + rank)
+    env = Go2Env(Cfg, sim_device=str(device), seed=1234 + rank, terrain_tiles=bool(args.terrain_tiles))
     if host_physx:
         env.physx = HostPhysX(args.num_envs, env.bufs["env_origins"], device, seed=1234 + rank, decimation=env.params.decimation)
     tc = class_to_dict(train_cfg)
@@ -360,7 +360,7 @@ def run_b200(args):
             class Cfg(env_cfg):
                 class env(env_cfg.env):
                     num_envs = N
-            envs = [env] + [Go2Env(Cfg, sim_device=str(device), seed=4321 + i) for i in range(sets - 1)]
+            envs = [env] + [Go2Env(Cfg, sim_device=str(device), seed=4321 + i, terrain_tiles=bool(args.terrain_tiles)) for i in range(sets - 1)]
             for e_ in envs[1:]:
                 e_.reset()
                 e_.episode_length_buf = torch.randint_like(e_.episode_length_buf, high=int(e_.max_episode_length))
@@ -624,6 +624,7 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=None, help="tcgen05 forward / dgrad: 2 = two persistent CTAs per SM on <= 128-wide tiles (A/B)")
     ap.add_argument("--tma-epilogue", type=int, default=None, help="dgrad epilogue tiles by TMA (1, default) or through the staging tiles (0) (A/B)")
     ap.add_argument("--wgrad-pairs", type=int, default=None, help="weight gradients on CTA pairs (A/B)")
+    ap.add_argument("--terrain-tiles", type=int, default=0, help="env kernel: height scan from a TMA-staged shared-memory terrain tile (A/B)")
     ap.add_argument("--no-pairs", action="store_true", help="single-CTA tcgen05 GEMMs only (A/B against the cta_group::2 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":

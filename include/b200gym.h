@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 #define B200_NUM_DOF 12          /* go2 family: {FL,FR,RL,RR}_{hip,thigh,calf}_joint */
 #define B200_NUM_BODIES 19       /* base, Head_upper, Head_lower, 4 x {hip,thigh,calf,foot} */
 #define B200_NUM_FEET 4          /* FL, FR, RL, RR (reference order, go2.py:295-298) */
@@ -174,6 +174,13 @@ typedef struct B200EnvParams {
   double cc_range0[2];                 /* cfg.commands.ranges.lin_vel_x as doubles: initial content of command_ranges */
   float cc_threshold;                  /* fp32(0.8 * reward_scales[tracking_lin_vel]) -- the fp32 tensor comparison of go2.py:91 */
   int32_t command_curriculum;
+  /* height_samples row pitch in ELEMENTS (>= hs_cols).  A multiple of 8 (16 bytes) lets the tile kernel fetch an env's scan
+   * neighbourhood as ONE 2-D TMA box; 0 means hs_cols. */
+  int32_t hs_pitch;
+  /* != 0 (needs hs_pitch % 8 == 0, the go2 layout and alias_outputs): the height scan stages the env's terrain tile -- the
+   * 32 x 32 int16 cells around its scan points, one TMA box -- in shared memory and reads the 132 x 3 cells from there
+   * (north_star design choice 2) instead of gathering them from the L2-resident field. */
+  int32_t terrain_tiles;
 } B200EnvParams;
 
 /* Device buffers of one env shard.  "PhysX" = written by the simulator each step and only
@@ -191,7 +198,7 @@ typedef struct B200EnvBuffers {
   const float* priv_mass_params;     /* [N,4] */
   const float* priv_friction;        /* [N,1] */
   /* terrain */
-  const int16_t* height_samples;     /* [hs_rows,hs_cols] or NULL */
+  const int16_t* height_samples;     /* [hs_rows,hs_cols] with row pitch params.hs_pitch, or NULL */
   const float* terrain_origins;      /* [max_terrain_level,terrain_cols,3] or NULL */
   /* own persistent state */
   float* actions;                /* [N,12] clipped actions of this step (written by b200_pd_torques) */

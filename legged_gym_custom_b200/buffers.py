@@ -51,6 +51,9 @@ class BufferSet:
             if name == "height_index" and record_height_index:
                 spec = ((p.num_envs, p.num_scan, 2), torch.int64)
             self.t[name] = None if spec is None else torch.zeros(spec[0], dtype=spec[1], device=self.device)
+        if self.t["height_samples"] is not None and p.hs_pitch > p.hs_cols:      # rows padded to params.hs_pitch elements
+            self._hs_storage = torch.zeros(p.hs_rows, p.hs_pitch, dtype=torch.int16, device=self.device)
+            self.t["height_samples"] = self._hs_storage[:, :p.hs_cols]
         self.t["root_states"][:, 6] = 1.0
         self.t["reset_buf"].fill_(True)                      # base_task.py:83
         self.set_command_range(p.cc_range0[0], p.cc_range0[1])
@@ -83,7 +86,7 @@ class BufferSet:
     def refresh_pointers(self):
         for name in BUFFER_FIELDS:
             t = self.t[name]
-            if t is not None and not (self.p.alias_outputs and name in self.ALIASED):
+            if t is not None and not (self.p.alias_outputs and name in self.ALIASED) and name != "height_samples":
                 assert t.is_contiguous(), name
             setattr(self.struct, name, None if t is None else C.c_void_p(t.data_ptr()))
 

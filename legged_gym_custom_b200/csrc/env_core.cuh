@@ -217,10 +217,12 @@ B200_HD void scan_point(const B200EnvParams& P, int j, float* vx, float* vy) {
   *vx = P.scan_x[gx];
   *vy = P.scan_y[j - gx * P.scan_ny];
 }
+B200_HD int hs_pitch_of(const B200EnvParams& P) { return P.hs_pitch > 0 ? P.hs_pitch : P.hs_cols; }
 B200_HD float height_at(const B200EnvParams& P, const int16_t* hs, int px, int py) {
-  const int16_t* p = hs + (px * P.hs_cols + py);        // rows * cols < 2^31 (checked at env creation)
+  const int pitch = hs_pitch_of(P);
+  const int16_t* p = hs + (px * pitch + py);            // rows * pitch < 2^31 (checked at env creation)
   const int16_t a = B200_LDG(p);
-  const int16_t b = B200_LDG(p + P.hs_cols);
+  const int16_t b = B200_LDG(p + pitch);
   const int16_t c = B200_LDG(p + 1);
   int16_t m = a < b ? a : b;
   m = m < c ? m : c;
@@ -833,7 +835,7 @@ B200_HD bool env_layout_is_go2(const B200EnvParams& P) {
 
 template <bool FIXED, class SC>
 B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, SC& S, const float* pt_x, const float* pt_y,
-                          int e, int lane_lo, int lane_hi, float* tail_dst = nullptr) {
+                          int e, int lane_lo, int lane_hi, float* tail_dst = nullptr, bool do_scan = true) {
   B200_ENV_DIMS;
 
   // ---- stage 0: stage the env's small rows into scratch (coalesced: consecutive lanes, consecutive floats).
@@ -912,11 +914,13 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, SC& S
 
   // ---- stage 1: height scan, points strided over lanes (legged_robot.py:997-1032): all cells of the lane first, then
   // all gathers (3 per point, independent), then the minima -- one round trip to the height field per lane
+  if (!do_scan) return;            // (the tile kernel's terrain-tile mode runs its own stage 1)
   B200_FOR_LANES(lane) {
     int n_out = 0;
     if (P.has_height_samples) {
       const YawQuat yq = yaw_quat(S.root + 3);
       const float inv_h = 1.0f / P.horizontal_scale;
+      const int hs_pitch = hs_pitch_of(P);
       constexpr int kMaxPerLane = (B200_MAX_SCAN + 31) / 32;
       const int per_lane = FIXED ? (B200_GO2_SCAN_NX * B200_GO2_SCAN_NY + 31) / 32 : kMaxPerLane;
       int px[kMaxPerLane], py[kMaxPerLane];
@@ -929,9 +933,9 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, SC& S
       }
 #pragma unroll
       for (int k = 0; k < per_lane; ++k) {
-        const int16_t* p = B.height_samples + (px[k] * P.hs_cols + py[k]);   // rows * cols < 2^31 (checked at env creation)
+        const int16_t* p = B.height_samples + (px[k] * hs_pitch + py[k]);    // rows * pitch < 2^31 (checked at env creation)
         ha[k] = B200_LDG(p);
-        hb[k] = B200_LDG(p + P.hs_cols);
+        hb[k] = B200_LDG(p + hs_pitch);
         hc[k] = B200_LDG(p + 1);
       }
 #pragma unroll

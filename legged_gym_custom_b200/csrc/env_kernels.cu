@@ -10,6 +10,7 @@
 // consecutive addresses (16-byte vectors for the bulk rows), the per-env working set lives in
 // shared memory, and the params/pointer structs travel as __grid_constant__ kernel arguments
 // (constant bank, no extra copy per launch).
+#include <cuda.h>
 #include <stdarg.h>
 
 #include "bulk_copy.cuh"
@@ -194,24 +195,32 @@ __device__ __forceinline__ void tile_cur_tail(const B200EnvParams& P, const EnvT
 
 __global__ void __launch_bounds__(kEnvsPerCta * 32, 4)
 post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t step,
-                         const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace) {
+                         const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace,
+                         const __grid_constant__ CUtensorMap hs_map, int terrain_tiles) {
   extern __shared__ __align__(128) uint8_t tile_smem_raw[];
   float* tile = reinterpret_cast<float*>(tile_smem_raw);
   TileScratch* scratch = reinterpret_cast<TileScratch*>(tile_smem_raw + (size_t)kEnvsPerCta * kTileRow * sizeof(float));
   __shared__ float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
   __shared__ EnvTables T;
   __shared__ __align__(8) uint64_t hist_bar;
+  __shared__ __align__(8) uint64_t terrain_bar[kEnvsPerCta];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int e0 = blockIdx.x * kEnvsPerCta;
   const int e = e0 + warp;
   const bool live = e < P.num_envs;
   const int n_live = min(kEnvsPerCta, P.num_envs - e0);
   constexpr int NP = B200_PROPRIO, NP4 = NP / 4, HN4 = kTileHist / 4, OBS4 = kTileObs / 4, NS4 = B200_GO2_SCAN_NX * B200_GO2_SCAN_NY / 4;
-  if (t == 0) {      // the history rows start towards shared memory before anything else happens
-    bulk::mbar_init(&hist_bar, 1);
-    bulk::mbar_expect_tx(&hist_bar, (uint32_t)(n_live * kTileHist * sizeof(float)));
-    for (int slot = 0; slot < n_live; ++slot)
-      bulk::load(tile + slot * kTileRow, B.obs_history_buf + (int64_t)(e0 + slot) * kTileHist, kTileHist * sizeof(float), &hist_bar);
+  if (t == 0) {      // the history rows start towards shared memory before anything else happens ...
+    // (... unless the head of every tile row first hosts the env's TERRAIN tile: then warp w fetches its history itself,
+    // right after its height scan -- n_live arrivals instead of one)
+    bulk::mbar_init(&hist_bar, terrain_tiles ? (uint32_t)n_live : 1u);
+    if (terrain_tiles) {
+      for (int w = 0; w < kEnvsPerCta; ++w) bulk::mbar_init(terrain_bar + w, 1);
+    } else {
+      bulk::mbar_expect_tx(&hist_bar, (uint32_t)(n_live * kTileHist * sizeof(float)));
+      for (int slot = 0; slot < n_live; ++slot)
+        bulk::load(tile + slot * kTileRow, B.obs_history_buf + (int64_t)(e0 + slot) * kTileHist, kTileHist * sizeof(float), &hist_bar);
+    }
   }
   if (t < P.num_scan) scan_point(P, t, &pt_x[t], &pt_y[t]);
   if (t >= 64 && t < 64 + B200_MAX_PROPRIO) env_tables_fill<TileScratch>(P, T, t - 64);
@@ -227,7 +236,71 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
   float* row = tile + warp * kTileRow;
 
   // ---- A: small rows -> scratch (the privileged statics straight into the tile's tail), height scan
-  if (live) env_warp_pre<true>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1, row + kTileObs);
+  if (live) env_warp_pre<true>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1, row + kTileObs, !terrain_tiles);
+  if (live && terrain_tiles) {
+    // Height scan from a shared-memory terrain tile (north_star design choice 2; legged_robot.py:997-1032).  The 132 scan
+    // points of an env cover at most ~23 x 23 cells of the field (1.65 m x 1.5 m rotated by any yaw, 0.1 m cells): the lanes
+    // compute their cells, the warp reduces the bounding box, lane 0 fetches the 32 x 32 int16 box at its corner with ONE
+    // 2-D TMA copy into the (still unused) head of the env's tile row, and the 3 cells of every point are read from there.
+    // A box wider than 31 cells (a layout this kernel does not run) falls back to the gathers.
+    TileScratch& S = scratch[warp];
+    constexpr int NS = B200_GO2_SCAN_NX * B200_GO2_SCAN_NY, PER = (NS + 31) / 32;
+    const YawQuat yq = yaw_quat(S.root + 3);
+    const float inv_h = 1.0f / P.horizontal_scale;
+    int px[PER], py[PER];
+    int lo_x = 0x7fffffff, lo_y = 0x7fffffff, hi_x = 0, hi_y = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int j = lane + 32 * k, jc = j < NS ? j : NS - 1;
+      height_cell_pt(P, pt_x[jc], pt_y[jc], yq, S.root, inv_h, &px[k], &py[k]);
+      lo_x = min(lo_x, px[k]); hi_x = max(hi_x, px[k]);
+      lo_y = min(lo_y, py[k]); hi_y = max(hi_y, py[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+      lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    const bool fits = hi_x - lo_x <= 30 && hi_y - lo_y <= 30;       // + the (px + 1, py) / (px, py + 1) neighbours
+    const int16_t* tl = reinterpret_cast<const int16_t*>(row);       // [32 x][32 y] int16
+    if (fits) {
+      if (lane == 0) {
+        bulk::mbar_expect_tx(terrain_bar + warp, 32 * 32 * 2);
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                         bulk::smem_addr(row)),
+                     "l"(&hs_map), "r"(bulk::smem_addr(terrain_bar + warp)), "r"(lo_y), "r"(lo_x)
+                     : "memory");
+      }
+      bulk::mbar_wait(terrain_bar + warp, 0);
+    }
+    int n_out = 0;
+    const int pitch = hs_pitch_of(P);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int j = lane + 32 * k;
+      if (j < NS) {
+        int16_t a, b, c;
+        if (fits) {
+          const int o = (px[k] - lo_x) * 32 + (py[k] - lo_y);
+          a = tl[o]; b = tl[o + 32]; c = tl[o + 1];
+        } else {
+          const int16_t* p = B.height_samples + (px[k] * pitch + py[k]);
+          a = __ldg(p); b = __ldg(p + pitch); c = __ldg(p + 1);
+        }
+        int16_t m = a < b ? a : b;
+        m = m < c ? m : c;
+        const float h = (float)m * P.vertical_scale;
+        S.heights[j] = h;
+        n_out += fabsf(h) > 0.1f;
+      }
+    }
+    S.outliers[lane] = n_out;
+    __syncwarp();                                                    // every lane is done with the terrain tile: the history may land
+    if (lane == 0) {
+      bulk::mbar_expect_tx(&hist_bar, (uint32_t)(kTileHist * sizeof(float)));
+      bulk::load(row, B.obs_history_buf + (int64_t)e * kTileHist, kTileHist * sizeof(float), &hist_bar);
+    }
+  }
   B200_TRACE(1)
   __syncthreads();
 
@@ -492,8 +565,11 @@ int b200_env_create(const B200EnvParams* p, int device, B200Env** out) {
   B200_CHECK_ARG(p->num_scan % 4 == 0, "b200_env_create: num_scan must be a multiple of 4 (rows move as 16-byte vectors)");
   B200_CHECK_ARG(p->num_priv == 29 && p->num_est == 3, "b200_env_create: privileged/estimated layout must be 29/3");
   B200_CHECK_ARG(p->n_penalised <= B200_NUM_BODIES && p->n_termination <= B200_NUM_BODIES, "b200_env_create: body tables");
-  B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2 && (int64_t)p->hs_rows * p->hs_cols < (1ll << 31)),
-                 "b200_env_create: height_samples shape");
+  B200_CHECK_ARG(!p->has_height_samples || (p->hs_rows >= 2 && p->hs_cols >= 2 && (p->hs_pitch == 0 || p->hs_pitch >= p->hs_cols) &&
+                                            (int64_t)p->hs_rows * (p->hs_pitch > 0 ? p->hs_pitch : p->hs_cols) < (1ll << 31)),
+                 "b200_env_create: height_samples shape / pitch");
+  B200_CHECK_ARG(!p->terrain_tiles || (p->has_height_samples && p->hs_pitch % 8 == 0 && p->hs_pitch > 0),
+                 "b200_env_create: terrain_tiles needs a height field with hs_pitch % 8 == 0");
   B200_CHECK_ARG(!p->has_height_samples || (p->horizontal_scale > 0.0f && (float)(p->hs_rows + p->hs_cols) * p->horizontal_scale < 8388608.0f),
                  "b200_env_create: height field extent must stay below 2^23 m");
   B200_CHECK_ARG(p->resample_interval > 0 && p->push_interval > 0, "b200_env_create: intervals must be > 0");
@@ -539,6 +615,33 @@ int b200_env_set_prefetch(B200Env* env, int on) {
   return 0;
 }
 
+// 2-D tensor map of the height field for the terrain-tile mode: int16 [hs_rows][hs_pitch], box 32 x 32, no swizzle
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_hs_map(CUtensorMap* map, const B200EnvParams& p, const int16_t* hs) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      b200_set_error("cuTensorMapEncodeTiled is unavailable");
+      return -2;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)p.hs_cols, (cuuint64_t)p.hs_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)p.hs_pitch * 2};
+  cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t*>(hs), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200_set_error("cuTensorMapEncodeTiled(height_samples) failed with %d", (int)r);
+    return -3;
+  }
+  return 0;
+}
+
 static int post_physics_attr() {
   static bool done = false;
   if (!done) {
@@ -562,17 +665,23 @@ static int post_physics_attr() {
 }
 
 // the go2 layout (history 10, scan 12 x 11) runs the variant with the layout baked in
-static void launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st,
+static int launch_post_physics(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st,
                                 int dry = 0) {
   const int ctas = (env->p.num_envs + kEnvsPerCta - 1) / kEnvsPerCta;
   const size_t smem = kEnvsPerCta * sizeof(EnvScratch);
-  if (env->p.alias_outputs && env_layout_is_go2(env->p) && !env->force_generic_layout && !dry && !bufs->height_index)
-    post_physics_tile_kernel<<<ctas, kEnvsPerCta * 32, kTileSmem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace);
+  if (env->p.alias_outputs && env_layout_is_go2(env->p) && !env->force_generic_layout && !dry && !bufs->height_index) {
+    CUtensorMap hs_map = {};
+    const int tiles = env->p.terrain_tiles && env->p.has_height_samples && ((uintptr_t)bufs->height_samples & 15) == 0;
+    if (tiles)
+      if (int rc = make_hs_map(&hs_map, env->p, bufs->height_samples)) return rc;
+    post_physics_tile_kernel<<<ctas, kEnvsPerCta * 32, kTileSmem, st>>>(env->p, *bufs, step, step_dev, env->phase_trace, hs_map, tiles);
+  }
   else if (env_layout_is_go2(env->p) && !env->force_generic_layout)
     post_physics_kernel<true><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, dry ? nullptr : env->phase_trace, env->prefetch_history, dry);
   else
     post_physics_kernel<false><<<ctas, kEnvsPerCta * 32, smem, st>>>(env->p, *bufs, step, step_dev, dry ? nullptr : env->phase_trace,
                                                                      env->prefetch_history, dry);
+  return 0;
 }
 
 // Command curriculum (go2.py:80-107, :222-223), one CTA per step when P.command_curriculum:
@@ -604,7 +713,7 @@ command_curriculum_kernel(const __grid_constant__ B200EnvParams P, const __grid_
 }
 
 static int launch_command_curriculum(const B200Env* env, const B200EnvBuffers* bufs, int64_t step, const int64_t* step_dev, cudaStream_t st) {
-  launch_post_physics(env, bufs, step, step_dev, st, /*dry=*/1);
+  if (int rc = launch_post_physics(env, bufs, step, step_dev, st, /*dry=*/1)) return rc;
   B200_CHECK_LAUNCH("post_physics_kernel (command-curriculum probe)");
   command_curriculum_kernel<<<1, 256, 0, st>>>(env->p, *bufs, step, step_dev);
   B200_CHECK_LAUNCH("command_curriculum_kernel");
@@ -644,7 +753,7 @@ int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64
   if (parts & 1) {
     if (env->p.command_curriculum)
       if (int rc = launch_command_curriculum(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream)) return rc;
-    launch_post_physics(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream);
+    if (int rc = launch_post_physics(env, bufs, common_step_counter, nullptr, (cudaStream_t)stream)) return rc;
     B200_CHECK_LAUNCH("post_physics_kernel");
   }
   if (parts & 2) {
@@ -676,7 +785,7 @@ int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t
   if (int rc = post_physics_attr()) return rc;
   if (env->p.command_curriculum)
     if (int rc = launch_command_curriculum(env, bufs, 0, step_counter_dev, (cudaStream_t)stream)) return rc;
-  launch_post_physics(env, bufs, 0, step_counter_dev, (cudaStream_t)stream);
+  if (int rc = launch_post_physics(env, bufs, 0, step_counter_dev, (cudaStream_t)stream)) return rc;
   B200_CHECK_LAUNCH("post_physics_kernel");
   extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
   B200_CHECK_LAUNCH("extras_kernel");

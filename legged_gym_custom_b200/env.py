@@ -87,7 +87,7 @@ def _buffer_property(name):
 class Go2Env:
     def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *, physx=None,
                  seed=None, index_div_mode=0, height_samples=None, terrain_origins=None, record_height_index=False,
-                 alias_outputs=True):
+                 alias_outputs=True, terrain_tiles=False):
         if not torch.cuda.is_available():
             raise RuntimeError("Go2Env needs a CUDA device: the hot path has no CPU fallback")
         self.lib = _lib.lib()
@@ -111,7 +111,8 @@ class Go2Env:
         # (identical values, go2.py:538-563) -- strided views instead of four more buffers; `bind_output_rows` lets a
         # runner point the rows at its rollout-storage slot.  Pass False for separate contiguous buffers.
         self.params = p = env_params_from_cfg(cfg, num_envs=N, seed=seed, index_div_mode=index_div_mode,
-                                              hs_shape=None if hs is None else hs.shape, alias_outputs=alias_outputs)
+                                              hs_shape=None if hs is None else hs.shape, alias_outputs=alias_outputs,
+                                              terrain_tiles=terrain_tiles and hs is not None)
         self.bufs = BufferSet(p, self.device, record_height_index=record_height_index)
         self._handle = C.c_void_p()
         _lib.check(self.lib.b200_env_create(C.byref(p), self.device.index or 0, C.byref(self._handle)))

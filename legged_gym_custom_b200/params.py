@@ -16,7 +16,7 @@ NUM_BODIES = 19
 NUM_FEET = 4
 MAX_SCAN_AXIS = 24
 MAX_PROPRIO = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # go2.urdf with collapse_fixed_joints (Head_*/foot joints are dont_collapse) -- SURVEY.md §8(c)
 BODY_NAMES = ["base", "Head_upper", "Head_lower"] + [
@@ -74,7 +74,7 @@ class EnvParams(C.Structure):
         ("seed", C.c_uint64),
         ("cc_vel_increment", C.c_double), ("cc_max_forward_vel", C.c_double), ("cc_max_reverse_vel", C.c_double),
         ("cc_range0", C.c_double * 2),
-        ("cc_threshold", f32), ("command_curriculum", i32),
+        ("cc_threshold", f32), ("command_curriculum", i32), ("hs_pitch", i32), ("terrain_tiles", i32),
     ]
 
     def reward_names(self):
@@ -152,7 +152,7 @@ def _names_containing(keys, names):
     return out
 
 
-def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shape=None, alias_outputs=False):
+def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shape=None, alias_outputs=False, terrain_tiles=False):
     """Pack a reference-style env cfg (class namespace or instance) into EnvParams.
 
     `hs_shape` = (rows, cols) of height_samples for heightfield/trimesh terrains.  `alias_outputs`: the observation outputs
@@ -160,6 +160,7 @@ def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shap
     """
     p = EnvParams()
     p.alias_outputs = int(bool(alias_outputs))
+    p.terrain_tiles = int(bool(terrain_tiles))
     env, ter, cmd, ctl, dr = cfg.env, cfg.terrain, cfg.commands, cfg.control, cfg.domain_rand
     rew, norm, noise = cfg.rewards, cfg.normalization, cfg.noise
     p.abi_version = ABI_VERSION
@@ -218,6 +219,7 @@ def env_params_from_cfg(cfg, num_envs=None, seed=1234, index_div_mode=0, hs_shap
     if p.has_height_samples:
         assert hs_shape is not None
         p.hs_rows, p.hs_cols = int(hs_shape[0]), int(hs_shape[1])
+        p.hs_pitch = (p.hs_cols + 7) // 8 * 8          # 16-byte rows: an env's scan neighbourhood is one 2-D TMA box
     p.border_size, p.horizontal_scale, p.vertical_scale = ter.border_size, ter.horizontal_scale, ter.vertical_scale
     p.index_div_mode = int(index_div_mode)
     p.parkour = int(bool(_get(ter, "parkour", False)))

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_mirrors_match_library():
     lib = _lib.lib()
-    assert lib.b200_abi_version() == 2
+    assert lib.b200_abi_version() == 3
     assert lib.b200_env_params_size() == C.sizeof(EnvParams)
     assert lib.b200_env_buffers_size() == C.sizeof(EnvBuffers)
 

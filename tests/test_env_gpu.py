@@ -24,10 +24,12 @@ DEV = "cuda:0"
 class CudaEnv:
     """thin driver of the C ABI over a BufferSet (what Go2Env does, minus the PhysX provider)."""
 
-    def __init__(self, p, record_height_index=True, force_generic=0, prefetch=0, alias=0):
+    def __init__(self, p, record_height_index=True, force_generic=0, prefetch=0, alias=0, terrain_tiles=0):
         """alias=1: observation outputs aliased into the critic rows (b200gym.h `alias_outputs`); with the go2 layout and no
-        height-index recording that is post_physics_tile_kernel"""
+        height-index recording that is post_physics_tile_kernel; terrain_tiles=1: its height scan reads a TMA-staged
+        shared-memory tile of the field"""
         p.alias_outputs = int(alias)
+        p.terrain_tiles = int(bool(terrain_tiles) and bool(p.has_height_samples))
         self.lib, self.p = _lib.lib(), p
         self.bufs = BufferSet(p, DEV, record_height_index=record_height_index)
         self.h = C.c_void_p()
@@ -54,14 +56,16 @@ class CudaEnv:
         self.lib.b200_env_destroy(self.h)
 
 
-@pytest.mark.parametrize("force_generic,prefetch,alias,record", [(0, 0, 0, 1), (1, 0, 0, 1), (0, 1, 0, 1), (1, 1, 0, 1), (0, 0, 1, 0), (1, 0, 1, 1), (0, 0, 1, 1)],
+@pytest.mark.parametrize("force_generic,prefetch,alias,record,tiles",
+                         [(0, 0, 0, 1, 0), (1, 0, 0, 1, 0), (0, 1, 0, 1, 0), (1, 1, 0, 1, 0), (0, 0, 1, 0, 0), (1, 0, 1, 1, 0), (0, 0, 1, 1, 0), (0, 0, 1, 0, 1)],
                          ids=["go2-layout-baked-in", "layout-generic", "go2-layout-baked-in+prefetch", "layout-generic+prefetch",
-                              "tile-kernel(aliased-rows)", "layout-generic+aliased-rows", "go2-layout-baked-in+aliased-rows"])
+                              "tile-kernel(aliased-rows)", "layout-generic+aliased-rows", "go2-layout-baked-in+aliased-rows",
+                              "tile-kernel+smem-terrain-tiles"])
 @pytest.mark.parametrize("task", gu.TASKS + gu.CC_SCENARIOS)
-def test_cuda_env_matches_reference_golden(task, force_generic, prefetch, alias, record):
+def test_cuda_env_matches_reference_golden(task, force_generic, prefetch, alias, record, tiles):
     g = gu.load(task)
     p = gu.params_for(task, g)
-    env = CudaEnv(p, force_generic=force_generic, prefetch=prefetch, alias=alias, record_height_index=bool(record))
+    env = CudaEnv(p, force_generic=force_generic, prefetch=prefetch, alias=alias, record_height_index=bool(record), terrain_tiles=tiles)
     env.bufs.load_statics(gu.statics_for(task, g))
     st = gu.init_state(g, p)
     step = int(st.pop("common_step_counter"))
@@ -94,7 +98,7 @@ def test_command_curriculum_with_device_step_counter(task):
     env.close()
 
 
-@pytest.mark.parametrize("tile", [0, 1], ids=["separate-outputs", "tile-kernel(aliased-rows)"])
+@pytest.mark.parametrize("tile", [0, 1, 2], ids=["separate-outputs", "tile-kernel(aliased-rows)", "tile-kernel+smem-terrain-tiles"])
 @pytest.mark.parametrize("task,num_envs,steps", [("go2_parkour", 4096, 3), ("go2_parkour_finetune", 1000, 2), ("go2", 777, 2),
                                                  ("go2_parkour", 1, 2), ("go2_parkour", 7, 2), ("go2_parkour", 9, 2),
                                                  ("go2_parkour", 65536, 1)])
@@ -108,7 +112,7 @@ def test_cuda_env_matches_oracle_at_scale(task, num_envs, steps, tile):
     statics = su.random_statics(p, rng, hs, origins)
     st = su.random_state(p, rng, origins)
     orc = Go2Oracle(p, statics, st)
-    env = CudaEnv(p, alias=tile, record_height_index=not tile)
+    env = CudaEnv(p, alias=int(tile > 0), record_height_index=not tile, terrain_tiles=int(tile == 2))
     env.bufs.load_statics(statics)
     st2 = dict(st)
     step = int(st2.pop("common_step_counter"))

@@ -18,7 +18,7 @@ class Cfg(configs.Go2ParkourCfg):
         num_envs = N
 
 
-env = Go2Env(Cfg, sim_device="cuda:0")
+env = Go2Env(Cfg, sim_device="cuda:0", terrain_tiles=bool(int(os.environ.get("B200_TERRAIN_TILES", "0"))))
 env.reset()
 env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=1000)
 actions = torch.randn(N, 12, device="cuda:0")
