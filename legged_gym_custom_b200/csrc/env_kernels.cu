@@ -169,7 +169,7 @@ static_assert((sizeof(TileScratch) / 16) % 2 == 1, "TileScratch stride would ban
 constexpr int kTileHist = B200_GO2_HISTORY * B200_PROPRIO;                       // 520
 constexpr int kTileObs = kTileHist + B200_PROPRIO;                               // 572
 constexpr int kTileRow = kTileObs + 32 + B200_GO2_SCAN_NX * B200_GO2_SCAN_NY;     // 736
-constexpr size_t kTileSmem = (size_t)kEnvsPerCta * (kTileRow * sizeof(float) + sizeof(TileScratch));
+constexpr size_t kTileSmem = (size_t)kEnvsPerCta * (kTileRow * sizeof(float) + sizeof(TileScratch)) + 128;
 static_assert((kTileRow * sizeof(float)) % 16 == 0 && (kTileHist * sizeof(float)) % 16 == 0, "rows move as 16-byte multiples");
 
 // cur (unclipped, go2.py:506-519) and the critic tail's est / scan parts of env `e` into its tile row; one warp
@@ -198,8 +198,10 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
                          const int64_t* __restrict__ step_dev, unsigned long long* __restrict__ trace,
                          const __grid_constant__ CUtensorMap hs_map, int terrain_tiles) {
   extern __shared__ __align__(128) uint8_t tile_smem_raw[];
-  float* tile = reinterpret_cast<float*>(tile_smem_raw);
-  TileScratch* scratch = reinterpret_cast<TileScratch*>(tile_smem_raw + (size_t)kEnvsPerCta * kTileRow * sizeof(float));
+  // tile rows start on 128-byte boundaries of the shared window (TMA destinations): align by hand, the launch adds 128 bytes
+  uint8_t* tile_base = tile_smem_raw + ((128u - (bulk::smem_addr(tile_smem_raw) & 127u)) & 127u);
+  float* tile = reinterpret_cast<float*>(tile_base);
+  TileScratch* scratch = reinterpret_cast<TileScratch*>(tile_base + (size_t)kEnvsPerCta * kTileRow * sizeof(float));
   __shared__ float pt_x[B200_MAX_SCAN], pt_y[B200_MAX_SCAN];
   __shared__ EnvTables T;
   __shared__ __align__(8) uint64_t hist_bar;
@@ -261,6 +263,9 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
       lo_x = min(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
       lo_y = min(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = max(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
     }
+    // a TMA box must start on a 16-byte boundary of its innermost dimension (8 int16 cells): measured -- an odd column start
+    // raises "illegal instruction" (tools/scratch/tma_u16_test.cu) -- so the box starts at the column rounded down to 8
+    lo_y &= ~7;
     const bool fits = hi_x - lo_x <= 30 && hi_y - lo_y <= 30;       // + the (px + 1, py) / (px, py + 1) neighbours
     const int16_t* tl = reinterpret_cast<const int16_t*>(row);       // [32 x][32 y] int16
     if (fits) {
