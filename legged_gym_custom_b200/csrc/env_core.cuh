@@ -834,6 +834,9 @@ B200_HD bool env_layout_is_go2(const B200EnvParams& P) {
 }
 
 template <bool FIXED, class SC>
+B200_HD void env_warp_scan(const B200EnvParams& P, const B200EnvBuffers& B, SC& S, const float* pt_x, const float* pt_y, int e, int lane_lo,
+                           int lane_hi);
+template <bool FIXED, class SC>
 B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, SC& S, const float* pt_x, const float* pt_y,
                           int e, int lane_lo, int lane_hi, float* tail_dst = nullptr, bool do_scan = true) {
   B200_ENV_DIMS;
@@ -912,9 +915,17 @@ B200_HD void env_warp_pre(const B200EnvParams& P, const B200EnvBuffers& B, SC& S
   }
   B200_WARP_SYNC();
 
-  // ---- stage 1: height scan, points strided over lanes (legged_robot.py:997-1032): all cells of the lane first, then
-  // all gathers (3 per point, independent), then the minima -- one round trip to the height field per lane
-  if (!do_scan) return;            // (the tile kernel's terrain-tile mode runs its own stage 1)
+  // ---- stage 1: height scan (env_warp_scan)
+  if (do_scan) env_warp_scan<FIXED>(P, B, S, pt_x, pt_y, e, lane_lo, lane_hi);
+}
+
+// ---- stage 1: height scan, points strided over lanes (legged_robot.py:997-1032): all cells of the lane first, then
+// all gathers (3 per point, independent), then the minima -- one round trip to the height field per lane.  Needs stage 0
+// (the root state) of its env only.
+template <bool FIXED, class SC>
+B200_HD void env_warp_scan(const B200EnvParams& P, const B200EnvBuffers& B, SC& S, const float* pt_x, const float* pt_y, int e, int lane_lo,
+                           int lane_hi) {
+  B200_ENV_DIMS;
   B200_FOR_LANES(lane) {
     int n_out = 0;
     if (P.has_height_samples) {

@@ -226,7 +226,6 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
   }
   if (t < P.num_scan) scan_point(P, t, &pt_x[t], &pt_y[t]);
   if (t >= 64 && t < 64 + B200_MAX_PROPRIO) env_tables_fill<TileScratch>(P, T, t - 64);
-  __syncthreads();
   if (step_dev) step = *step_dev;
 #define B200_TRACE(slot)                                                                          \
   if (trace && t == 0) {                                                                          \
@@ -237,8 +236,36 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
   B200_TRACE(0)
   float* row = tile + warp * kTileRow;
 
-  // ---- A: small rows -> scratch (the privileged statics straight into the tile's tail), height scan
-  if (live) env_warp_pre<true>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1, row + kTileObs, !terrain_tiles);
+  // ---- A0: small rows -> scratch (the privileged statics straight into the tile's tail).  Needs neither the tables nor
+  //      the scan points, so the barrier behind it is also the one that publishes them (no barrier of its own for those).
+  if (live) env_warp_pre<true>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1, row + kTileObs, /*do_scan=*/false);
+  B200_TRACE(1)
+  __syncthreads();
+
+  // ---- A1 + E: the items of all 8 envs packed type by type (as post_physics_kernel; the termination flags, which need the
+  //      scan's outlier counts, moved to B1) and then every warp's height scan: both read only what A0 staged, so the
+  //      gathers of one warp fly under the item arithmetic of the others
+  {
+    constexpr int kBodies = kEnvsPerCta * B200_NUM_BODIES, kDofs = kEnvsPerCta * B200_NUM_DOF;
+    if (t < kBodies) {
+      const int slot = t / B200_NUM_BODIES;
+      if (slot < n_live) env_item_body(P, scratch[slot], t - slot * B200_NUM_BODIES);
+    } else if (t < kBodies + kDofs) {
+      const int slot = (t - kBodies) / B200_NUM_DOF;
+      if (slot < n_live) env_item_dof(P, T, scratch[slot], (t - kBodies) - slot * B200_NUM_DOF);
+    }
+    const int slot4 = lane >> 2;
+    if (warp == 0) {
+      if (slot4 < n_live) env_item_leg(P, scratch[slot4], lane & 3);
+    } else if (warp == 1) {
+      if (slot4 < n_live) env_item_angle(P, scratch[slot4], lane & 3, (uint32_t)(e0 + slot4), (uint32_t)step);
+    } else if (warp == 2) {
+      if (lane < n_live) env_item_velocities(scratch[lane]);
+    } else if (warp == 3) {
+      if (lane < n_live) env_item_feet_push(P, scratch[lane], (uint32_t)(e0 + lane), step);
+    }
+  }
+  if (live && !terrain_tiles) env_warp_scan<true>(P, B, scratch[warp], pt_x, pt_y, e, lane, lane + 1);
   if (live && terrain_tiles) {
     // Height scan from a shared-memory terrain tile (north_star design choice 2; legged_robot.py:997-1032).  The 132 scan
     // points of an env cover at most ~23 x 23 cells of the field (1.65 m x 1.5 m rotated by any yaw, 0.1 m cells): the lanes
@@ -306,38 +333,27 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
       bulk::load(row, B.obs_history_buf + (int64_t)e * kTileHist, kTileHist * sizeof(float), &hist_bar);
     }
   }
-  B200_TRACE(1)
-  __syncthreads();
-
-  // ---- E: items, packed type by type (as post_physics_kernel)
-  {
-    constexpr int kBodies = kEnvsPerCta * B200_NUM_BODIES, kDofs = kEnvsPerCta * B200_NUM_DOF;
-    if (t < kBodies) {
-      const int slot = t / B200_NUM_BODIES;
-      if (slot < n_live) env_item_body(P, scratch[slot], t - slot * B200_NUM_BODIES);
-    } else if (t < kBodies + kDofs) {
-      const int slot = (t - kBodies) / B200_NUM_DOF;
-      if (slot < n_live) env_item_dof(P, T, scratch[slot], (t - kBodies) - slot * B200_NUM_DOF);
-    } else if (t - (kBodies + kDofs) < n_live) {
-      env_item_flags(P, scratch[t - (kBodies + kDofs)]);
-    }
-    const int slot4 = lane >> 2;
-    if (warp == 0) {
-      if (slot4 < n_live) env_item_leg(P, scratch[slot4], lane & 3);
-    } else if (warp == 1) {
-      if (slot4 < n_live) env_item_angle(P, scratch[slot4], lane & 3, (uint32_t)(e0 + slot4), (uint32_t)step);
-    } else if (warp == 2) {
-      if (lane < n_live) env_item_velocities(scratch[lane]);
-    } else if (warp == 3) {
-      if (lane < n_live) env_item_feet_push(P, scratch[lane], (uint32_t)(e0 + lane), step);
-    }
-  }
   B200_TRACE(2)
   __syncthreads();
 
-  // ---- B1: reward terms (warp = part, lane = env slot); the Philox blocks of a reset; lane 16 of warp w sends env w's
-  //      shifted history home (in place in global memory: the source is the shared-memory copy, which has fully arrived)
-  if (lane < n_live) env_terms_part<true>(P, scratch[lane], warp);
+  // ---- B1: lane 16 of warp w: termination flags of env w (check_termination + next step's jump flags); then reward terms
+  //      (warp = part: a compile-time constant per case, so every warp runs straight-line code for ITS terms only; lane = env
+  //      slot), the Philox blocks of a reset, and lane 16 sends env w's shifted history home (in place in global memory: the
+  //      source is the shared-memory copy, which has fully arrived)
+  if (live && lane == 16) env_item_flags(P, scratch[warp]);
+  __syncwarp();
+  if (lane < n_live) {
+    switch (warp) {
+      case 0: env_terms_part<true>(P, scratch[lane], 0); break;
+      case 1: env_terms_part<true>(P, scratch[lane], 1); break;
+      case 2: env_terms_part<true>(P, scratch[lane], 2); break;
+      case 3: env_terms_part<true>(P, scratch[lane], 3); break;
+      case 4: env_terms_part<true>(P, scratch[lane], 4); break;
+      case 5: env_terms_part<true>(P, scratch[lane], 5); break;
+      case 6: env_terms_part<true>(P, scratch[lane], 6); break;
+      default: env_terms_part<true>(P, scratch[lane], 7); break;
+    }
+  }
   if (live && scratch[warp].early_reset && lane >= 8 && lane < 8 + B200_RESET_BLOCKS)
     env_reset_draw(P, scratch[warp].reset_draws, (uint32_t)e, (uint32_t)step, lane - 8);
   const bool shift = live && !scratch[warp].early_refill;
