@@ -215,7 +215,7 @@ class PPO:
         self.use_streams = True
         # SMs the low-priority side chains of a minibatch (estimator, critic) may occupy; 0 = all.  Their big GEMMs are
         # one-wave persistent kernels that hold every SM until they end, which starves the small kernels of the critical
-        # path whatever the stream priorities are (b200_tc_set_sm_cap).  Measured on B200 (148 SMs), update of 20 minibatches:
+        # path whatever the stream priorities are (b200_tc_set_stream_sm_cap, registered per side stream).  Measured on B200 (148 SMs), update of 20 minibatches:
         # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt)
         self.side_sm_cap = 116
         # weight-gradient GEMMs of the actor / encoder chains on a fifth (low-priority, capped) stream: the dgrad chain that

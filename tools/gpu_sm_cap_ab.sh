@@ -1,12 +1,11 @@
 #!/bin/bash
-# A/B of PPO.side_sm_cap (b200_tc_set_sm_cap on the low-priority chains of a minibatch): one bench line per setting
+# A/B of PPO.side_sm_cap (b200_tc_set_stream_sm_cap on the low-priority chains of a minibatch): one bench line per setting
 cd "${GRAFT_REPO_ROOT:-.}"
-# arguments: <cap>[:<forward cap>] ...
+# arguments: <cap> ...
 for spec in "$@"; do
-  cap=${spec%%:*}; fwd=""
-  if [[ "$spec" == *:* ]]; then fwd="--side-sm-cap-forward ${spec##*:}"; cap="${spec%%:*}"; fi
-  tag=${spec//:/f}
-  timeout 60 python bench.py --no-cpu-baseline --e2e-steps 0 --side-sm-cap $cap $fwd > gpurun_out/bench_smcap_$tag.json 2> gpurun_out/bench_smcap_$tag.err
+  cap=$spec
+  tag=$spec
+  timeout 90 python bench.py --no-cpu-baseline --e2e-steps 0 --side-sm-cap $cap > gpurun_out/bench_smcap_$tag.json 2> gpurun_out/bench_smcap_$tag.err
   python - <<PY
 import json
 try:
