@@ -411,6 +411,23 @@ int b200_tc_set_tma_epilogue(int on);
 /* != 0: weight gradients with >= 256 output rows run on CTA pairs (cta_group::2, 256-row UMMA: X is staged once per pair);
  * (default); 0: single CTAs (A/B switch).  Measured on B200, M = 24576: 512 x 627 49.7 -> 43.9 us, 512 x 736 45.4 -> 37.9 us. */
 int b200_tc_set_wgrad_pairs(int on);
+/* A whole Linear / ELU chain (an MLP's forward pass) in ONE persistent launch: Y_0 = act_0(X . W_0^T + b_0), Y_l =
+ * act_l(Y_{l-1} . W_l^T + b_l).  Replaces num_layers b200_tc_linear_forward launches (actor_critic.py:84-135,
+ * support_networks.py:9-120 at rollout batch sizes, where launch latency, TMEM allocation and pipeline fill dominate): the
+ * CTAs stay resident across the layers and meet at a grid-wide barrier in global memory between two layers.  Every Y_l must
+ * be a distinct buffer with ldy % 4 == 0 (it is the next layer's TMA operand); K >= 8; any N (TMA zero-fills the weight
+ * rows of a narrow head).  `sync`: 4 zero-initialised uint32 on the device, owned by this call site (concurrent chains
+ * on different streams need their own); never reset by the host.  `max_ctas` (0 = all): the CTAs of the launch wait for
+ * each other, so all of them must be resident -- an SM holds two -- and chains that may run CONCURRENTLY must share the
+ * budget of 2 x SMs between them.  Same arithmetic as b200_tc_linear_forward (kind::tf32, fp32 accumulation), for every N. */
+typedef struct B200MlpLayer {
+  const float* W;      /* [N, ldw] */
+  const float* bias;   /* [N] or NULL */
+  float* Y;            /* [M, ldy] */
+  int32_t ldw, ldy, N, K, act;   /* act: 0 none, 1 ELU */
+} B200MlpLayer;
+int b200_tc_mlp_forward(const B200MlpLayer* layers /* host */, int num_layers, const float* X, int ldx, int M, unsigned int* sync, int max_ctas,
+                        void* stream);
 /* dgrad `accumulate`: 0 = overwrite dX; 1 = add to the existing dX; n > 1 = add to the first n columns of dX only (the
  * PPO loss head leaves the ROA regulariser's gradient in the latent columns of the [latent | scan latent] gradient). */
 int b200_tc_linear_supported(int M, int N, int K);

@@ -58,6 +58,7 @@ SYMBOLS = {
     "b200_elu_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b200_clip_adam": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p]),
     "b200_dist_adam": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_tc_mlp_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_parkour_field": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "b200_heightfield_to_trimesh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                               C.c_void_p]),
@@ -72,6 +73,12 @@ SYMBOLS = {
 class CopySeg(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("src_ld", C.c_int32), ("dst_ld", C.c_int32),
                 ("_pad", C.c_int32)]
+
+
+class MlpLayer(C.Structure):
+    """B200MlpLayer (include/b200gym.h)"""
+    _fields_ = [("W", C.c_void_p), ("bias", C.c_void_p), ("Y", C.c_void_p), ("ldw", C.c_int32), ("ldy", C.c_int32), ("N", C.c_int32),
+                ("K", C.c_int32), ("act", C.c_int32)]
 
 
 class ParkourTile(C.Structure):
@@ -103,7 +110,7 @@ class PpoLossArgs(C.Structure):
 _lib = None
 
 # kernels launched per ABI call (for bench.py's `gpu_launches` and per-kernel timing)
-LAUNCHES = {"b200_post_physics_step": 2, "b200_post_physics_step_dev": 3, "b200_sample_actions_dev": 2, "b200_tc_linear_wgrad": 1, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
+LAUNCHES = {"b200_tc_mlp_forward": 1, "b200_post_physics_step": 2, "b200_post_physics_step_dev": 3, "b200_sample_actions_dev": 2, "b200_tc_linear_wgrad": 1, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
 
 
 class _Proxy:

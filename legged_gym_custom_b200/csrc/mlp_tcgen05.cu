@@ -610,6 +610,210 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+
+// ---- tc_chain_kernel: a whole Linear / ELU CHAIN (an MLP's forward) in ONE persistent launch -------------------------------
+// The rollout's policy inference runs 17 GEMMs per env step at M = 4096, each 10-18 us of which ~3 us is work: launch latency,
+// TMEM allocation, barrier set-up and the pipeline fill are paid per layer.  This kernel keeps the CTAs (TMEM, barriers, the
+// warp roles of tc_gemm_kernel's forward path) alive across the layers of a chain: every layer is the usual persistent tile
+// loop over ITS tensor maps, and between two layers the CTAs meet at a grid-wide barrier in global memory -- the epilogue
+// threads of a CTA finish their stores, one of them fences and bumps a monotonic counter, and the TMA producer of every CTA
+// spins until all CTAs have bumped it before it loads the next layer's activations (which are this layer's outputs, read back
+// from L2).  Every CTA of the (persistent, at most two per SM) grid is resident, so the spin cannot deadlock.  The counter's
+// base for the next launch is published by the last CTA to leave: CUDA-graph replays need no host reset.
+constexpr int kMaxChain = 8;
+struct ChainLayer {
+  float* C;
+  const float* bias;
+  int ldc, N, K, act;
+};
+struct ChainArgs {
+  ChainLayer layer[kMaxChain];
+  int num_layers, M;
+  unsigned int* sync;      // device [4], zero-initialised once: [0] arrivals (monotonic), [1] base of this launch, [2] exit counter
+};
+struct ChainMaps {
+  CUtensorMap a[kMaxChain], b[kMaxChain];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int BN, int CPS>
+__global__ void __launch_bounds__(NUM_THREADS, CPS)
+tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
+  using Cfg = TileCfg<BN, false, CPS>;
+  constexpr int STAGES = Cfg::STAGES_;
+  constexpr uint32_t A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  constexpr int STG_PITCH = 36;
+  float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512);      // [8 epilogue warps][32 rows][STG_PITCH]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int worker = (int)blockIdx.x, num_workers = (int)gridDim.x;
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const unsigned int base = g.sync[1];                      // arrivals before this launch (written by the previous launch's last CTA)
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + a, 1);
+      mbar_init(tmem_empty + a, 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int l = 0; l < g.num_layers; ++l) {
+        const int n_tiles = (g.layer[l].N + BN - 1) / BN, num_tiles = m_tiles * n_tiles;
+        const int num_kb = (g.layer[l].K + BK - 1) / BK;
+        prefetch_tmap(&maps.a[l]);
+        prefetch_tmap(&maps.b[l]);
+        if (l > 0) {      // this layer's activations are the previous layer's outputs: every CTA must have stored them
+          const unsigned int want = (unsigned int)l * (unsigned int)num_workers;
+          while (ld_acquire_gpu_u32(g.sync) - base < want) {
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores (observed above) before our TMA loads
+        }
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+          const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(empty_bar + s, ph ^ 1);
+            uint8_t* sa = smem + s * STAGE_BYTES;
+            mbar_expect_tx(full_bar + s, STAGE_BYTES);
+            tma_load_2d(sa, &maps.a[l], full_bar + s, kb * BK, m0);
+            tma_load_2d(sa + A_BYTES, &maps.b[l], full_bar + s, kb * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t it = 0, local_tile = 0;
+      for (int l = 0; l < g.num_layers; ++l) {
+        const int n_tiles = (g.layer[l].N + BN - 1) / BN, num_tiles = m_tiles * n_tiles;
+        const int num_kb = (g.layer[l].K + BK - 1) / BK;
+        for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_tile) {
+          const uint32_t acc = local_tile & 1, acc_ph = (local_tile >> 1) & 1;
+          mbar_wait(tmem_empty + acc, acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(full_bar + s, ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32(tmem_d, make_desc(sa + k * 32, 16, 1024, 2), make_desc(sb + k * 32, 16, 1024, 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar + s);
+          }
+          umma_commit(tmem_full + acc);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..9 (tc_gemm_kernel's forward epilogue: bias, ELU, staged coalesced stores) =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 32, CH_PER_HALF = (CHUNKS + 1) / 2;
+    float* stg = stage + (warp - 2) * (32 * STG_PITCH);
+    const int sr = lane >> 3, sc = (lane & 7) * 4;
+    uint32_t local_tile = 0;
+    for (int l = 0; l < g.num_layers; ++l) {
+      const ChainLayer L = g.layer[l];
+      const int n_tiles = (L.N + BN - 1) / BN, num_tiles = m_tiles * n_tiles;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++local_tile) {
+        const uint32_t acc = local_tile & 1, acc_ph = (local_tile >> 1) & 1;
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        const int row0 = m0 + quarter * 32;
+        const int ci_lo = half * CH_PER_HALF, ci_hi = min(CHUNKS, (half + 1) * CH_PER_HALF);
+        mbar_wait(tmem_full + acc, acc_ph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ci = ci_lo; ci < ci_hi; ++ci) {
+          const int c = ci * 32, col0 = n0 + c;
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
+          if (col0 >= L.N) continue;                            // warp-uniform
+          if (L.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < L.N) v[j] += __ldg(L.bias + col0 + j);
+          }
+          if (L.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = __expf(fminf(v[j], 0.0f)) - 1.0f;
+              v[j] = v[j] > 0.0f ? v[j] : e;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int col = col0 + sc;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = row0 + it * 4 + sr;
+            if (r >= g.M || col >= L.N) continue;
+            const float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + sr) * STG_PITCH + sc);
+            float* dst = L.C + (int64_t)r * L.ldc + col;
+            if (col + 3 < L.N && (((uintptr_t)dst) & 15) == 0) {
+              *reinterpret_cast<float4*>(dst) = x;
+            } else {
+              dst[0] = x.x;
+              if (col + 1 < L.N) dst[1] = x.y;
+              if (col + 2 < L.N) dst[2] = x.z;
+              if (col + 3 < L.N) dst[3] = x.w;
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + acc);
+      }
+      // ---- grid barrier, arrive side: all 8 epilogue warps of this CTA have stored this layer's tiles
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        __threadfence();
+        atomicAdd(g.sync, 1u);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) {      // the last CTA to leave publishes the base of the next launch
+    __threadfence();
+    if (atomicAdd(g.sync + 2, 1u) == (unsigned int)num_workers - 1u) {
+      g.sync[1] = base + (unsigned int)g.num_layers * (unsigned int)num_workers;
+      g.sync[2] = 0u;
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -801,6 +1005,28 @@ int pick_bn(int rows, int cols, int split_k = 0) {
   return best;
 }
 
+
+template <int BN, int CPS>
+int launch_chain(const ChainMaps& maps, const ChainArgs& g, int workers, cudaStream_t st, const char* name) {
+  using Cfg = TileCfg<BN, false, CPS>;
+  constexpr int smem = Cfg::STAGES_ * (int)Cfg::STAGE_BYTES + 512 + 8 * 32 * 36 * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "chain tile configuration does not fit shared memory");
+  auto kern = tc_chain_kernel<BN, CPS>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && CPS == 2) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) {
+      b200_set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+      return (int)e;
+    }
+    done = true;
+  }
+  kern<<<workers, NUM_THREADS, smem, st>>>(maps, g);
+  B200_CHECK_LAUNCH(name);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -885,6 +1111,49 @@ int b200_tc_linear_forward(const float* X, int ldx, const float* W, int ldw, con
     case 64: return launch_tc<NT, 64>(ta, tb, g, 1, st, "tc_forward<64>");
     default: return launch_tc<NT, 32>(ta, tb, g, 1, st, "tc_forward<32>");
   }
+}
+
+
+// A chain of Linear (+ ELU) layers, Y_l = act_l(Y_{l-1} . W_l^T + b_l), in ONE launch (tc_chain_kernel); see include/b200gym.h
+int b200_tc_mlp_forward(const B200MlpLayer* layers, int num_layers, const float* X, int ldx, int M, unsigned int* sync, int max_ctas,
+                        void* stream) {
+  B200_CHECK_ARG(layers && X && sync && M > 0 && num_layers >= 1 && num_layers <= kMaxChain, "b200_tc_mlp_forward: bad argument");
+  ChainMaps maps;
+  ChainArgs g{};
+  g.num_layers = num_layers;
+  g.M = M;
+  g.sync = sync;
+  const float* in = X;
+  int ld_in = ldx, max_n = 0;
+  for (int l = 0; l < num_layers; ++l) {
+    const B200MlpLayer& L = layers[l];
+    B200_CHECK_ARG(L.W && L.Y && L.N > 0 && L.K >= 8, "b200_tc_mlp_forward: layer %d: needs W, Y, N > 0, K >= 8", l);
+    B200_CHECK_ARG(ld_in % 4 == 0 && L.ldw % 4 == 0 && aligned16(in) && aligned16(L.W), "b200_tc_mlp_forward: layer %d: operands need 16-byte rows", l);
+    if (int rc = make_tmap(&maps.a[l], in, M, L.K, ld_in, BM, 0)) return rc;
+    g.layer[l].C = L.Y; g.layer[l].bias = L.bias; g.layer[l].ldc = L.ldy; g.layer[l].N = L.N; g.layer[l].K = L.K; g.layer[l].act = L.act;
+    in = L.Y;
+    ld_in = L.ldy;
+    max_n = L.N > max_n ? L.N : max_n;
+  }
+  // one tile width for the whole chain: 64 columns, two CTAs per SM (the rollout's problems are latency-bound; narrow tiles
+  // give every layer of a 4096-row batch >= 32 tiles); 32 for chains no wider than 32
+  const int bn = max_n <= 32 ? 32 : 64;
+  for (int l = 0; l < num_layers; ++l)
+    if (int rc = make_tmap(&maps.b[l], layers[l].W, layers[l].N, layers[l].K, layers[l].ldw, bn, 0)) return rc;
+  const int m_tiles = (M + BM - 1) / BM;
+  int max_tiles = 1;
+  for (int l = 0; l < num_layers; ++l) {
+    const int t = m_tiles * ((layers[l].N + bn - 1) / bn);
+    max_tiles = t > max_tiles ? t : max_tiles;
+  }
+  // Every CTA of the grid must be RESIDENT (they wait for each other): an SM holds two of these CTAs, so all chain launches
+  // that can run concurrently must together stay within 2 x SMs -- the caller splits that budget with `max_ctas`.
+  cudaStream_t st = (cudaStream_t)stream;
+  int workers = num_sms() * 2;
+  if (max_ctas > 0 && max_ctas < workers) workers = max_ctas;
+  workers = max_tiles < workers ? max_tiles : workers;
+  if (bn == 32) return launch_chain<32, 2>(maps, g, workers, st, "tc_chain<32>");
+  return launch_chain<64, 2>(maps, g, workers, st, "tc_chain<64>");
 }
 
 // dX[M,K] (+)= (dY[M,N] . W[N,K]) * elu'(Yprev);  dbias_prev[K] += column sums of dX (the bias gradient of the layer below)

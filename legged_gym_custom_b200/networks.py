@@ -165,8 +165,26 @@ class Kernels:
                                                   _lib.stream_ptr()))
 
 
-def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M):
-    """run a Linear/ELU chain; hidden activations live in ws under `<tag><i>`; the last layer writes (out, ldo)."""
+CHAIN_MAX_ROWS = 8192      # batches up to this many rows run a whole chain as ONE launch (b200_tc_mlp_forward)
+
+
+def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74):
+    """run a Linear/ELU chain; hidden activations live in ws under `<tag><i>`; the last layer writes (out, ldo).
+    Rollout-sized batches (M <= CHAIN_MAX_ROWS, production kernels) take ONE persistent launch for the whole chain --
+    the CTAs stay resident across the layers and meet at grid-wide barriers -- instead of one GEMM launch per layer;
+    `max_ctas` is this chain's share of the 2 x SMs resident CTAs that concurrently running chains must fit in."""
+    if (k.use_tc and M <= CHAIN_MAX_ROWS and len(layers) <= 8 and ldx % 4 == 0 and X % 16 == 0 and ldo % 4 == 0 and out % 16 == 0
+            and all(lin.K >= 8 for lin in layers)):
+        arr = (_lib.MlpLayer * len(layers))()
+        for i, lin in enumerate(layers):
+            last = i == len(layers) - 1
+            ldy = ldo if last else ceil4(lin.N)
+            Y = out if last else ws.ptr(f"{tag}{i}", M, ldy)
+            arr[i].W, arr[i].bias, arr[i].Y, arr[i].ldw, arr[i].ldy = lin.w(), lin.b(), Y, lin.ldw, ldy
+            arr[i].N, arr[i].K, arr[i].act = lin.N, lin.K, lin.act
+        sync = ws.ptr(f"chain_sync_{tag}", 1, 4)
+        _lib.check(k.lib.b200_tc_mlp_forward(arr, len(layers), X, ldx, M, sync, int(max_ctas), _lib.stream_ptr()))
+        return
     for i, lin in enumerate(layers):
         last = i == len(layers) - 1
         if last:
@@ -355,17 +373,19 @@ class ActorCritic:
             self._ws[M] = Workspace(self.device)
         return self._ws[M]
 
+    # Budgets of the one-launch chains (CTAs; an SM holds two, 296 on a B200): the estimator (100), the two encoders (48 each)
+    # and the critic (74) may run concurrently, then the actor (148) beside the critic -- never more than 270 in flight.
     def fwd_priv(self, ws, X, ldx, out, ldo, M):
-        chain_forward(self.k, self.priv, ws, "p", X, ldx, out, ldo, M)
+        chain_forward(self.k, self.priv, ws, "p", X, ldx, out, ldo, M, max_ctas=48)
 
     def fwd_scan(self, ws, X, ldx, out, ldo, M):
-        chain_forward(self.k, self.scan, ws, "s", X, ldx, out, ldo, M)
+        chain_forward(self.k, self.scan, ws, "s", X, ldx, out, ldo, M, max_ctas=48)
 
     def fwd_actor(self, ws, X, ldx, out, ldo, M):
-        chain_forward(self.k, self.actor, ws, "a", X, ldx, out, ldo, M)
+        chain_forward(self.k, self.actor, ws, "a", X, ldx, out, ldo, M, max_ctas=148)
 
     def fwd_critic(self, ws, X, ldx, out, ldo, M):
-        chain_forward(self.k, self.critic, ws, "c", X, ldx, out, ldo, M)
+        chain_forward(self.k, self.critic, ws, "c", X, ldx, out, ldo, M, max_ctas=74)
 
     def fwd_adapt(self, ws, X, ldx, out, ldo, M, save=False):
         """AdaptationEncoder.forward (support_networks.py:128-175) on obs rows (history = first 520 columns): one fused
@@ -547,7 +567,7 @@ class MlpEstimator:
         return self._ws[M]
 
     def fwd(self, ws, X, ldx, out, ldo, M):
-        chain_forward(self.k, self.layers, ws, "e", X + 4 * self.in_col, ldx, out, ldo, M)
+        chain_forward(self.k, self.layers, ws, "e", X + 4 * self.in_col, ldx, out, ldo, M, max_ctas=100)
 
     def forward(self, obs_with_history):
         M = obs_with_history.shape[0]

@@ -571,3 +571,53 @@ def test_act_and_storage_vs_oracle(precise):
     s = ppo.storage
     ret, adv = lo.compute_returns(s.rewards.cpu(), s.dones.cpu(), s.values.cpu(), ppo.last_values.cpu(), 0.99, 0.95)
     assert torch.equal(s.returns.cpu(), ret) and gu.rel_err(s.advantages.cpu().numpy(), adv.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("M", [4096, 1000, 100])
+def test_mlp_chain_kernel_matches_per_layer_launches(M):
+    """b200_tc_mlp_forward (one persistent launch for a whole Linear / ELU chain, grid-wide barriers between the layers)
+    against one b200_tc_linear_forward launch per layer: the same tcgen05 arithmetic in the same k order -> bit-identical for
+    every layer the per-layer path runs on tcgen05; a 3-wide head (zero-filled weight rows) against fp64 of truncated operands.
+    Launched three times and replayed from a CUDA graph: the barrier epochs advance on the device."""
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M)
+    dims = [572, 256, 128, 3]
+    X = torch.randn(M, dims[0], generator=g).to(DEV)
+    Ws = [(torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5).to(DEV) for i in range(3)]
+    bs = [torch.randn(dims[i + 1], generator=g).to(DEV) for i in range(3)]
+    ld = lambda n: (n + 3) // 4 * 4
+    Ys = [torch.zeros(M, ld(dims[i + 1]), device=DEV) for i in range(3)]
+    ref = [torch.zeros(M, ld(dims[i + 1]), device=DEV) for i in range(2)]
+    st = _lib.stream_ptr()
+    inp, ldi = X, dims[0]
+    for i in range(2):
+        _lib.check(lib.b200_tc_linear_forward(inp.data_ptr(), ldi, Ws[i].data_ptr(), dims[i], bs[i].data_ptr(), ref[i].data_ptr(), ld(dims[i + 1]),
+                                              M, dims[i + 1], dims[i], 1, st))
+        inp, ldi = ref[i], ld(dims[i + 1])
+    arr = (_lib.MlpLayer * 3)()
+    for i in range(3):
+        arr[i].W, arr[i].bias, arr[i].Y, arr[i].ldw, arr[i].ldy = Ws[i].data_ptr(), bs[i].data_ptr(), Ys[i].data_ptr(), dims[i], ld(dims[i + 1])
+        arr[i].N, arr[i].K, arr[i].act = dims[i + 1], dims[i], int(i < 2)
+    sync = torch.zeros(4, dtype=torch.int32, device=DEV)
+    run = lambda: _lib.check(lib.b200_tc_mlp_forward(arr, 3, X.data_ptr(), dims[0], M, sync.data_ptr(), 74, _lib.stream_ptr()))
+    for _ in range(3):
+        for y in Ys:
+            y.zero_()
+        run()
+        torch.cuda.synchronize()
+        assert torch.equal(Ys[0], ref[0]) and torch.equal(Ys[1], ref[1])
+        head = (lo.tf32_trunc(ref[1][:, :128].cpu()).double() @ lo.tf32_trunc(Ws[2].cpu()).double().t() + bs[2].cpu().double()).float()
+        assert scale_err(Ys[2][:, :3], head) <= 2e-5 and float(Ys[2][:, 3:].abs().max()) == 0.0
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            run()
+    for _ in range(3):
+        Ys[2].zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert scale_err(Ys[2][:, :3], head) <= 2e-5
+    per_launch = 3 * min(74, max((M + 127) // 128 * 4, 1))
+    assert int(sync[1].item()) == 7 * per_launch and int(sync[0].item()) == int(sync[1].item()) and int(sync[2].item()) == 0
