@@ -794,9 +794,14 @@ tc_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + acc);
       }
-      // ---- grid barrier, arrive side: all 8 epilogue warps of this CTA have stored this layer's tiles
+      // ---- grid barrier, arrive side: all 8 epilogue warps of this CTA have stored this layer's tiles.  The counter is ONE
+      //      monotonic count of arrivals, so nobody may arrive for layer l before the barrier of layer l - 1 is complete -- a
+      //      CTA without tiles in a layer would otherwise run ahead and its early arrivals would release the others' waits
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (warp == 2 && lane == 0) {
+        const unsigned int prev = (unsigned int)l * (unsigned int)num_workers;
+        while (ld_acquire_gpu_u32(g.sync) - base < prev) {
+        }
         __threadfence();
         atomicAdd(g.sync, 1u);
       }

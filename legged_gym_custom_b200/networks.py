@@ -173,8 +173,7 @@ def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74):
     Rollout-sized batches (M <= CHAIN_MAX_ROWS, production kernels) take ONE persistent launch for the whole chain --
     the CTAs stay resident across the layers and meet at grid-wide barriers -- instead of one GEMM launch per layer;
     `max_ctas` is this chain's share of the 2 x SMs resident CTAs that concurrently running chains must fit in."""
-    if (k.use_tc and M <= CHAIN_MAX_ROWS and len(layers) <= 8 and ldx % 4 == 0 and X % 16 == 0 and ldo % 4 == 0 and out % 16 == 0
-            and all(lin.K >= 8 for lin in layers)):
+    if k.use_tc and M <= CHAIN_MAX_ROWS and len(layers) <= 8 and ldx % 4 == 0 and X % 16 == 0 and all(lin.K >= 8 for lin in layers):
         arr = (_lib.MlpLayer * len(layers))()
         for i, lin in enumerate(layers):
             last = i == len(layers) - 1

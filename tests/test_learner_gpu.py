@@ -219,10 +219,10 @@ def test_tcgen05_pair_pdl_switches_and_launch_trace():
     assert 5e3 < t[0, 1] - t[0, 0] < 5e5                       # tens of microseconds
 
 
-def assert_params_close(mine, ref, move, name):
+def assert_params_close(mine, ref, move, name, max_frac=1e-3):
     d = (mine.cpu() - ref).abs()
     frac = float((d > 0.02 * move).float().mean())
-    assert frac <= 1e-3 and float(d.max()) <= 2.2 * move, (name, frac, float(d.max()), move)
+    assert frac <= max_frac and float(d.max()) <= 2.2 * move, (name, frac, float(d.max()), move)
 
 
 def _build(hid, precise=True):
@@ -352,10 +352,10 @@ def test_production_path_update_on_reference_golden_storage(dagger_first):
     sdo = ac.state_dict()
     for k in orc.main_keys + (orc.adapt_keys if dagger_first else []):
         mine = orc.sd[k].detach() if k != "std" else torch.min(orc.sd[k].detach(), torch.tensor(1.0))
-        assert_params_close(sdo[k], mine, 2e-4 * 4, k)
+        assert_params_close(sdo[k], mine, 2e-4 * 4, k, max_frac=3e-3)      # TF32 on both sides: more near-zero gradients flip sign
     sde = est.state_dict()
     for k in orc.est_keys:
-        assert_params_close(sde[k], orc.sd_est[k].detach(), 1e-4 * 4, k)
+        assert_params_close(sde[k], orc.sd_est[k].detach(), 1e-4 * 4, k, max_frac=3e-3)
 
 
 def test_dagger_then_update_matches_reference_golden():
