@@ -127,6 +127,7 @@ class Kernels:
         self.lib = _lib.lib()
         self.precise = int(precise)
         self.use_tc = bool(use_tc) and not precise
+        self.use_chain = False      # one launch per Linear / ELU chain at rollout sizes (measured slower: networks.CHAIN_MAX_ROWS)
 
     def fwd(self, lin, X, ldx, Y, ldy, M, act=None):
         act = lin.act if act is None else act
@@ -165,15 +166,20 @@ class Kernels:
                                                   _lib.stream_ptr()))
 
 
-CHAIN_MAX_ROWS = 8192      # batches up to this many rows run a whole chain as ONE launch (b200_tc_mlp_forward)
+# One persistent launch for a whole chain (b200_tc_mlp_forward) is OFF: measured on B200 at M = 4096, replayed from CUDA graphs
+# (tools/probe_chain.py): estimator chain 22.8 us as three launches vs 25.9 us as one, actor 34.6 vs 42.7, scan 14.6 vs 19.0 --
+# a kernel boundary inside a graph costs ~2 us, the grid-wide barrier of the chain kernel (atomic + spin through L2) as much,
+# and its one narrow tile shape for all layers is less efficient.  Kernels.use_chain = True switches it on (A/B, tests).
+CHAIN_MAX_ROWS = 8192
 
 
 def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74):
     """run a Linear/ELU chain; hidden activations live in ws under `<tag><i>`; the last layer writes (out, ldo).
-    Rollout-sized batches (M <= CHAIN_MAX_ROWS, production kernels) take ONE persistent launch for the whole chain --
-    the CTAs stay resident across the layers and meet at grid-wide barriers -- instead of one GEMM launch per layer;
+    With `k.use_chain` (off by default, see CHAIN_MAX_ROWS) rollout-sized batches take ONE persistent launch for the whole
+    chain -- the CTAs stay resident across the layers and meet at grid-wide barriers -- instead of one GEMM launch per layer;
     `max_ctas` is this chain's share of the 2 x SMs resident CTAs that concurrently running chains must fit in."""
-    if k.use_tc and M <= CHAIN_MAX_ROWS and len(layers) <= 8 and ldx % 4 == 0 and X % 16 == 0 and all(lin.K >= 8 for lin in layers):
+    if (k.use_tc and getattr(k, "use_chain", False) and M <= CHAIN_MAX_ROWS and len(layers) <= 8 and ldx % 4 == 0 and X % 16 == 0
+            and all(lin.K >= 8 for lin in layers)):
         arr = (_lib.MlpLayer * len(layers))()
         for i, lin in enumerate(layers):
             last = i == len(layers) - 1

@@ -81,15 +81,16 @@ _ROUND = {"trunc": tf32_trunc, "rna": tf32_rna, "fp32": lambda x: x}
 
 
 CHAIN_MAX_ROWS = 8192
+_CHAIN = [False]      # Kernels.use_chain of the product under test (off by default): forward chains as one tcgen05 launch
 
 
 def production_gemm_modes(M, N, K):
     """operand rounding of (forward, dgrad, wgrad) of a Linear [K -> N] on M rows, as legged_gym_custom_b200.networks
     dispatches it with precise=False: tcgen05 when N >= 8 and K >= 8 (wgrad: and M >= 32), else mma.sync; the dgrad of a
-    head with N <= 4 is an fp32 outer product; FORWARD chains of up to CHAIN_MAX_ROWS rows run as one tcgen05 launch
-    (b200_tc_mlp_forward), narrow heads included"""
+    head with N <= 4 is an fp32 outer product; with the optional one-launch chains (b200_tc_mlp_forward) the FORWARD of a
+    narrow head runs on tcgen05 too"""
     tc = N >= 8 and K >= 8
-    fwd = "trunc" if (tc or (K >= 8 and M <= CHAIN_MAX_ROWS)) else "rna"
+    fwd = "trunc" if (tc or (_CHAIN[0] and K >= 8 and M <= CHAIN_MAX_ROWS)) else "rna"
     return (fwd, "trunc" if tc else ("fp32" if N <= 4 else "rna"), "trunc" if (tc and M >= 32) else "rna")
 
 

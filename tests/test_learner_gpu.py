@@ -539,12 +539,15 @@ def test_gradients_match_oracle_full_size(dagger, precise, T=4, N=96):
                 assert fro_err(gsd[k], ref) <= 1e-3 and scale_err(gsd[k], ref) <= 1e-2, (k, fro_err(gsd[k], ref), scale_err(gsd[k], ref))
 
 
-@pytest.mark.parametrize("precise", [True, False], ids=["3xTF32-vs-fp32-oracle", "production-tcgen05-vs-tf32-oracle"])
-def test_act_and_storage_vs_oracle(precise):
+@pytest.mark.parametrize("precise,chain", [(True, False), (False, False), (False, True)],
+                         ids=["3xTF32-vs-fp32-oracle", "production-tcgen05-vs-tf32-oracle", "production+one-launch-chains"])
+def test_act_and_storage_vs_oracle(precise, chain):
     """PPO.act / process_env_step / compute_returns on the GPU vs the oracle (keyed action noise)."""
     hid = dict(actor=[512, 256, 128], critic=[512, 256, 128], priv=[64, 20], scan=[128, 64], est=[256, 128])
     T, N = 3, 200
     ac, est = _build(hid, precise=precise)
+    ac.k.use_chain = est.k.use_chain = chain
+    lo._CHAIN[0] = chain
     ppo = _ppo(ac, est, N, T)
     sd = {k: v.cpu() for k, v in ac.state_dict().items()}
     sd_est = {k: v.cpu() for k, v in est.state_dict().items()}
@@ -568,6 +571,7 @@ def test_act_and_storage_vs_oracle(precise):
         assert torch.equal(ppo.storage.rewards[t, :, 0].cpu(), ref_r)
     ppo.compute_returns(st["critic_obs"][0].to(DEV))
     torch.cuda.synchronize()
+    lo._CHAIN[0] = False
     s = ppo.storage
     ret, adv = lo.compute_returns(s.rewards.cpu(), s.dones.cpu(), s.values.cpu(), ppo.last_values.cpu(), 0.99, 0.95)
     assert torch.equal(s.returns.cpu(), ret) and gu.rel_err(s.advantages.cpu().numpy(), adv.numpy()) <= 1e-5
