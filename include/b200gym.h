@@ -333,8 +333,8 @@ int b200_post_physics_step(B200Env* env, const B200EnvBuffers* bufs, int64_t com
  * bit 1 = extras_kernel (episode means / time_outs over the envs that reset).  parts = 3 is b200_post_physics_step. */
 int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, int parts, void* stream);
 
-/* Same, with `common_step_counter` kept in DEVICE memory: the call increments *step_counter_dev and then uses
- * it, so a captured CUDA graph of the rollout replays with advancing step numbers. */
+/* Same, with `common_step_counter` kept in DEVICE memory: the step's kernels use *step_counter_dev + 1 and the last
+ * launch of the call stores the increment, so a captured CUDA graph of the rollout replays with advancing step numbers. */
 int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream);
 int b200_counter_add(int64_t* counter_dev, int64_t delta, void* stream);
 

@@ -31,7 +31,8 @@ constexpr int kHistPerThread = 5;   // 8 envs x 130 vectors = 1040 <= 5 x 224
 static_assert(B200_TERM_PARTS == kEnvsPerCta, "one reward-term part per warp");
 static_assert(kEnvsPerCta * (B200_NUM_BODIES + B200_NUM_DOF + 1) <= kEnvsPerCta * 32, "item pass 1 must fit the CTA");
 
-// `step_dev` != nullptr: the step counter lives in device memory (CUDA-graph replay); else `step` is used.
+// `step_dev` != nullptr: the step counter lives in device memory (CUDA-graph replay) and `step` is an offset to it (1: the
+// counter is advanced AFTER the step's kernels, by extras_kernel); else `step` is the counter.
 //
 // Phases of a CTA (8 envs, 8 warps; every phase ends with __syncthreads):
 //   A   warp w: load env w's small rows, height scan (stage 0 / 1 of env_core.cuh)
@@ -53,7 +54,7 @@ post_physics_kernel(const __grid_constant__ B200EnvParams P, const __grid_consta
   if (threadIdx.x < P.num_scan) scan_point(P, threadIdx.x, &pt_x[threadIdx.x], &pt_y[threadIdx.x]);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + B200_MAX_PROPRIO) env_tables_fill(P, T, threadIdx.x - 64);
   __syncthreads();
-  if (step_dev) step = *step_dev;
+  if (step_dev) step += *step_dev;
   // `dry`: the probe pass of a command curriculum (launched only when P.command_curriculum): an ordinary step ends here
   if (dry && step % P.max_episode_length != 0) return;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -226,7 +227,7 @@ post_physics_tile_kernel(const __grid_constant__ B200EnvParams P, const __grid_c
   }
   if (t < P.num_scan) scan_point(P, t, &pt_x[t], &pt_y[t]);
   if (t >= 64 && t < 64 + B200_MAX_PROPRIO) env_tables_fill<TileScratch>(P, T, t - 64);
-  if (step_dev) step = *step_dev;
+  if (step_dev) step += *step_dev;
 #define B200_TRACE(slot)                                                                          \
   if (trace && t == 0) {                                                                          \
     unsigned long long t_;                                                                        \
@@ -514,10 +515,12 @@ __device__ T cta_sum_256(T v, T* smem) {
 // extras["episode"]["terrain_level"] = mean(terrain_levels), extras["time_outs"] = time_out_buf --
 // all only when at least one env reset this step (go2.py:214-215, :246-263).
 __global__ void __launch_bounds__(256)
-extras_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B) {
+extras_kernel(const __grid_constant__ B200EnvParams P, const __grid_constant__ B200EnvBuffers B, int64_t* __restrict__ step_dev) {
   __shared__ float fsm[256];
   __shared__ int ism[256];
   const int k = blockIdx.x, T = B200_NUM_REWARD_TERMS, N = P.num_envs;
+  // device-resident step counter (go2.py:355): the step's kernels ran with counter + 1, the last launch of the step commits it
+  if (step_dev && k == 0 && threadIdx.x == 0) *step_dev += 1;
   int cnt = 0;
   float acc = 0.0f;
   // thread t owns envs [16 t, 16 t + 16) of every 4096-env chunk: the 16 reset flags arrive as one 16-byte load and only
@@ -714,7 +717,7 @@ command_curriculum_kernel(const __grid_constant__ B200EnvParams P, const __grid_
                           const int64_t* __restrict__ step_dev) {
   __shared__ double dsm[256];
   __shared__ int ism[256];
-  if (step_dev) step = *step_dev;
+  if (step_dev) step += *step_dev;
   double* cr = B.command_ranges;
   if (threadIdx.x == 0) {
     cr[0] = cr[2];
@@ -778,7 +781,7 @@ int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64
     B200_CHECK_LAUNCH("post_physics_kernel");
   }
   if (parts & 2) {
-    extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+    extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs, nullptr);
     B200_CHECK_LAUNCH("extras_kernel");
   }
   return 0;
@@ -802,13 +805,14 @@ int b200_counter_add(int64_t* counter, int64_t delta, void* stream) {
 int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream) {
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step_dev")) return rc;
   B200_CHECK_ARG(step_counter_dev, "b200_post_physics_step_dev: null counter");
-  counter_add_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev, 1);       // go2.py:355
+  // go2.py:355: every kernel of the step reads counter + 1; extras_kernel, the last launch, stores the increment (one launch
+  // fewer on the rollout's critical path than a counter kernel in front)
   if (int rc = post_physics_attr()) return rc;
   if (env->p.command_curriculum)
-    if (int rc = launch_command_curriculum(env, bufs, 0, step_counter_dev, (cudaStream_t)stream)) return rc;
-  if (int rc = launch_post_physics(env, bufs, 0, step_counter_dev, (cudaStream_t)stream)) return rc;
+    if (int rc = launch_command_curriculum(env, bufs, 1, step_counter_dev, (cudaStream_t)stream)) return rc;
+  if (int rc = launch_post_physics(env, bufs, 1, step_counter_dev, (cudaStream_t)stream)) return rc;
   B200_CHECK_LAUNCH("post_physics_kernel");
-  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs, step_counter_dev);
   B200_CHECK_LAUNCH("extras_kernel");
   return 0;
 }
@@ -817,7 +821,7 @@ int b200_reset_all(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step
   if (int rc = check_bufs(env, bufs, "b200_reset_all")) return rc;
   reset_all_kernel<<<(env->p.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->p, *bufs, common_step_counter, init_done);
   B200_CHECK_LAUNCH("reset_all_kernel");
-  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs);
+  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs, nullptr);
   B200_CHECK_LAUNCH("extras_kernel");
   return 0;
 }

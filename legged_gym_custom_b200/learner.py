@@ -312,10 +312,15 @@ class PPO:
                 segs.append((_p(critic_obs), critic_obs.stride(0), _p(s.critic_observations[t]), s.ld_crit, s.d_crit))
             elif not s.alias_critic_rows:
                 segs.append((_p(privileged_obs), privileged_obs.stride(0), _p(s._priv[t]), s.ld_priv, s.d_priv))
+            # in place, the latent encoder reads the privileged columns of the storage row: it goes first and the copy of the
+            # proprioceptive columns (needed by the actor's first layer only) follows it
+            first_priv = in_place and not adaptation_mode
+            if first_priv:
+                ac.fwd_priv(ws, _p(s._priv[t]), s.ld_priv, _p(x, ac.col_latent), ld, N)
             self._copy_segments(segs, N)
             if adaptation_mode:
                 ac.fwd_adapt(ws, _p(x), ld, _p(x, ac.col_latent), ld, N)
-            else:
+            elif not first_priv:
                 ac.fwd_priv(ws, _p(s._priv[t]), s.ld_priv, _p(x, ac.col_latent), ld, N)
         with self._on(s_scan):
             ac.fwd_scan(ws, _p(scan_obs), scan_obs.stride(0), _p(x, ac.col_scan), ld, N)
