@@ -457,7 +457,9 @@ int b200_gather_bytes(const uint8_t* src, const int64_t* idx, uint8_t* dst, int6
 int b200_sample_actions(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t step, float* actions, float* logp,
                         float* mu_out, float* sigma_out, int N, int A, void* stream);
 
-/* Same with the noise step counter in device memory (read, then incremented by the call). */
+/* Same with the noise step counter in device memory: `step_counter_dev` points at TWO int64 words -- [0] the counter (read by
+ * the launch, then incremented by its last CTA), [1] a ticket word the caller zero-initialises once and the kernel leaves at
+ * zero.  One launch; replays of a captured graph advance the counter. */
 int b200_sample_actions_dev(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t* step_counter_dev, float* actions,
                             float* logp, float* mu_out, float* sigma_out, int N, int A, void* stream);
 

@@ -91,15 +91,20 @@ gather_bytes_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__
 }
 
 // actions ~ Normal(mu, std): z from two keyed uniforms (Box-Muller); log_prob summed over actions.
+// 16 lanes per env (one per action, A <= 16), 16 envs per CTA: coalesced rows, the per-env log-prob is summed by the group's
+// first lane in action order (the order of the serial loop this replaces, so the bits do not change).
+// `step_dev` != nullptr: [0] = the noise step counter in device memory, [1] = a ticket the kernel keeps at zero: the LAST CTA
+// to finish (every CTA has read the counter by then) advances the counter -- no separate counter launch.
+constexpr int kSampleEnvsPerCta = 16;
 __global__ void __launch_bounds__(256)
 sample_actions_kernel(const float* __restrict__ mu, int ldmu, const float* __restrict__ std, uint64_t seed, uint32_t step,
-                      const int64_t* __restrict__ step_dev, float* __restrict__ actions, float* __restrict__ logp,
+                      int64_t* __restrict__ step_dev, float* __restrict__ actions, float* __restrict__ logp,
                       float* __restrict__ mu_out, float* __restrict__ sigma_out, int N, int A) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= N) return;
-  if (step_dev) step = (uint32_t)*step_dev;
-  float lp = 0.0f;
-  for (int a = 0; a < A; ++a) {
+  const int a = threadIdx.x & 15;
+  const int e = blockIdx.x * kSampleEnvsPerCta + (threadIdx.x >> 4);
+  if (step_dev) step = (uint32_t)*reinterpret_cast<const volatile int64_t*>(step_dev);
+  float term = 0.0f;
+  if (e < N && a < A) {
     const float u1 = ((float)(keyed_u32(seed, SITE_ACTION_NOISE, step, e, 2 * a) >> 8) + 0.5f) * 5.9604644775390625e-08f;
     const float u2 = u32_to_uniform(keyed_u32(seed, SITE_ACTION_NOISE, step, e, 2 * a + 1));
     const float z = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
@@ -109,9 +114,23 @@ sample_actions_kernel(const float* __restrict__ mu, int ldmu, const float* __res
     if (mu_out) mu_out[(int64_t)e * A + a] = m;
     if (sigma_out) sigma_out[(int64_t)e * A + a] = s;
     const float d = act - m;
-    lp += -(d * d) / (2.0f * s * s) - logf(s) - 0.9189385332046727f;
+    term = -(d * d) / (2.0f * s * s) - logf(s) - 0.9189385332046727f;
   }
-  logp[e] = lp;
+  const int base = threadIdx.x & 16;           // first lane of this env's group within the warp
+  float lp = 0.0f;
+  for (int i = 0; i < A; ++i) lp += __shfl_sync(0xffffffffu, term, base + i);
+  if (e < N && a == 0) logp[e] = lp;
+  if (step_dev) {
+    __syncthreads();                           // every thread of the CTA has read the counter
+    if (threadIdx.x == 0) {
+      unsigned long long* ticket = reinterpret_cast<unsigned long long*>(step_dev + 1);
+      __threadfence();
+      if (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        *ticket = 0ull;
+        *step_dev += 1;
+      }
+    }
+  }
 }
 
 typedef B200PpoLossArgs PpoLossArgs;
@@ -615,25 +634,20 @@ int b200_gather_bytes(const uint8_t* src, const int64_t* idx, uint8_t* dst, int6
 int b200_sample_actions(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t step, float* actions, float* logp,
                         float* mu_out, float* sigma_out, int N, int A, void* stream) {
   B200_CHECK_ARG(mu && std && actions && logp && N > 0 && A > 0 && A <= 16 && ldmu >= A, "b200_sample_actions: bad argument");
-  sample_actions_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, seed, (uint32_t)step, nullptr, actions, logp,
-                                                                         mu_out, sigma_out, N, A);
+  sample_actions_kernel<<<(N + kSampleEnvsPerCta - 1) / kSampleEnvsPerCta, 256, 0, (cudaStream_t)stream>>>(
+      mu, ldmu, std, seed, (uint32_t)step, nullptr, actions, logp, mu_out, sigma_out, N, A);
   B200_CHECK_LAUNCH("sample_actions_kernel");
   return 0;
 }
 
-__global__ void counter_inc_kernel(int64_t* c) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1;
-}
-
-// same, with the noise step counter in device memory; the call increments it afterwards (CUDA-graph replay)
+// same, with the noise step counter in device memory: step_counter_dev[0] is read, then incremented by the kernel's last CTA;
+// step_counter_dev[1] is the kernel's ticket word (zero-initialised by the caller, left at zero by every launch)
 int b200_sample_actions_dev(const float* mu, int ldmu, const float* std, uint64_t seed, int64_t* step_counter_dev, float* actions,
                             float* logp, float* mu_out, float* sigma_out, int N, int A, void* stream) {
   B200_CHECK_ARG(mu && std && actions && logp && step_counter_dev && N > 0 && A > 0 && A <= 16 && ldmu >= A, "b200_sample_actions_dev: bad argument");
-  sample_actions_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mu, ldmu, std, seed, 0, step_counter_dev, actions, logp, mu_out,
-                                                                         sigma_out, N, A);
+  sample_actions_kernel<<<(N + kSampleEnvsPerCta - 1) / kSampleEnvsPerCta, 256, 0, (cudaStream_t)stream>>>(
+      mu, ldmu, std, seed, 0, step_counter_dev, actions, logp, mu_out, sigma_out, N, A);
   B200_CHECK_LAUNCH("sample_actions_kernel");
-  counter_inc_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter_dev);
-  B200_CHECK_LAUNCH("counter_inc_kernel");
   return 0;
 }
 

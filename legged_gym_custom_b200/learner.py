@@ -209,7 +209,7 @@ class PPO:
         from .dist import enable_fused_dist_adam
         self.dist_mode = enable_fused_dist_adam([ac.main, ac.adapt, estimator.group], process_group, max_grad_norm)
         self._perm_gen = torch.Generator(device=self.device).manual_seed(seed + 12345)
-        self.act_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.act_counter_dev = torch.zeros(2, dtype=torch.int64, device=self.device)     # [counter, the kernel's ticket word]
         self.use_device_counter = False
         self.use_graphs = False
         self.use_streams = True
@@ -598,7 +598,7 @@ class PPO:
 
     # ---- CUDA graphs: a minibatch is ~90 launches with fixed pointers -> capture once per minibatch slot, replay ----
     def set_device_counter(self, enabled=True):
-        self.act_counter_dev.fill_(self.act_counter)
+        self.act_counter_dev[0:1].fill_(self.act_counter)
         self.use_device_counter = bool(enabled)
 
     def _run_captured(self, key, fn):
