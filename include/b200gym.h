@@ -336,6 +336,9 @@ int b200_post_physics_step_parts(B200Env* env, const B200EnvBuffers* bufs, int64
 /* Same, with `common_step_counter` kept in DEVICE memory: the step's kernels use *step_counter_dev + 1 and the last
  * launch of the call stores the increment, so a captured CUDA graph of the rollout replays with advancing step numbers. */
 int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream);
+/* The same split into its two kernels (`parts` as in b200_post_physics_step_parts): bit 1 (extras_kernel, which also commits
+ * the counter) may be launched on another stream, ordered after bit 0 and before the next step's bit 0. */
+int b200_post_physics_step_dev_parts(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, int parts, void* stream);
 int b200_counter_add(int64_t* counter_dev, int64_t delta, void* stream);
 
 /* Replaces BaseTask.reset's reset_idx(arange(N)) (base_task.py:131-135): resets every env

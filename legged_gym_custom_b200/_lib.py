@@ -23,6 +23,7 @@ SYMBOLS = {
     "b200_post_physics_step": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_void_p]),
     "b200_post_physics_step_parts": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_int, C.c_void_p]),
     "b200_post_physics_step_dev": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_void_p]),
+    "b200_post_physics_step_dev_parts": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p, C.c_int, C.c_void_p]),
     "b200_counter_add": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "b200_reset_all": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_int64, C.c_int, C.c_void_p]),
     "b200_get_heights": (C.c_int, [C.c_void_p, C.POINTER(EnvBuffers), C.c_void_p]),
@@ -110,7 +111,7 @@ class PpoLossArgs(C.Structure):
 _lib = None
 
 # kernels launched per ABI call (for bench.py's `gpu_launches` and per-kernel timing)
-LAUNCHES = {"b200_tc_mlp_forward": 1, "b200_post_physics_step": 2, "b200_post_physics_step_dev": 3, "b200_sample_actions_dev": 2, "b200_tc_linear_wgrad": 1, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
+LAUNCHES = {"b200_tc_mlp_forward": 1, "b200_post_physics_step": 2, "b200_post_physics_step_dev": 2, "b200_tc_linear_wgrad": 1, "b200_reset_all": 2, "b200_compute_returns": 2, "b200_clip_adam": 3}
 
 
 class _Proxy:

@@ -802,19 +802,27 @@ int b200_counter_add(int64_t* counter, int64_t delta, void* stream) {
   return 0;
 }
 
-int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream) {
+int b200_post_physics_step_dev_parts(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, int parts, void* stream) {
   if (int rc = check_bufs(env, bufs, "b200_post_physics_step_dev")) return rc;
   B200_CHECK_ARG(step_counter_dev, "b200_post_physics_step_dev: null counter");
   // go2.py:355: every kernel of the step reads counter + 1; extras_kernel, the last launch, stores the increment (one launch
   // fewer on the rollout's critical path than a counter kernel in front)
-  if (int rc = post_physics_attr()) return rc;
-  if (env->p.command_curriculum)
-    if (int rc = launch_command_curriculum(env, bufs, 1, step_counter_dev, (cudaStream_t)stream)) return rc;
-  if (int rc = launch_post_physics(env, bufs, 1, step_counter_dev, (cudaStream_t)stream)) return rc;
-  B200_CHECK_LAUNCH("post_physics_kernel");
-  extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs, step_counter_dev);
-  B200_CHECK_LAUNCH("extras_kernel");
+  if (parts & 1) {
+    if (int rc = post_physics_attr()) return rc;
+    if (env->p.command_curriculum)
+      if (int rc = launch_command_curriculum(env, bufs, 1, step_counter_dev, (cudaStream_t)stream)) return rc;
+    if (int rc = launch_post_physics(env, bufs, 1, step_counter_dev, (cudaStream_t)stream)) return rc;
+    B200_CHECK_LAUNCH("post_physics_kernel");
+  }
+  if (parts & 2) {
+    extras_kernel<<<B200_NUM_REWARD_TERMS + 1, 256, 0, (cudaStream_t)stream>>>(env->p, *bufs, step_counter_dev);
+    B200_CHECK_LAUNCH("extras_kernel");
+  }
   return 0;
+}
+
+int b200_post_physics_step_dev(B200Env* env, const B200EnvBuffers* bufs, int64_t* step_counter_dev, void* stream) {
+  return b200_post_physics_step_dev_parts(env, bufs, step_counter_dev, 3, stream);
 }
 
 int b200_reset_all(B200Env* env, const B200EnvBuffers* bufs, int64_t common_step_counter, int init_done, void* stream) {

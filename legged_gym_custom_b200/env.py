@@ -128,6 +128,10 @@ class Go2Env:
         self.max_episode_length = float(np.ceil(self.max_episode_length_s / self.dt))
         self.common_step_counter = 0
         self.step_counter_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # set by a caller that consumes `extras` (time_outs, episode sums) on that stream or after wait_extras() only
+        # (runner.OnPolicyRunner: the critic / bookkeeping stream of its PPO); None: everything on the current stream
+        self.extras_stream = None
+        self._extras_done = None
         self.use_device_counter = False        # True: common_step_counter lives on the device (CUDA-graph replay of the rollout)
         self.init_done = False
         self.reward_names = p.reward_names()
@@ -173,7 +177,21 @@ class Go2Env:
             self.physx.simulate(self, k)
         self.physx.refresh(self)
         self.common_step_counter += 1
-        if self.use_device_counter:
+        if self.use_device_counter and self.extras_stream is not None:
+            # the episode statistics / time-out copy (extras_kernel, which also commits the device step counter) leave the
+            # critical path: launched on `extras_stream` behind the per-env kernel; the NEXT step's per-env kernel waits for it
+            ctr = C.c_void_p(self.step_counter_dev.data_ptr())
+            if self._extras_done is not None:
+                torch.cuda.current_stream().wait_event(self._extras_done)
+            _lib.check(self.lib.b200_post_physics_step_dev_parts(self._handle, C.byref(b.struct), ctr, 1, st))
+            ev = torch.cuda.Event()
+            ev.record()
+            self.extras_stream.wait_event(ev)
+            with torch.cuda.stream(self.extras_stream):
+                _lib.check(self.lib.b200_post_physics_step_dev_parts(self._handle, C.byref(b.struct), ctr, 2, _lib.stream_ptr()))
+                self._extras_done = torch.cuda.Event()
+                self._extras_done.record()
+        elif self.use_device_counter:
             _lib.check(self.lib.b200_post_physics_step_dev(self._handle, C.byref(b.struct), C.c_void_p(self.step_counter_dev.data_ptr()), st))
         else:
             _lib.check(self.lib.b200_post_physics_step(self._handle, C.byref(b.struct), self.common_step_counter, st))
@@ -182,8 +200,15 @@ class Go2Env:
                 b["rew_buf"], b["reset_buf"], self.extras)
 
     def set_device_counter(self, enabled=True):
+        self.wait_extras()
         self.step_counter_dev.fill_(self.common_step_counter)
         self.use_device_counter = bool(enabled)
+
+    def wait_extras(self):
+        """order the current stream after the last step's extras launch (only needed with `extras_stream`)"""
+        if self._extras_done is not None:
+            torch.cuda.current_stream().wait_event(self._extras_done)
+            self._extras_done = None
 
     @property
     def supports_output_binding(self):

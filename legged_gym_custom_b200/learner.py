@@ -223,6 +223,12 @@ class PPO:
         self.offload_wgrads = False
         self.defer_critic_join = False      # act(): leave the critic chain running until process_env_step (OnPolicyRunner sets it)
         self._pending_critic = None
+        # `defer_store` (OnPolicyRunner sets it): process_env_step() runs on the critic's stream, so neither the critic chain
+        # nor the bookkeeping sits on the rollout's critical path; act() makes the main stream wait for it only AFTER the next
+        # actor chain is queued (before the caller's env.step can overwrite the env's reward / flag buffers)
+        self.defer_store = False
+        self._store_done = None
+        self.critic_fork_after = 1      # actor layer index the critic chain is forked behind when the store is deferred (-1: beside the actor)
         self._graphs, self._graph_calls = {}, {}
 
     @property
@@ -327,8 +333,13 @@ class PPO:
         mu = ws.get("mu", N, s.d_act)
         with self._on(s_hi):
             self._join([s_lat, s_scan])
-            self._fork_onto([s_crit])                     # the critic's big first layer must not take the SMs before this point
-            ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N)
+            # the critic's big first layer must not take the SMs before this point; with a deferred store nothing on the
+            # main stream waits for the critic, so it starts behind the actor's wide layers instead of beside them
+            late = self.defer_store and self.defer_critic_join and s_crit is not None and self.critic_fork_after >= 0
+            if not late:
+                self._fork_onto([s_crit])
+            ac.fwd_actor(ws, _p(x), ld, _p(mu), s.d_act, N,
+                         after=(min(self.critic_fork_after, len(ac.actor) - 1), lambda: self._fork_onto([s_crit])) if late else None)
         with self._on(s_crit):
             if s.alias_critic_rows:
                 if not in_place and s_lat is not None:    # the row copy above rides on the latent stream
@@ -361,20 +372,38 @@ class PPO:
                                                     _p(s.actions_log_prob[t]), _p(s.mu[t]), _p(s.sigma[t]), N, s.d_act, _lib.stream_ptr()))
         self.act_counter += 1
         self.transition.actions, self.transition.values = s.actions[t], s.values[t]
+        self._wait_store()              # the caller's env.step may overwrite what the previous step's deferred store reads
         return s.actions[t]
+
+    def bookkeeping_stream(self):
+        """the stream the critic chain and (with `defer_store`) process_env_step run on; None without side streams"""
+        return self._fork(4)[3]
+
+    def _wait_store(self):
+        if self._store_done is not None:
+            torch.cuda.current_stream().wait_event(self._store_done)
+            self._store_done = None
 
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:156-171: time-out bootstrap + scalar part of add_transitions."""
         s = self.storage
         t = s.step
-        if self._pending_critic is not None:              # values[t] (time-out bootstrap below) come from the critic's stream
+        side = self._pending_critic if self.defer_store else None
+        if self._pending_critic is not None and side is None:   # values[t] (time-out bootstrap below) come from the critic's stream
             self._join([self._pending_critic])
-            self._pending_critic = None
+        self._pending_critic = None
         tmo = infos["time_outs"] if "time_outs" in infos else None
         rewards, dones, tmo = self._as_step_scalars(rewards, dones, tmo)
         p = lambda x: C.c_void_p(x.data_ptr())
-        _lib.check(self.lib.b200_store_step_scalars(p(rewards), p(dones), p(tmo) if tmo is not None else None, p(s.values[t]), self.gamma,
-                                                    p(s.rewards[t]), p(s.dones[t]), s.num_envs, _lib.stream_ptr()))
+        if side is not None:
+            self._wait_store()
+            self._fork_onto([side])                          # the env step's outputs are queued on the main stream
+        with self._on(side):
+            _lib.check(self.lib.b200_store_step_scalars(p(rewards), p(dones), p(tmo) if tmo is not None else None, p(s.values[t]),
+                                                        self.gamma, p(s.rewards[t]), p(s.dones[t]), s.num_envs, _lib.stream_ptr()))
+            if side is not None:
+                self._store_done = torch.cuda.Event()
+                self._store_done.record()
         s.step += 1
         self.transition.clear()
 
@@ -402,6 +431,7 @@ class PPO:
     def compute_returns(self, last_critic_obs):
         """ppo.py:174-179."""
         s, ac = self.storage, self.actor_critic
+        self._wait_store()
         x = _rows16(last_critic_obs)
         ac.fwd_critic(self.roll_ws, _p(x), x.stride(0), _p(self.last_values), 1, s.num_envs)
         s.compute_returns(self.last_values, self.gamma, self.lam)
@@ -619,6 +649,7 @@ class PPO:
 
     def update(self):
         """ppo.py:182-293 -> (value_loss, surrogate_loss, reg_loss, reg_coef, estimator_loss)."""
+        self._wait_store()
         indices = torch.randperm(self.num_mini_batches * self.mb, device=self.device, generator=self._perm_gen)
         return self.update_with_indices(indices)
 
@@ -658,6 +689,7 @@ class PPO:
         self._adam(ac.adapt)
 
     def update_dagger(self):
+        self._wait_store()
         indices = torch.randperm(self.num_mini_batches * self.mb, device=self.device, generator=self._perm_gen)
         return self.update_dagger_with_indices(indices)
 

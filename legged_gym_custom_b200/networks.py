@@ -173,7 +173,7 @@ class Kernels:
 CHAIN_MAX_ROWS = 8192
 
 
-def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74):
+def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74, after=None):
     """run a Linear/ELU chain; hidden activations live in ws under `<tag><i>`; the last layer writes (out, ldo).
     With `k.use_chain` (off by default, see CHAIN_MAX_ROWS) rollout-sized batches take ONE persistent launch for the whole
     chain -- the CTAs stay resident across the layers and meet at grid-wide barriers -- instead of one GEMM launch per layer;
@@ -199,6 +199,8 @@ def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74):
             Y = ws.ptr(f"{tag}{i}", M, ldy)
         k.fwd(lin, X, ldx, Y, ldy, M)
         X, ldx = Y, ldy
+        if after is not None and after[0] == i:       # (layer index, callback): e.g. fork another stream behind this layer
+            after[1]()
 
 
 def chain_backward(k, layers, ws, tag, X0, ldx0, dOut, lddo, M, need_dx0=False, dX0=None, lddx0=0, wgrad_on=None):
@@ -386,8 +388,8 @@ class ActorCritic:
     def fwd_scan(self, ws, X, ldx, out, ldo, M):
         chain_forward(self.k, self.scan, ws, "s", X, ldx, out, ldo, M, max_ctas=48)
 
-    def fwd_actor(self, ws, X, ldx, out, ldo, M):
-        chain_forward(self.k, self.actor, ws, "a", X, ldx, out, ldo, M, max_ctas=148)
+    def fwd_actor(self, ws, X, ldx, out, ldo, M, after=None):
+        chain_forward(self.k, self.actor, ws, "a", X, ldx, out, ldo, M, max_ctas=148, after=after)
 
     def fwd_critic(self, ws, X, ldx, out, ldo, M):
         chain_forward(self.k, self.critic, ws, "c", X, ldx, out, ldo, M, max_ctas=74)

@@ -52,6 +52,9 @@ class OnPolicyRunner:
             from .dist import broadcast_parameters
             broadcast_parameters([actor_critic.main, actor_critic.adapt, estimator.group], process_group)
         self.alg.defer_critic_join = True      # every act() of this runner is followed by process_env_step()
+        self.alg.defer_store = True            # ... so its bookkeeping may ride on the critic's stream (learner.PPO.defer_store)
+        if hasattr(env, "extras_stream"):      # and the env's episode statistics / time-out copy with it (Go2Env.extras_stream)
+            env.extras_stream = self.alg.bookkeeping_stream()
         self.dagger_update_freq = ac_["dagger_update_freq"]
         self.num_steps_per_env, self.save_interval = self.cfg["num_steps_per_env"], self.cfg["save_interval"]
         # an env that can write its observation rows anywhere (Go2Env with alias_outputs) writes them straight into the
@@ -163,6 +166,8 @@ class OnPolicyRunner:
                 self._cur_rew.masked_fill_(done, 0.0)
                 self._cur_len.masked_fill_(done, 0.0)
         alg.compute_returns(crit)
+        if hasattr(env, "wait_extras"):
+            env.wait_extras()
 
     def iteration(self, it):
         use_adaptation_mode = it % self.dagger_update_freq == 0
