@@ -86,11 +86,11 @@ _CHAIN = [False]      # Kernels.use_chain of the product under test (off by defa
 
 def production_gemm_modes(M, N, K):
     """operand rounding of (forward, dgrad, wgrad) of a Linear [K -> N] on M rows, as legged_gym_custom_b200.networks
-    dispatches it with precise=False: tcgen05 when N >= 8 and K >= 8 (wgrad: and M >= 32), else mma.sync; the dgrad of a
-    head with N <= 4 is an fp32 outer product; with the optional one-launch chains (b200_tc_mlp_forward) the FORWARD of a
-    narrow head runs on tcgen05 too"""
+    dispatches it with precise=False: tcgen05 when N >= 8 and K >= 8 (wgrad: and M >= 32), else mma.sync; the forward and
+    the dgrad of a head with N <= 4 are fp32 dot / outer products; with the optional one-launch chains (b200_tc_mlp_forward)
+    the FORWARD of a narrow head runs on tcgen05 instead"""
     tc = N >= 8 and K >= 8
-    fwd = "trunc" if (tc or (_CHAIN[0] and K >= 8 and M <= CHAIN_MAX_ROWS)) else "rna"
+    fwd = "trunc" if (tc or (_CHAIN[0] and K >= 8 and M <= CHAIN_MAX_ROWS)) else ("fp32" if N <= 4 else "rna")
     return (fwd, "trunc" if tc else ("fp32" if N <= 4 else "rna"), "trunc" if (tc and M >= 32) else "rna")
 
 

@@ -308,17 +308,34 @@ def test_tcgen05_operands_are_truncated_tf32():
 
 
 def test_mma_sync_heads_round_to_nearest():
-    """the other half of numerics('tf32'): layers narrower than 8 run on mma.sync with cvt.rna operands"""
+    """the other half of numerics('tf32'): layers 5..7 wide run on mma.sync with cvt.rna operands; heads with N <= 4 are
+    streaming fp32 dot products (small_n_forward_kernel), exact to fp32 summation order"""
     lib = _lib.lib()
-    for (M, N, K) in ((512, 1, 128), (512, 3, 128)):
+    for (M, N, K) in ((512, 6, 128), (512, 7, 64)):
         g = torch.Generator().manual_seed(3)
         X, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
-        Xd, Wd, Y = X.to(DEV), W.to(DEV), torch.zeros(M, 4, device=DEV)
-        _lib.check(lib.b200_linear_forward(Xd.data_ptr(), K, Wd.data_ptr(), K, None, Y.data_ptr(), 4, M, N, K, 0, 0, _lib.stream_ptr()))
+        Xd, Wd, Y = X.to(DEV), W.to(DEV), torch.zeros(M, 8, device=DEV)
+        _lib.check(lib.b200_linear_forward(Xd.data_ptr(), K, Wd.data_ptr(), K, None, Y.data_ptr(), 8, M, N, K, 0, 0, _lib.stream_ptr()))
         torch.cuda.synchronize()
         e_r = scale_err(Y[:, :N], (lo.tf32_rna(X).double() @ lo.tf32_rna(W).double().t()).float())
         e_t = scale_err(Y[:, :N], (lo.tf32_trunc(X).double() @ lo.tf32_trunc(W).double().t()).float())
         assert e_r <= 2e-5 and e_t >= 10 * e_r, (e_r, e_t)
+    for (M, N, K, ldx, act) in ((512, 1, 128, 128, 0), (4096, 3, 128, 132, 0), (333, 4, 70, 72, 1), (1, 2, 9, 12, 0)):
+        g = torch.Generator().manual_seed(5)
+        ldw = (K + 3) // 4 * 4
+        X, Wp, b = torch.randn(M, ldx, generator=g), torch.randn(N, ldw, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+        W = Wp[:, :K]
+        Xd, Wd, bd, Y = X.to(DEV), Wp.to(DEV), b.to(DEV), torch.full((M, 4), 7.0, device=DEV)
+        _lib.check(lib.b200_linear_forward(Xd.data_ptr(), ldx, Wd.data_ptr(), ldw, bd.data_ptr(), Y.data_ptr(), 4, M, N, K, act, 0,
+                                           _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = X[:, :K].double() @ W.double().t() + b.double()
+        if act:
+            ref = torch.where(ref > 0, ref, torch.expm1(ref))
+        assert scale_err(Y[:, :N], ref.float()) <= 2e-6, (M, N, K)
+        assert (Y[:, N:] == 7.0).all()                      # columns beyond N are not touched
+        e_r = scale_err(Y[:, :N], (lo.tf32_rna(X[:, :K]).double() @ lo.tf32_rna(W).double().t() + b.double()).float())
+        assert act or e_r >= 1e-5
 
 
 @pytest.mark.parametrize("dagger_first", [False, True], ids=["update", "dagger-then-update"])

@@ -129,11 +129,11 @@ def test_tf32_numerics_mode():
     assert (t.abs() <= x.abs()).all() and ((t - x).abs() / x.abs()).max() < 2.0 ** -10
     assert ((r - x).abs() / x.abs()).max() <= 2.0 ** -11 and float((t != r).float().mean()) > 0.3
     assert lo.production_gemm_modes(24576, 512, 627) == ("trunc", "trunc", "trunc")
-    assert lo.production_gemm_modes(24576, 1, 128) == ("rna", "fp32", "rna") and lo.production_gemm_modes(16, 12, 128)[2] == "rna"
+    assert lo.production_gemm_modes(24576, 1, 128) == ("fp32", "fp32", "rna") and lo.production_gemm_modes(16, 12, 128)[2] == "rna"
     lo._CHAIN[0] = True
     assert lo.production_gemm_modes(4096, 3, 128) == ("trunc", "fp32", "rna")        # optional one-launch forward chains
     lo._CHAIN[0] = False
-    assert lo.production_gemm_modes(4096, 3, 128) == ("rna", "fp32", "rna")
+    assert lo.production_gemm_modes(4096, 3, 128) == ("fp32", "fp32", "rna") and lo.production_gemm_modes(24576, 6, 128)[0] == "rna"
     sd, sd_est, st = _sd("init/ac/"), _sd("init/est/"), _storage()
     b = lu.minibatch(st, torch.arange(T * N))
     outs = {}
