@@ -209,6 +209,8 @@ class Go2Env:
         if self._extras_done is not None:
             torch.cuda.current_stream().wait_event(self._extras_done)
             self._extras_done = None
+        if hasattr(self.physx, "finish"):          # HostPhysX: the last step's state push rides on a copy stream
+            self.physx.finish()
 
     @property
     def supports_output_binding(self):
@@ -343,7 +345,8 @@ class HostPhysX:
         densely and are copied -- except the dof_state of substeps 0..2, whose only reader is the next PD-torque kernel:
         that kernel streams the pinned frame in place (`zero_copy_dof`); rigid_body_states [N*19,13] is read at 4 floats
         per env (the feet heights), so the kernel reads it in place too (`zero_copy_rigid`) instead of copying 4 MB.
-    device -> host (pinned mirrors): the torques of EVERY substep (gym.set_dof_actuation_force_tensor, legged_robot.py:81-83),
+    device -> host (pinned mirrors): the torques of EVERY substep (gym.set_dof_actuation_force_tensor, legged_robot.py:81-83;
+        substeps 0..2 are written by the PD kernel straight into the mirror -- `zero_copy_torques` -- the last one is copied),
         and after the step the state the reference pushes back with set_dof_state_tensor_indexed /
         set_actor_root_state_tensor_indexed (legged_robot.py:504-506, :530-532, :539): root_states, dof_state and the reset
         flags that select the rows -- copied whole (a fixed-size, graph-capturable transfer; an upper bound of the rows the
@@ -351,7 +354,7 @@ class HostPhysX:
     `bytes_per_step` / `d2h_bytes_per_step` count what crosses the bus per env step.  Used by bench.py's end-to-end leg."""
 
     def __init__(self, num_envs, env_origins, device, ring=4, seed=1234, decimation=4, zero_copy_rigid=True, zero_copy_dof=True,
-                 read_back_results=True, **frame_kw):
+                 read_back_results=True, zero_copy_torques=True, **frame_kw):
         rng = np.random.default_rng(seed)
         origins = env_origins.detach().cpu().numpy() if isinstance(env_origins, torch.Tensor) else np.asarray(env_origins)
         self.frames = []
@@ -359,6 +362,8 @@ class HostPhysX:
             f = synth.make_frames(num_envs, origins, rng, decimation=decimation, **frame_kw)
             self.frames.append({k: torch.from_numpy(v).pin_memory() for k, v in f.items()})
         self.cursor, self.h2d_bytes, self.d2h_bytes = -1, 0, 0
+        self._pushed = None
+        self.zero_copy_torques = bool(zero_copy_torques)
         self.zero_copy_rigid = bool(zero_copy_rigid)
         self.zero_copy_dof, self.decimation = bool(zero_copy_dof), int(decimation)
         f0 = self.frames[0]
@@ -376,16 +381,35 @@ class HostPhysX:
 
     def begin_step(self, env):
         self.cursor = (self.cursor + 1) % len(self.frames)
+        self.finish()                  # the previous step's state push reads buffers this step's frames overwrite
+        if self.zero_copy_torques and self.decimation > 1:
+            env.bufs.rebind_host_mapped("torques", self.host_torques[0])
+
+    def finish(self):
+        """order the current stream after the last push_state() (issued on the copy-back stream)"""
+        if self._pushed is not None:
+            torch.cuda.current_stream().wait_event(self._pushed)
+            self._pushed = None
 
     def simulate(self, env, substep):
         """torques of this substep -> host; dof_state after substep k -> device.  Between substeps the only reader of
         dof_state is the next PD-torque kernel (legged_robot.py:81-85), which streams it once: that kernel reads the pinned
         frame in place (`zero_copy_dof`); the frame of the LAST substep is what post_physics_step and the env's `dof_state`
         attribute see, so it is copied."""
-        self.host_torques[substep].copy_(env.bufs["torques"], non_blocking=True)
+        last = substep == self.decimation - 1
+        if self.zero_copy_torques:
+            # substeps 0..D-2: the PD kernel has written its torques straight into the pinned mirror (posted writes over the
+            # bus, no copy launch); only the last substep's torques have a device-side reader (the reward terms) and are copied
+            if last:
+                self.host_torques[substep].copy_(env.bufs["torques"], non_blocking=True)
+            elif substep + 1 < self.decimation - 1:
+                env.bufs.rebind_host_mapped("torques", self.host_torques[substep + 1])
+            else:
+                env.bufs.unbind_host_mapped("torques")
+        else:
+            self.host_torques[substep].copy_(env.bufs["torques"], non_blocking=True)
         self.d2h_bytes += 4 * env.bufs["torques"].numel()
         src = self.frames[self.cursor]["dof"][substep]
-        last = substep == self.decimation - 1
         if self.zero_copy_dof and not last:
             env.bufs.rebind_host_mapped("dof_state", src)
         else:
@@ -421,10 +445,21 @@ class HostPhysX:
         """the reset / pushed rows go back to the host simulator (whole tensors + the flags that select the rows), and the
         step's rewards / dones to the host caller"""
         b = env.bufs
-        self.host_root.copy_(b["root_states"], non_blocking=True)
-        self.host_dof.copy_(b["dof_state"], non_blocking=True)
-        self.host_reset.copy_(b["reset_buf"], non_blocking=True)
-        if self.read_back_results:
-            self.host_rew.copy_(b["rew_buf"], non_blocking=True)
-            self.host_done.copy_(b["reset_buf"], non_blocking=True)
+        # The host simulator needs these before its NEXT simulate(), i.e. after the next policy inference: the copies go out
+        # on their own stream behind the step's kernels and are joined at the next begin_step() (finish()), so the policy
+        # inference of the next step overlaps them instead of queueing behind five bus transfers.
+        if not hasattr(self, "_back_stream"):
+            self._back_stream = torch.cuda.Stream(device=env.device)
+        fork = torch.cuda.Event()
+        fork.record()
+        self._back_stream.wait_event(fork)
+        with torch.cuda.stream(self._back_stream):
+            self.host_root.copy_(b["root_states"], non_blocking=True)
+            self.host_dof.copy_(b["dof_state"], non_blocking=True)
+            self.host_reset.copy_(b["reset_buf"], non_blocking=True)
+            if self.read_back_results:
+                self.host_rew.copy_(b["rew_buf"], non_blocking=True)
+                self.host_done.copy_(b["reset_buf"], non_blocking=True)
+            self._pushed = torch.cuda.Event()
+            self._pushed.record()
         self.d2h_bytes += self.d2h_bytes_per_step - 4 * self.host_torques.numel()

@@ -276,8 +276,9 @@ def test_every_reward_term_active_matches_oracle():
 
 
 def test_host_physx_zero_copy_matches_copy():
-    """HostPhysX (bench.py's end-to-end arm): reading rigid_body_states in place from pinned host memory gives
-    bit-identical steps to copying the whole tensor to the device first."""
+    """HostPhysX (bench.py's end-to-end arm): reading rigid_body_states / dof_state in place from pinned host memory and writing
+    the torques of substeps 0..2 straight into the pinned mirror give bit-identical steps -- and identical host-side mirrors --
+    to copying whole tensors both ways."""
     from legged_gym_custom_b200.env import Go2Env, HostPhysX
 
     class Cfg(configs.Go2ParkourCfg):
@@ -287,12 +288,16 @@ def test_host_physx_zero_copy_matches_copy():
     for zero_copy in (True, False):
         env = Go2Env(Cfg, sim_device=DEV, seed=3)
         env.physx = HostPhysX(512, env.bufs["env_origins"], torch.device(DEV), seed=3, decimation=env.params.decimation,
-                              zero_copy_rigid=zero_copy, zero_copy_dof=zero_copy)
+                              zero_copy_rigid=zero_copy, zero_copy_dof=zero_copy, zero_copy_torques=zero_copy)
         env.reset()
         g = torch.Generator(device=DEV).manual_seed(0)
         for _ in range(5):
             out = env.step(torch.randn(512, NUM_DOF, device=DEV, generator=g))
+        env.wait_extras()                          # joins the copy-back stream of the last step's state push
         torch.cuda.synchronize()
-        outs.append([t.clone() for t in out[:7]] + [env.bufs["last_contact_heights"].clone()])
+        px = env.physx
+        assert float(px.host_torques.abs().max()) > 0.0 and torch.equal(px.host_torques[-1], env.bufs["torques"].cpu())
+        outs.append([t.clone() for t in out[:7]] + [env.bufs["last_contact_heights"].clone()] +
+                    [px.host_torques.clone(), px.host_root.clone(), px.host_dof.clone(), px.host_reset.clone(), px.host_rew.clone()])
     for a, b in zip(*outs):
-        assert torch.equal(a, b)
+        assert torch.equal(a, b)        # incl. what went back to the host: the torques of all 4 substeps, pushed state, rewards
