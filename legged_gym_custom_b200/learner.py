@@ -516,9 +516,16 @@ class PPO:
             est.fwd(ws, X, ld, _p(pred), 4, M)
             _lib.check(self.lib.b200_mse_rows_loss(_p(pred), 4, tgt_est, ldte, _p(dpred), 4, _p(self.loss_sums, 4), M, est.output_dim,
                                                    _lib.stream_ptr()))
+        # Data parallel with schedule='adaptive': the KL all-reduce (NCCL, on the critical stream) and the estimator's fused
+        # optimiser step are both kernels that WAIT for the peer ranks.  On unordered graph branches nothing stops two ranks
+        # from starting them in opposite order, each then needing the other kernel co-resident to make progress; the
+        # estimator's step is therefore issued behind the all-reduce, which gives the blocking collectives one total order on
+        # every rank (KL all-reduce -> estimator step -> main step) whatever the GPU can co-schedule.
+        est_step_after_kl = self.adaptive and self.process_group is not None
         with self._capped(s_est):
             chain_backward(est.k, est.layers, ws, "e", X + 4 * est.in_col, ld, _p(dpred), 4, M)
-            self._adam(est.group)
+            if not est_step_after_kl:
+                self._adam(est.group)
         with self._capped(s_crit, forward=True):
             ac.fwd_critic(ws, crit, s.d_crit, _p(val), 4, M)
         with self._on(s_hi):
@@ -526,6 +533,10 @@ class PPO:
             ac.fwd_actor(ws, X, ld, _p(mu), A, M)
             if self.adaptive:
                 self._adaptive_lr(mu, r0, M)
+            if est_step_after_kl:
+                self._fork_onto([s_est])
+                with self._capped(s_est):
+                    self._adam(est.group)
             self._join([s_crit])
             # PPO loss head (ppo.py:249-270)
             a = _lib.PpoLossArgs()

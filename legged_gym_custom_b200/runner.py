@@ -94,6 +94,17 @@ class OnPolicyRunner:
         self.alg.use_graphs = bool(enabled)
         self._rollout_graphs, self._rollout_calls = {}, {}
 
+    def release_graphs(self):
+        """destroy every captured graph (rollout and minibatch slots).  Call before torch.distributed.destroy_process_group():
+        graphs that captured NCCL work (schedule='adaptive' under data parallelism) keep the communicator busy and the
+        teardown would wait for them forever."""
+        torch.cuda.synchronize()
+        self._rollout_graphs, self._rollout_calls = {}, {}
+        self.alg._graphs, self.alg._graph_calls = {}, {}
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def capture_graphs(self):
         """Capture EVERY graph a training run replays -- both rollout graphs (adaptation_mode False / True) and every
         ("ppo", i) / ("dagger", i) minibatch graph -- now, instead of lazily on the second use of each (the adaptation-mode

@@ -102,3 +102,65 @@ def test_fused_dist_adam_two_gpus(multicast):
     mp.spawn(_worker, args=(2, _free_port(), 1 << 18, 4, multicast, out), nprocs=2, join=True)
     assert len(out) == 2 and all(v.startswith("ok") for v in out.values()), dict(out)
     print(dict(out))
+
+
+def _runner_worker(rank, world, port, schedule, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from legged_gym_custom_b200 import configs
+    from legged_gym_custom_b200.env import Go2Env
+    from legged_gym_custom_b200.runner import OnPolicyRunner, class_to_dict
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", device_id=dev)
+    try:
+        env_cfg, train_cfg = configs.TASKS["go2_parkour"]
+
+        class Cfg(env_cfg):
+            class env(env_cfg.env):
+                num_envs = 256
+        env = Go2Env(Cfg, sim_device=str(dev), seed=1234 + rank)          # every rank simulates its own shard of the envs
+        tc = class_to_dict(train_cfg)
+        tc["runner"]["resume"] = False
+        tc["algorithm"]["schedule"] = schedule
+        runner = OnPolicyRunner(env, tc, log_dir=None, device=dev, process_group=dist.group.WORLD)
+        runner.enable_graphs()
+        runner.capture_graphs()
+        for it in range(3):                                               # DAgger iteration, then two PPO iterations (graph replays)
+            runner.iteration(it)
+        torch.cuda.synchronize()
+        ac, est = runner.alg.actor_critic, runner.alg.estimator
+        flat = torch.cat([ac.main.params, ac.adapt.params, est.group.params,
+                          ac.main.state[:5].float(), est.group.state[:5].float(), ac.adapt.state[:5].float()])
+        assert torch.isfinite(flat).all()
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        assert all(torch.equal(b, both[0]) for b in both), "replicas diverged"
+        # the shards are different data: the rollouts must NOT be identical
+        obs = runner.alg.storage.observations[0, :8].clone()
+        obs_all = [torch.empty_like(obs) for _ in range(world)]
+        dist.all_gather(obs_all, obs)
+        assert not torch.equal(obs_all[0], obs_all[1])
+        out[rank] = (runner.alg.dist_mode, float(ac.main.state[4].item()), int(ac.main.state[1].item()))
+        runner.release_graphs()                 # graphs with captured NCCL work must go before the communicator does
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("schedule", ["fixed", "adaptive"])
+def test_two_gpu_runner_keeps_replicas_bit_identical(schedule):
+    """the whole learning iteration on 2 ranks (envs sharded, captured graphs, fused optimiser step; with schedule='adaptive'
+    the NCCL all-reduce of the KL sums inside every minibatch graph): parameters, Adam step counts and learning rates stay
+    bit-identical across the ranks while their rollouts differ"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_runner_worker, args=(2, _free_port(), schedule, out), nprocs=2, join=True)
+    assert len(out) == 2 and out[0] == out[1], dict(out)
+    mode, lr, steps = out[0]
+    assert steps == 2 * 20                                   # two PPO updates of 5 epochs x 4 minibatches
+    if schedule == "adaptive":
+        assert lr != 2e-4                                    # the KL rule moved the learning rate (and identically on both ranks)
+    print(dict(out))

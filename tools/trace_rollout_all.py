@@ -14,6 +14,9 @@ from legged_gym_custom_b200.runner import OnPolicyRunner, class_to_dict  # noqa:
 DEV = torch.device("cuda:0")
 env_cfg, train_cfg = configs.TASKS["go2_parkour"]
 env = Go2Env(env_cfg, sim_device="cuda:0", seed=1234)
+if os.environ.get("B200_HOST_PHYSX") == "1":       # the end-to-end arm of bench.py: PhysX frames in pinned host memory
+    from legged_gym_custom_b200.env import HostPhysX
+    env.physx = HostPhysX(env.num_envs, env.bufs["env_origins"], DEV, seed=1234, decimation=env.params.decimation)
 tc = class_to_dict(train_cfg)
 tc["runner"]["resume"] = False
 runner = OnPolicyRunner(env, tc, log_dir=None, device=DEV)
@@ -26,7 +29,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     runner.rollout(False)
     torch.cuda.synchronize()
 runner.alg.storage.clear()
-evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "Event" not in e.name]
 evs.sort(key=lambda e: e.time_range.start)
 t0 = evs[0].time_range.start
 posts = [i for i, e in enumerate(evs) if "post_physics" in e.name]
