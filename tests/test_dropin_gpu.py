@@ -74,7 +74,9 @@ def test_reference_runner_drives_go2env_and_kernel_ppo():
     ck = torch.load(os.path.join(log_dir, "model_2.pt"), map_location="cpu")
     assert set(ck) == {"model_state_dict", "optimizer_state_dict", "iter", "infos"} and "actor.0.weight" in ck["model_state_dict"]
 
-    # --- our runner from the same seeds: same kernels, same numbers (fp32 atomics of the split-K wgrads reorder sums)
+    # --- our runner from the same seeds: same kernels, same numbers up to the run-to-run spread of the fp32 atomics (split-K
+    # wgrads, bias / loss sums): two identical runs of EITHER runner differ by 2e-5 .. 3.8e-4 in actor.0.weight after these 60
+    # optimiser steps (tools/scratch/dbg_repeat.py, B200) -- Adam turns a sign flip of a tiny gradient into a +-lr step
     env2, _ = _env(N)
     ours = OurRunner(env2, tc, log_dir=None, device=DEV)
     for it in range(2):
@@ -83,7 +85,8 @@ def test_reference_runner_drives_go2env_and_kernel_ppo():
     a, b = runner.alg.actor_critic.state_dict(), ours.alg.actor_critic.state_dict()
     moved = 0.0
     for k in a:
-        assert torch.allclose(a[k], b[k], rtol=0, atol=2.5e-4), (k, float((a[k] - b[k]).abs().max()))      # <= lr x steps
+        assert torch.allclose(a[k], b[k], rtol=0, atol=1.5e-3), (k, float((a[k] - b[k]).abs().max()))     # spread above x 4
+        assert float((a[k] - b[k]).pow(2).mean().sqrt()) <= 2e-4, k              # per-tensor rms (measured spread: up to 4.3e-5)
         moved = max(moved, float((a[k] - ours.alg.actor_critic._random_state_dict(1.0, 0)[k].to(a[k].device)).abs().max()))
     assert moved > 1e-4                                        # the weights did train
     assert torch.equal(env.obs_buf, env2.obs_buf) or float((env.obs_buf - env2.obs_buf).abs().max()) < 10.0
