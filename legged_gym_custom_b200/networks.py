@@ -189,6 +189,8 @@ def chain_forward(k, layers, ws, tag, X, ldx, out, ldo, M, max_ctas=74, after=No
             arr[i].N, arr[i].K, arr[i].act = lin.N, lin.K, lin.act
         sync = ws.ptr(f"chain_sync_{tag}", 1, 4)
         _lib.check(k.lib.b200_tc_mlp_forward(arr, len(layers), X, ldx, M, sync, int(max_ctas), _lib.stream_ptr()))
+        if after is not None:                          # one launch: the hook can only run behind the whole chain
+            after[1]()
         return
     for i, lin in enumerate(layers):
         last = i == len(layers) - 1
