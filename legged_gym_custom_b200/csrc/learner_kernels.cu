@@ -260,103 +260,6 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const __grid_con
   if (threadIdx.x < p.A) atomicAdd(p.dstd + threadIdx.x, dstd_s[threadIdx.x]);
 }
 
-// The same loss head with one WARP per sample (A <= 16 actions and L <= 32 latent values: lane a owns action a, lane l owns
-// latent l): every row access is coalesced and a minibatch of 24 576 samples fills the SMs (the thread-per-sample kernel above
-// runs 5 warps per SM through ~60 dependent loads).  The per-sample sums (log-prob over the actions, squared latent distance)
-// are accumulated in the serial kernel's order through shuffles, so per-sample results are the same bits; the sums over the
-// samples end in the same fp32 atomics as before.
-constexpr int kLossWarpSamples = 4;            // consecutive samples per warp
-__global__ void __launch_bounds__(256) ppo_loss_warp_kernel(const __grid_constant__ PpoLossArgs p) {
-  __shared__ float red[4 * 8];
-  __shared__ float dstd_s[kMaxA];
-  __shared__ float c_s[kMaxA], c_inv2s2[kMaxA], c_logs[kMaxA], c_invs2[kMaxA], c_invs3[kMaxA];
-  if (threadIdx.x < kMaxA) {
-    dstd_s[threadIdx.x] = 0.0f;
-    if (threadIdx.x < p.A) {
-      const float s = p.std[threadIdx.x];
-      c_s[threadIdx.x] = s;
-      c_inv2s2[threadIdx.x] = 1.0f / (2.0f * s * s);
-      c_logs[threadIdx.x] = logf(s);
-      c_invs2[threadIdx.x] = 1.0f / (s * s);
-      c_invs3[threadIdx.x] = 1.0f / (s * s * s);
-    }
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float invM = 1.0f / (float)p.M;
-  const float reg_coef = p.reg_coef_dev ? p.reg_coef_dev[0] : p.reg_coef;
-  const float dsig_entropy = -p.entropy_coef * invM;
-  float ent = 0.0f;
-  for (int a = 0; a < p.A; ++a) ent += 1.4189385332046727f + c_logs[a];
-  float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};      // lane 0 accumulates the warp's samples
-  float dsig = 0.0f;                              // lane a: d(loss)/d(std[a]) over the warp's samples
-  const int i0 = (blockIdx.x * 8 + warp) * kLossWarpSamples;
-  for (int k = 0; k < kLossWarpSamples; ++k) {
-    const int i = i0 + k;
-    if (i >= p.M) break;                          // warp-uniform
-    float d = 0.0f, term = 0.0f;
-    if (lane < p.A) {
-      d = p.actions[(int64_t)i * p.A + lane] - p.mu[(int64_t)i * p.ldmu + lane];
-      term = -(d * d) * c_inv2s2[lane] - c_logs[lane] - 0.9189385332046727f;
-    }
-    float e = 0.0f;
-    if (lane < p.L) e = p.latent_p[(int64_t)i * p.ldlp + lane] - p.latent_a[(int64_t)i * p.ldla + lane];
-    float lp = 0.0f, n2 = 0.0f;
-    for (int a = 0; a < p.A; ++a) lp += __shfl_sync(0xffffffffu, term, a);
-    for (int l = 0; l < p.L; ++l) {               // n2 += e * e, contracted to one FMA as in the serial kernel
-      const float el = __shfl_sync(0xffffffffu, e, l);
-      n2 = fmaf(el, el, n2);
-    }
-    const float adv = p.adv[i];
-    const float ratio = expf(lp - p.old_logp[i]);
-    const float s1 = -adv * ratio;
-    const float rc = fminf(fmaxf(ratio, 1.0f - p.clip), 1.0f + p.clip);
-    const float s2 = -adv * rc;
-    const bool inside = (ratio >= 1.0f - p.clip) && (ratio <= 1.0f + p.clip);
-    const float dlp = (inside || s1 > s2) ? (-adv * ratio) * invM : 0.0f;
-    if (lane < p.A) {
-      p.dmu[(int64_t)i * p.lddmu + lane] = dlp * d * c_invs2[lane];
-      dsig += dlp * (d * d - c_s[lane] * c_s[lane]) * c_invs3[lane] + dsig_entropy / c_s[lane];
-    }
-    const float nrm = sqrtf(n2);
-    const float g = nrm > 0.0f ? reg_coef * invM / nrm : 0.0f;
-    if (lane < p.L) p.dlatent_p[(int64_t)i * p.lddlp + lane] = g * e;
-    if (lane == 0) {
-      // value loss (ppo.py:256-264)
-      const float v = p.value[(int64_t)i * p.ldv], R = p.returns[i];
-      float dv, vl;
-      if (p.use_clipped_value_loss) {
-        const float tv = p.target_values[i];
-        const float dvt = v - tv;
-        const float vc = tv + fminf(fmaxf(dvt, -p.clip), p.clip);
-        const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
-        vl = fmaxf(l1, l2);
-        const bool in_v = (dvt >= -p.clip) && (dvt <= p.clip);
-        const float d1 = 2.0f * (v - R), d2 = in_v ? 2.0f * (vc - R) : 0.0f;
-        dv = l1 > l2 ? d1 : (l1 < l2 ? d2 : 0.5f * (d1 + d2));
-      } else {
-        vl = (R - v) * (R - v);
-        dv = 2.0f * (v - R);
-      }
-      p.dvalue[(int64_t)i * p.lddv] = p.value_coef * dv * invM;
-      part[0] += fmaxf(s1, s2);
-      part[1] += vl;
-      part[2] += nrm;
-      part[3] += ent;
-    }
-  }
-  if (lane < p.A) atomicAdd(&dstd_s[lane], dsig);
-  if (lane == 0)
-    for (int k = 0; k < 4; ++k) red[k * 8 + warp] = part[k];
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    float t = 0.0f;
-    for (int w = 0; w < 8; ++w) t += red[threadIdx.x * 8 + w];
-    atomicAdd(p.sums + threadIdx.x, t);
-  }
-  if (threadIdx.x < p.A) atomicAdd(p.dstd + threadIdx.x, dstd_s[threadIdx.x]);
-}
-
 // loss = mean_i ||pred_i - target_i||_2^2 ; dpred = 2 (pred - target) / M      (estimator, ppo.py:224-226)
 __global__ void __launch_bounds__(256)
 mse_rows_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ target, int ldt, float* __restrict__ dpred,
@@ -753,12 +656,6 @@ int b200_ppo_loss(const PpoLossArgs* a, void* stream) {
   B200_CHECK_ARG(a->mu && a->std && a->actions && a->old_logp && a->adv && a->returns && a->target_values && a->value && a->latent_p &&
                      a->latent_a && a->dmu && a->dvalue && a->dlatent_p && a->dstd && a->sums,
                  "b200_ppo_loss: null pointer");
-  if (a->L <= 32) {                              // one warp per sample (every shipped configuration: A = 12, L = 20)
-    const int per_block = 8 * kLossWarpSamples;
-    ppo_loss_warp_kernel<<<(a->M + per_block - 1) / per_block, 256, 0, (cudaStream_t)stream>>>(*a);
-    B200_CHECK_LAUNCH("ppo_loss_warp_kernel");
-    return 0;
-  }
   ppo_loss_kernel<<<(a->M + kLossThreads - 1) / kLossThreads, kLossThreads, 0, (cudaStream_t)stream>>>(*a);
   B200_CHECK_LAUNCH("ppo_loss_kernel");
   return 0;
