@@ -216,8 +216,10 @@ class PPO:
         # SMs the low-priority side chains of a minibatch (estimator, critic) may occupy; 0 = all.  Their big GEMMs are
         # one-wave persistent kernels that hold every SM until they end, which starves the small kernels of the critical
         # path whatever the stream priorities are (b200_tc_set_stream_sm_cap, registered per side stream).  Measured on B200 (148 SMs), update of 20 minibatches:
-        # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt)
-        self.side_sm_cap = 116
+        # no cap 14.13-14.15 ms; 132: 13.94; 124: 13.89; 116: 13.76; 108: 13.89; 100: 13.89 (profiles/r3_side_sm_cap_ab.txt).
+        # Re-measured with round 2's kernels (whole iteration, ms): no cap 16.08; 132: 15.89; 116: 15.76-15.77; 104: 15.72;
+        # 96: 15.67-15.74; 80: 15.83
+        self.side_sm_cap = 96
         # weight-gradient GEMMs of the actor / encoder chains on a fifth (low-priority, capped) stream: the dgrad chain that
         # the encoders' backward waits for no longer queues behind them
         self.offload_wgrads = False
