@@ -166,8 +166,19 @@ __global__ void __launch_bounds__(kThreads) dist_adam_kernel(const __grid_consta
     }
   }
   wait_flags(mine + W, W, epoch);
+  // the flags were acquired (and the block synchronised) in wait_flags: the partials behind them are visible, so the W loads
+  // go out together as relaxed loads instead of W dependent acquire round trips; summed in rank order: identical everywhere
+  double partial[kMaxWorld];
+#pragma unroll
+  for (int p = 0; p < kMaxWorld; ++p) {
+    unsigned long long bits = 0ull;
+    if (p < W) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(mine + 3 * W + p) : "memory");
+    partial[p] = __longlong_as_double((long long)bits);
+  }
   double total_sq = 0.0;
-  for (int p = 0; p < W; ++p) total_sq += __longlong_as_double((long long)ld_acquire_sys(mine + 3 * W + p));      // rank order: identical everywhere
+#pragma unroll
+  for (int p = 0; p < kMaxWorld; ++p)
+    if (p < W) total_sq += partial[p];
 
   // ---- 3. clip coefficient (gradient = sum / W, b200_clip_adam's grad_scale) and Adam on the shard
   const float grad_scale = 1.0f / (float)W;
